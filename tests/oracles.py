@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE: ctypes loaders for the two parity oracles.
+
+* ``ref``  – oracle/_ref/libbcd_ref.so: the unmodified reference CPU path (superboubek/bcd src/core/*.cpp) compiled
+             in place by oracle/Makefile.  Travels to the GPU box as a prebuilt file; never reads /root/reference
+             at run time.
+* ``port`` – oracle/liboracle.so: plain-C restatement of the same algorithm (oracle/bcd_oracle.c) with stage-level
+             entry points (selection masks, marking, pyramid).
+
+Nothing under bcd_b200/ imports this module; the product path never routes through an oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbcd_ref.so")
+PORT_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def have_port():
+    return os.path.exists(PORT_SO)
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        lib.bcdref_max_threads.restype = C.c_int
+        lib.bcdref_denoise.restype = C.c_int
+        lib.bcdref_denoise.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int,
+                                       C.c_float, C.c_int, C.c_int, C.c_float,
+                                       C.c_int, C.c_float, C.c_int, C.c_int, _fp, C.c_int]
+        lib.bcdref_accumulate.restype = C.c_int
+        lib.bcdref_accumulate.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                          _fp, _fp, _fp, _fp]
+        lib.bcdref_spike_removal.restype = C.c_int
+        lib.bcdref_spike_removal.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float]
+        _ref = lib
+    return _ref
+
+
+def ref_denoise(color, nsamples, hist, cov, tau=1.0, w=1, b=6, eps=1e-8, random_order=False, m=1.0,
+                cores=1, scales=1, quiet=True):
+    """Reference Denoiser / MultiscaleDenoiser on host arrays (H,W,C) float32 -> (H,W,3)."""
+    H, W, _ = color.shape
+    B = hist.shape[2]
+    out = np.zeros((H, W, 3), np.float32)
+    rc = ref_lib().bcdref_denoise(np.ascontiguousarray(color, np.float32), np.ascontiguousarray(nsamples, np.float32),
+                                  np.ascontiguousarray(hist, np.float32), np.ascontiguousarray(cov, np.float32),
+                                  W, H, B, tau, w, b, eps, int(random_order), float(m), cores, scales, out,
+                                  int(quiet))
+    if rc != 0:
+        raise RuntimeError("reference denoise() returned false")
+    return out
+
+
+def ref_accumulate(samples, nb_bins=20, gamma=2.2, max_value=2.5):
+    """samples: (H,W,spp,3) float32 -> dict(color,nsamples,hist,cov) via the reference SamplesAccumulator."""
+    H, W, spp, _ = samples.shape
+    color = np.zeros((H, W, 3), np.float32)
+    ns = np.zeros((H, W, 1), np.float32)
+    hist = np.zeros((H, W, 3 * nb_bins), np.float32)
+    cov = np.zeros((H, W, 6), np.float32)
+    ref_lib().bcdref_accumulate(np.ascontiguousarray(samples, np.float32), W, H, spp, nb_bins, gamma, max_value,
+                                color, ns, hist, cov)
+    return dict(color=color, nsamples=ns, hist=hist, cov=cov)
+
+
+def load_test_raw(path):
+    """data/raw/test.raw layout (src/raw_converter/main.cpp:65-72,159-171): 5 x int32 header
+    {version, W, H, spp, channels} then float RGB samples, pixel-major."""
+    with open(path, "rb") as f:
+        hdr = np.frombuffer(f.read(20), np.int32)
+        _, W, H, spp, ch = [int(v) for v in hdr]
+        data = np.frombuffer(f.read(4 * W * H * spp * ch), np.float32)  # (the file carries 4 trailing bytes)
+    return data.reshape(H, W, spp, ch)
+
+
+def rel_linf(a, ref):
+    """max|a-ref| / max|ref| over all pixels x channels. NaNs must coincide."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    nan_a, nan_r = np.isnan(a), np.isnan(ref)
+    if (nan_a != nan_r).any():
+        return float("inf")
+    ok = ~nan_r
+    if not ok.any():
+        return 0.0
+    return float(np.abs(a[ok] - ref[ok]).max() / max(np.abs(ref[ok]).max(), 1e-30))
