@@ -97,3 +97,93 @@ def rel_linf(a, ref):
     if not ok.any():
         return 0.0
     return float(np.abs(a[ok] - ref[ok]).max() / max(np.abs(ref[ok]).max(), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ port (C restatement)
+class _Params(C.Structure):
+    _fields_ = [("tau", C.c_float), ("w", C.c_int), ("b", C.c_int), ("eps", C.c_float), ("marking", C.c_int)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [(k, C.c_longlong) for k in ("interior", "active", "full", "fallback", "strong", "sum_n_full")]
+
+
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_port = None
+
+
+def port_lib():
+    global _port
+    if _port is None:
+        lib = C.CDLL(PORT_SO)
+        lib.bcdo_mask_words.restype = C.c_int
+        lib.bcdo_mask_words.argtypes = [C.c_int]
+        lib.bcdo_pixel_cov.argtypes = [_fp, _fp, C.c_longlong, _fp]
+        lib.bcdo_select_all.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _u32p, _i32p]
+        lib.bcdo_marking.argtypes = [_u32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.bcdo_eigh.restype = C.c_int
+        lib.bcdo_eigh.argtypes = [_fp, C.c_int, _fp, _fp, _fp]
+        lib.bcdo_denoise.restype = C.c_int
+        lib.bcdo_denoise.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(_Params), _fp,
+                                     C.POINTER(_Stats), C.c_void_p, C.c_void_p]
+        lib.bcdo_denoise_multiscale.restype = C.c_int
+        lib.bcdo_denoise_multiscale.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.POINTER(_Params),
+                                                C.c_int, _fp]
+        lib.bcdo_downscale_sum.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp]
+        lib.bcdo_downscale_avg.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp]
+        lib.bcdo_downscale_cov.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp]
+        lib.bcdo_interpolate.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int]
+        lib.bcdo_merge.argtypes = [_fp, C.c_int, C.c_int, _fp]
+        _port = lib
+    return _port
+
+
+def _c(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def port_select(hist, nsamples, w=1, b=6, tau=1.0):
+    """-> masks (H,W,words) uint32 in window row-major bit order, counts (H,W) int32."""
+    H, W, B = hist.shape
+    words = port_lib().bcdo_mask_words(b)
+    masks = np.zeros((H, W, words), np.uint32)
+    counts = np.zeros((H, W), np.int32)
+    port_lib().bcdo_select_all(_c(hist), _c(nsamples), W, H, B, w, b, tau, masks, counts)
+    return masks, counts
+
+
+def port_marking(masks, counts, w=1, b=6):
+    H, W = counts.shape
+    active = np.zeros((H, W), np.uint8)
+    port_lib().bcdo_marking(np.ascontiguousarray(masks), np.ascontiguousarray(counts), W, H, w, b, active)
+    return active
+
+
+def port_eigh(A):
+    n = A.shape[0]
+    ev = np.zeros(n, np.float32)
+    V = np.zeros((n, n), np.float32)  # column-major storage: V.T[r, c]... returned transposed below
+    work = np.zeros(n * n + 4 * n, np.float32)
+    rc = port_lib().bcdo_eigh(_c(A.T), n, ev, V, work)  # column-major == transpose of row-major
+    return rc, ev, V.T.copy()
+
+
+def port_denoise(color, nsamples, hist, cov, tau=1.0, w=1, b=6, eps=1e-8, m=1.0, scales=1, want_stats=False):
+    H, W, _ = color.shape
+    B = hist.shape[2]
+    out = np.zeros((H, W, 3), np.float32)
+    p = _Params(tau, w, b, eps, 1 if m == 1.0 else 0)
+    st = _Stats()
+    if scales > 1:
+        rc = port_lib().bcdo_denoise_multiscale(_c(color), _c(nsamples), _c(hist), _c(cov), W, H, B, C.byref(p),
+                                                scales, out)
+    else:
+        rc = port_lib().bcdo_denoise(_c(color), _c(nsamples), _c(hist), _c(cov), W, H, B, C.byref(p), out,
+                                     C.byref(st), None, None)
+    if rc != 0:
+        raise RuntimeError("port denoise failed")
+    if want_stats:
+        return out, {k: getattr(st, k) for k, _ in _Stats._fields_}
+    return out
