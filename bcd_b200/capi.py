@@ -1,0 +1,204 @@
+"""ctypes binding of the C ABI declared in include/bcd_b200.h (libbcd_b200.so: sm_100a kernels + host engine).
+
+This is the only way Python reaches the kernels; there is no Python or CPU fallback. Importing works anywhere (so the
+CPU test-suite can check that the library loads and exports every declared symbol); creating a handle without a CUDA
+device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbcd_b200.so")
+
+STAGE_NAMES = ["prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
+               "finalize", "pyramid"]
+
+# every symbol include/bcd_b200.h declares (tests/test_capi_symbols.py cross-checks this list against the header)
+SYMBOLS = [
+    "bcd_b200_default_params", "bcd_b200_last_error", "bcd_b200_abi_version", "bcd_b200_device_count",
+    "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_upload",
+    "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
+    "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
+]
+
+
+class Images(C.Structure):
+    _fields_ = [("color", C.c_void_p), ("nsamples", C.c_void_p), ("hist", C.c_void_p), ("cov", C.c_void_p),
+                ("width", C.c_int32), ("height", C.c_int32), ("hist_depth", C.c_int32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("tau", C.c_float), ("patch_radius", C.c_int32), ("search_radius", C.c_int32), ("min_eig", C.c_float),
+                ("random_order", C.c_int32), ("skip_prob", C.c_float), ("nb_scales", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full",
+                                         "kernel_launches")]
+
+
+class Timings(C.Structure):
+    _fields_ = [("stage_ms", C.c_float * len(STAGE_NAMES)), ("total_ms", C.c_float)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_float, C.c_void_p)
+
+
+class BcdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bcd_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libbcd_b200.so (built in-tree by `make` / __graft_entry__.build()). Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `make` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.bcd_b200_last_error.restype = C.c_char_p
+        L.bcd_b200_default_params.argtypes = [C.POINTER(Params)]
+        L.bcd_b200_default_params.restype = None
+        L.bcd_b200_denoise.argtypes = [C.POINTER(Images), C.POINTER(Params), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.bcd_b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.bcd_b200_destroy.argtypes = [C.c_void_p]
+        L.bcd_b200_destroy.restype = None
+        L.bcd_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_upload.argtypes = [C.c_void_p, C.POINTER(Images)]
+        L.bcd_b200_bind_device.argtypes = [C.c_void_p, C.POINTER(Images)]
+        L.bcd_b200_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
+        L.bcd_b200_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_result_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.bcd_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.bcd_b200_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+        L.bcd_b200_mask_words.argtypes = [C.c_int]
+        L.bcd_b200_debug_read_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bcd_b200_debug_read_active.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise BcdError(rc, lib().bcd_b200_last_error().decode("utf-8", "replace"))
+
+
+def make_params(tau=1.0, w=1, b=6, eps=1e-8, random_order=False, m=1.0, scales=1):
+    return Params(float(tau), int(w), int(b), float(eps), int(bool(random_order)), float(m), int(scales), 0)
+
+
+def _host_images(color, nsamples, hist, cov):
+    color = np.ascontiguousarray(color, np.float32)
+    H, W = color.shape[0], color.shape[1]
+    nsamples = np.ascontiguousarray(nsamples, np.float32).reshape(H, W)
+    hist = np.ascontiguousarray(hist, np.float32)
+    cov = np.ascontiguousarray(cov, np.float32)
+    if color.shape != (H, W, 3) or hist.shape[:2] != (H, W) or cov.shape != (H, W, 6):
+        raise ValueError("expected color (H,W,3), nsamples (H,W[,1]), hist (H,W,B), cov (H,W,6)")
+    keep = (color, nsamples, hist, cov)
+    img = Images(color.ctypes.data, nsamples.ctypes.data, hist.ctypes.data, cov.ctypes.data, W, H, hist.shape[2])
+    return img, keep
+
+
+def denoise(color, nsamples, hist, cov, params=None, device=0, **kw):
+    """One-shot host-in / host-out call: bcd_b200_denoise (what bcd::Denoiser::denoise() forwards to)."""
+    p = params if params is not None else make_params(**kw)
+    img, keep = _host_images(color, nsamples, hist, cov)
+    out = np.empty((img.height, img.width, 3), np.float32)
+    _check(lib().bcd_b200_denoise(C.byref(img), C.byref(p), out.ctypes.data, device, None, None))
+    return out
+
+
+class Handle:
+    """Persistent device buffers + stream (bcd_b200_create ... bcd_b200_destroy)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().bcd_b200_create(C.byref(self._h), device))
+        self.device = device
+        self.shape = None
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().bcd_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().bcd_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def upload(self, color, nsamples, hist, cov):
+        img, keep = _host_images(color, nsamples, hist, cov)
+        _check(lib().bcd_b200_upload(self._h, C.byref(img)))
+        self.shape = (img.height, img.width, img.hist_depth)
+
+    def upload_ptrs(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B):
+        """Host pointers (e.g. pinned torch tensors' data_ptr())."""
+        img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B)
+        _check(lib().bcd_b200_upload(self._h, C.byref(img)))
+        self.shape = (H, W, B)
+
+    def bind_device(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B):
+        """Borrow DEVICE pointers (e.g. torch CUDA tensors' data_ptr()) as the level-0 inputs."""
+        img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B)
+        _check(lib().bcd_b200_bind_device(self._h, C.byref(img)))
+        self.shape = (H, W, B)
+
+    def run(self, params=None, progress=None, **kw):
+        p = params if params is not None else make_params(**kw)
+        cb = PROGRESS_FN(lambda v, _u: progress(v)) if progress else None
+        _check(lib().bcd_b200_run(self._h, C.byref(p), cb, None))
+        self._last_b = p.search_radius
+
+    def download(self, out=None):
+        H, W, _ = self.shape
+        if out is None:
+            out = np.empty((H, W, 3), np.float32)
+        _check(lib().bcd_b200_download(self._h, out.ctypes.data))
+        return out
+
+    def download_ptr(self, host_ptr):
+        _check(lib().bcd_b200_download(self._h, C.c_void_p(host_ptr)))
+
+    def result_device_ptr(self):
+        p = C.c_void_p()
+        _check(lib().bcd_b200_result_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def stats(self):
+        s = Stats()
+        _check(lib().bcd_b200_get_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def timings(self):
+        t = Timings()
+        _check(lib().bcd_b200_get_timings(self._h, C.byref(t)))
+        d = {n: float(t.stage_ms[i]) for i, n in enumerate(STAGE_NAMES)}
+        d["total"] = float(t.total_ms)
+        return d
+
+    def read_selection(self):
+        H, W, _ = self.shape
+        words = lib().bcd_b200_mask_words(self._last_b)
+        masks = np.zeros((H, W, words), np.uint32)
+        counts = np.zeros((H, W), np.int32)
+        _check(lib().bcd_b200_debug_read_selection(self._h, masks.ctypes.data, counts.ctypes.data))
+        return masks, counts
+
+    def read_active(self):
+        H, W, _ = self.shape
+        active = np.zeros((H, W), np.uint8)
+        _check(lib().bcd_b200_debug_read_active(self._h, active.ctypes.data))
+        return active

@@ -1,0 +1,596 @@
+// C ABI (include/bcd_b200.h) and the host-side engine that sequences the kernels of the hot path.
+//
+// Replaces the drivers of the reference (paths relative to /root/reference):
+//   Denoiser::denoise            src/core/Denoiser.cpp:84-212        -> Engine::denoiseLevel
+//   MultiscaleDenoiser::denoise  src/core/MultiscaleDenoiser.cpp:31-136 -> Engine::run
+// Everything data-parallel happens in the kernels (k_*.cu); this file only owns device buffers, streams, events,
+// error reporting and the order of launches. There is no CPU fallback: without a CUDA device every entry point fails.
+
+#include "../../include/bcd_b200.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bcdk;
+
+namespace
+{
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...)
+{
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_lastError = buf;
+	return code;
+}
+
+#define CU(call) \
+	do { \
+		cudaError_t e_ = (call); \
+		if(e_ != cudaSuccess) \
+			return fail(BCD_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while(0)
+
+// grow-only device buffer
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t bytes)
+	{
+		if(bytes <= cap)
+			return cudaSuccess;
+		if(p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		cudaError_t e = cudaMalloc(&p, bytes);
+		if(e == cudaSuccess) cap = bytes;
+		return e;
+	}
+	void release()
+	{
+		if(p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LevelBufs
+{
+	int W = 0, H = 0;
+	const float *color = nullptr, *ns = nullptr, *hist = nullptr, *cov = nullptr; // inputs of this level
+	DevBuf ownColor, ownNs, ownHist, ownCov;                                         // storage when owned
+	DevBuf out;                                                                      // W*H*3
+};
+
+} // namespace
+
+struct bcd_b200_handle
+{
+	int device = 0;
+	cudaStream_t ownStream = nullptr, stream = nullptr;
+	int W = 0, H = 0, B = 0;
+	bool haveInputs = false;
+	std::vector<LevelBufs> levels; // [0] = full resolution
+	// scratch shared by all levels (sized for level 0)
+	DevBuf sP, cP, mplus, smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr, tmpLow;
+	DevBuf fA, fMinv, fMean, fNoise, fX;
+	int filterChunk = 0;
+	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
+	bool ran = false;
+	bcd_b200_stats stats;
+	bcd_b200_timings timings;
+	std::vector<cudaEvent_t> events; // pairs (begin, end) per timed stage instance
+	std::vector<int> eventStage;
+	cudaEvent_t fev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t evTotal[2] = {nullptr, nullptr};
+	size_t eventsUsed = 0;
+	int launches = 0;
+	DeviceCounters* hostCtr = nullptr; // pinned
+};
+
+namespace
+{
+
+int stageBegin(bcd_b200_handle* h, int stage)
+{
+	if(h->eventsUsed + 2 > h->events.size())
+	{
+		for(int i = 0; i < 2; ++i)
+		{
+			cudaEvent_t e;
+			CU(cudaEventCreate(&e));
+			h->events.push_back(e);
+		}
+		h->eventStage.push_back(stage);
+	}
+	h->eventStage[h->eventsUsed / 2] = stage;
+	CU(cudaEventRecord(h->events[h->eventsUsed], h->stream));
+	return 0;
+}
+
+int stageEnd(bcd_b200_handle* h)
+{
+	CU(cudaEventRecord(h->events[h->eventsUsed + 1], h->stream));
+	h->eventsUsed += 2;
+	return 0;
+}
+
+#define STAGE(h, stage, ...) \
+	do { \
+		int rc_ = stageBegin(h, stage); \
+		if(rc_) return rc_; \
+		__VA_ARGS__; \
+		rc_ = stageEnd(h); \
+		if(rc_) return rc_; \
+	} while(0)
+
+int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	LevelGeom g = makeGeom(L.W, L.H, h->B, p.patch_radius, p.search_radius);
+	if(k == 0)
+		h->g0 = g;
+	cudaStream_t st = h->stream;
+	const size_t npix = (size_t)g.W * g.H;
+	const int Wp = markingRowWords(g.W);
+
+	STAGE(h, BCD_B200_STAGE_PREPASS, {
+		CU(launchPixelCov(L.cov, L.ns, npix, h->pixcov.as<float>(), st, &h->launches));
+		CU(cudaMemsetAsync(h->acc.p, 0, npix * sizeof(float4), st));
+		CU(cudaMemsetAsync(h->active.p, 0, npix, st));
+		CU(cudaMemsetAsync(h->ctr.p, 0, sizeof(DeviceCounters), st));
+	});
+	STAGE(h, BCD_B200_STAGE_PAIR, {
+		CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+	});
+	STAGE(h, BCD_B200_STAGE_SELECT, {
+		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
+		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, h->smask.as<uint32_t>(), h->counts.as<int>(),
+				h->pre.as<uint32_t>(), st, &h->launches));
+	});
+	STAGE(h, BCD_B200_STAGE_MARKING, {
+		if(p.skip_prob > 0.f)
+		{
+			CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
+			CU(launchMarking(h->pre.as<uint32_t>(), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<unsigned char>(),
+					h->asBits.as<uint32_t>(), Wp, h->progress.as<unsigned int>(), st, &h->launches));
+		}
+		else
+			CU(launchAllActive(g, h->active.as<unsigned char>(), st, &h->launches));
+		CU(launchBuildLists(h->counts.as<int>(), h->active.as<unsigned char>(), g, h->fullList.as<int>(),
+				h->fallbackList.as<int>(), h->ctr.as<DeviceCounters>(), st, &h->launches));
+		CU(cudaMemcpyAsync(h->hostCtr, h->ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+	});
+	CU(cudaStreamSynchronize(st));
+	const DeviceCounters c = *h->hostCtr;
+	h->stats.interior += (int64_t)c.interior;
+	h->stats.strong += (int64_t)c.strong;
+	h->stats.active += (int64_t)c.active;
+	h->stats.full += (int64_t)c.full;
+	h->stats.fallback += (int64_t)c.fallback;
+	h->stats.sum_n_full += (int64_t)c.sum_n_full;
+
+	STAGE(h, BCD_B200_STAGE_FALLBACK, {
+		if(c.nFallback > 0)
+			CU(launchFallback(L.color, h->smask.as<uint32_t>(), h->counts.as<int>(), g, h->fallbackList.as<int>(),
+					&h->ctr.as<DeviceCounters>()->nFallback, h->acc.as<float4>(), st, &h->launches));
+	});
+	if(c.nFull > 0)
+	{
+		FilterBuffers fb;
+		fb.A = h->fA.as<float>();
+		fb.Minv = h->fMinv.as<float>();
+		fb.mean = h->fMean.as<float>();
+		fb.noise = h->fNoise.as<float>();
+		fb.xScratch = h->fX.as<float>();
+		fb.gridCap = 148 * 2;
+		float ms[3] = {0.f, 0.f, 0.f};
+		for(int first = 0; first < c.nFull; first += h->filterChunk)
+		{
+			const int count = std::min(h->filterChunk, c.nFull - first);
+			cudaError_t e = launchFilterChunk(L.color, h->pixcov.as<float>(), h->smask.as<uint32_t>(), h->counts.as<int>(), g,
+					p.min_eig, h->fullList.as<int>(), first, count, fb, h->acc.as<float4>(), st, &h->launches, ms, h->fev);
+			if(e != cudaSuccess)
+				return fail(e == cudaErrorInvalidConfiguration ? BCD_B200_ERR_UNSUPPORTED : BCD_B200_ERR_CUDA,
+						"filter chunk failed: %s", cudaGetErrorString(e));
+		}
+		h->timings.stage_ms[BCD_B200_STAGE_FILTER_STATS] += ms[0];
+		h->timings.stage_ms[BCD_B200_STAGE_FILTER_EIG] += ms[1];
+		h->timings.stage_ms[BCD_B200_STAGE_FILTER_APPLY] += ms[2];
+	}
+	STAGE(h, BCD_B200_STAGE_FINALIZE, {
+		CU(launchFinalize(h->acc.as<float4>(), npix, L.out.as<float>(), st, &h->launches));
+	});
+	return 0;
+}
+
+int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
+{
+	const int nl = p.nb_scales;
+	if((int)h->levels.size() < nl)
+		h->levels.resize(nl);
+	int W = h->W, H = h->H;
+	for(int k = 0; k < nl; ++k)
+	{
+		LevelBufs& L = h->levels[k];
+		L.W = W;
+		L.H = H;
+		const size_t np = (size_t)W * H;
+		CU(L.out.reserve(std::max<size_t>(np * 3 * sizeof(float), 16)));
+		if(k > 0)
+		{
+			CU(L.ownColor.reserve(std::max<size_t>(np * 3 * sizeof(float), 16)));
+			CU(L.ownNs.reserve(std::max<size_t>(np * sizeof(float), 16)));
+			CU(L.ownHist.reserve(std::max<size_t>(np * h->B * sizeof(float), 16)));
+			CU(L.ownCov.reserve(std::max<size_t>(np * 6 * sizeof(float), 16)));
+			L.color = L.ownColor.as<float>();
+			L.ns = L.ownNs.as<float>();
+			L.hist = L.ownHist.as<float>();
+			L.cov = L.ownCov.as<float>();
+		}
+		W /= 2;
+		H /= 2;
+	}
+	const LevelGeom g = makeGeom(h->W, h->H, h->B, p.patch_radius, p.search_radius);
+	const size_t npix = (size_t)g.W * g.H;
+	CU(h->sP.reserve(npix * g.J * sizeof(float)));
+	CU(h->cP.reserve(npix * g.J));
+	CU(h->mplus.reserve(npix * g.Jw * 4));
+	CU(h->smask.reserve(npix * g.Nw * 4));
+	CU(h->pre.reserve(npix * g.Pw * 4));
+	CU(h->counts.reserve(npix * 4));
+	CU(h->active.reserve(npix));
+	CU(h->asBits.reserve((size_t)g.H * markingRowWords(g.W) * 4));
+	CU(h->progress.reserve((size_t)(divUp(g.H, 32) + 2) * 4));
+	CU(h->fullList.reserve(npix * 4));
+	CU(h->fallbackList.reserve(npix * 4));
+	CU(h->acc.reserve(npix * sizeof(float4)));
+	CU(h->pixcov.reserve(npix * 6 * sizeof(float)));
+	CU(h->ctr.reserve(sizeof(DeviceCounters)));
+	CU(h->tmpLow.reserve(std::max<size_t>((size_t)(g.W / 2) * (g.H / 2) * 3 * sizeof(float), 16)));
+	// filter chunk: bounded scratch (two d x d matrices per slot)
+	const size_t perSlot = (size_t)2 * g.d * g.d * 4;
+	size_t chunk = (size_t)(768u << 20) / perSlot;
+	chunk = std::max<size_t>(1024, std::min<size_t>(chunk, 1u << 18));
+	chunk = std::min<size_t>(chunk, std::max<size_t>(npix, 1));
+	h->filterChunk = (int)chunk;
+	CU(h->fA.reserve(chunk * g.d * g.d * 4));
+	CU(h->fMinv.reserve(chunk * g.d * g.d * 4));
+	CU(h->fMean.reserve(chunk * g.d * 4));
+	CU(h->fNoise.reserve(chunk * g.np * 6 * 4));
+	// global X scratch only when n_max x d does not fit shared memory next to the d x d inverse
+	const size_t xBytes = (size_t)g.Ns * g.d * 4;
+	if(xBytes + (size_t)g.d * g.d * 4 + 8 * 1024 > 190 * 1024)
+		CU(h->fX.reserve(xBytes * 148 * 2));
+	if(!h->hostCtr)
+		CU(cudaMallocHost(&h->hostCtr, sizeof(DeviceCounters)));
+	for(int i = 0; i < 6; ++i)
+		if(!h->fev[i]) CU(cudaEventCreate(&h->fev[i]));
+	for(int i = 0; i < 2; ++i)
+		if(!h->evTotal[i]) CU(cudaEventCreate(&h->evTotal[i]));
+	return 0;
+}
+
+int checkParams(const bcd_b200_params* p)
+{
+	if(!p)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null parameters");
+	if(p->patch_radius < 0 || p->search_radius < 1 || p->nb_scales < 1 || p->nb_scales > 16)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad radii / number of scales (w=%d b=%d s=%d)", p->patch_radius,
+				p->search_radius, p->nb_scales);
+	if(p->search_radius > 15)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "search radius %d > 15 is not supported by the marking kernel", p->search_radius);
+	const int d = 3 * (2 * p->patch_radius + 1) * (2 * p->patch_radius + 1);
+	if(d > 160)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "patch radius %d (d=%d) exceeds the shared-memory eigen solver (d <= 160)",
+				p->patch_radius, d);
+	if(!(p->skip_prob >= 0.f && p->skip_prob <= 1.f))
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "skipping probability %g outside [0,1]", (double)p->skip_prob);
+	return 0;
+}
+
+int checkImages(const bcd_b200_images* in)
+{
+	// same conditions Denoiser::inputsOutputsAreOk rejects (reference Denoiser.cpp:269-346)
+	if(!in)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for inputs");
+	if(!in->color)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for input color image");
+	if(!in->nsamples)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for input number of samples image");
+	if(!in->hist)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for input histogram image");
+	if(!in->cov)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for input covariance image");
+	if(in->width <= 0 || in->height <= 0 || in->hist_depth <= 0)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: input image is empty (%dx%dx%d)", in->width,
+				in->height, in->hist_depth);
+	if(in->hist_depth > 255)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "histogram depth %d > 255 is not supported", in->hist_depth);
+	if((size_t)in->width * in->height > (size_t)1 << 30)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "image too large");
+	return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+const char* bcd_b200_last_error(void) { return g_lastError.c_str(); }
+int bcd_b200_abi_version(void) { return BCD_B200_ABI_VERSION; }
+
+int bcd_b200_device_count(void)
+{
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+void bcd_b200_default_params(bcd_b200_params* p)
+{
+	if(!p) return;
+	p->tau = 1.f;
+	p->patch_radius = 1;
+	p->search_radius = 6;
+	p->min_eig = 0.00000001f;
+	p->random_order = 1;
+	p->skip_prob = 1.f;
+	p->nb_scales = 1;
+	p->reserved = 0;
+}
+
+int bcd_b200_mask_words(int search_radius)
+{
+	const int ns = (2 * search_radius + 1) * (2 * search_radius + 1);
+	return (ns + 31) / 32;
+}
+
+int bcd_b200_create(bcd_b200_handle** out, int device)
+{
+	if(!out)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle pointer");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if(e != cudaSuccess || n == 0)
+	{
+		cudaGetLastError();
+		return fail(BCD_B200_ERR_NO_DEVICE, "no CUDA device available (%s); bcd_b200 has no CPU path",
+				e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+	}
+	if(device < 0) device = 0;
+	if(device >= n)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, n);
+	CU(cudaSetDevice(device));
+	bcd_b200_handle* h = new bcd_b200_handle();
+	h->device = device;
+	memset(&h->stats, 0, sizeof(h->stats));
+	memset(&h->timings, 0, sizeof(h->timings));
+	e = cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking);
+	if(e != cudaSuccess)
+	{
+		delete h;
+		return fail(BCD_B200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+	}
+	h->stream = h->ownStream;
+	*out = h;
+	return 0;
+}
+
+void bcd_b200_destroy(bcd_b200_handle* h)
+{
+	if(!h) return;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	for(auto& L : h->levels)
+	{
+		L.ownColor.release(); L.ownNs.release(); L.ownHist.release(); L.ownCov.release(); L.out.release();
+	}
+	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->smask, &h->counts, &h->pre, &h->active, &h->asBits, &h->progress,
+			&h->fullList, &h->fallbackList, &h->acc, &h->pixcov, &h->ctr, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX};
+	for(DevBuf* b : bufs) b->release();
+	for(cudaEvent_t e : h->events) cudaEventDestroy(e);
+	for(int i = 0; i < 6; ++i) if(h->fev[i]) cudaEventDestroy(h->fev[i]);
+	for(int i = 0; i < 2; ++i) if(h->evTotal[i]) cudaEventDestroy(h->evTotal[i]);
+	if(h->hostCtr) cudaFreeHost(h->hostCtr);
+	if(h->ownStream) cudaStreamDestroy(h->ownStream);
+	delete h;
+}
+
+int bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->ownStream;
+	return 0;
+}
+
+int bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	int rc = checkImages(in);
+	if(rc) return rc;
+	CU(cudaSetDevice(h->device));
+	if(h->levels.empty()) h->levels.resize(1);
+	LevelBufs& L = h->levels[0];
+	const size_t np = (size_t)in->width * in->height;
+	CU(L.ownColor.reserve(np * 3 * sizeof(float)));
+	CU(L.ownNs.reserve(np * sizeof(float)));
+	CU(L.ownHist.reserve(np * in->hist_depth * sizeof(float)));
+	CU(L.ownCov.reserve(np * 6 * sizeof(float)));
+	CU(cudaMemcpyAsync(L.ownColor.p, in->color, np * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(L.ownNs.p, in->nsamples, np * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(L.ownHist.p, in->hist, np * in->hist_depth * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaMemcpyAsync(L.ownCov.p, in->cov, np * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	L.color = L.ownColor.as<float>();
+	L.ns = L.ownNs.as<float>();
+	L.hist = L.ownHist.as<float>();
+	L.cov = L.ownCov.as<float>();
+	h->W = in->width; h->H = in->height; h->B = in->hist_depth;
+	h->haveInputs = true;
+	h->ran = false;
+	return 0;
+}
+
+int bcd_b200_bind_device(bcd_b200_handle* h, const bcd_b200_images* in)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	int rc = checkImages(in);
+	if(rc) return rc;
+	if(h->levels.empty()) h->levels.resize(1);
+	LevelBufs& L = h->levels[0];
+	L.color = in->color; L.ns = in->nsamples; L.hist = in->hist; L.cov = in->cov;
+	h->W = in->width; h->H = in->height; h->B = in->hist_depth;
+	h->haveInputs = true;
+	h->ran = false;
+	return 0;
+}
+
+int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress_fn progress, void* user)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "bcd_b200_run called before upload/bind_device");
+	int rc = checkParams(p);
+	if(rc) return rc;
+	CU(cudaSetDevice(h->device));
+	rc = ensureBuffers(h, *p);
+	if(rc) return rc;
+	memset(&h->stats, 0, sizeof(h->stats));
+	memset(&h->timings, 0, sizeof(h->timings));
+	h->eventsUsed = 0;
+	h->launches = 0;
+	cudaStream_t st = h->stream;
+	const int s = p->nb_scales;
+	CU(cudaEventRecord(h->evTotal[0], st));
+	if(progress) progress(0.f, user);
+	// pyramid build (MultiscaleDenoiser.cpp:41-48)
+	if(s > 1)
+		STAGE(h, BCD_B200_STAGE_PYRAMID, {
+			for(int k = 1; k < s; ++k)
+			{
+				const LevelBufs& Lp = h->levels[k - 1];
+				LevelBufs& L = h->levels[k];
+				CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
+						L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), st, &h->launches));
+			}
+		});
+	// coarsest to finest (MultiscaleDenoiser.cpp:79-134); progress mapped like :85,:103-112
+	const float total = float(((1 << (2 * s)) - 1) / 3);
+	for(int k = s - 1; k >= 0; --k)
+	{
+		rc = denoiseLevel(h, k, *p);
+		if(rc) return rc;
+		if(k < s - 1)
+			STAGE(h, BCD_B200_STAGE_PYRAMID, {
+				CU(launchMerge(h->levels[k].out.as<float>(), h->levels[k].W, h->levels[k].H, h->levels[k + 1].out.as<float>(),
+						h->tmpLow.as<float>(), st, &h->launches));
+			});
+		if(progress)
+		{
+			const int sdone = s - 1 - k;
+			progress(float(((1 << (2 * (sdone + 1))) - 1) / 3) / total, user);
+		}
+	}
+	CU(cudaEventRecord(h->evTotal[1], st));
+	CU(cudaStreamSynchronize(st));
+	for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
+	{
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]));
+		h->timings.stage_ms[h->eventStage[i / 2]] += ms;
+	}
+	CU(cudaEventElapsedTime(&h->timings.total_ms, h->evTotal[0], h->evTotal[1]));
+	h->stats.kernel_launches = h->launches;
+	h->ran = true;
+	return 0;
+}
+
+int bcd_b200_download(bcd_b200_handle* h, float* out_rgb)
+{
+	if(!h || !out_rgb) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	if(!h->ran) return fail(BCD_B200_ERR_STATE, "bcd_b200_download called before a successful run");
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemcpyAsync(out_rgb, h->levels[0].out.p, (size_t)h->W * h->H * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+int bcd_b200_result_device_ptr(bcd_b200_handle* h, const float** out_dev)
+{
+	if(!h || !out_dev) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	if(!h->ran) return fail(BCD_B200_ERR_STATE, "no result yet");
+	*out_dev = h->levels[0].out.as<float>();
+	return 0;
+}
+
+int bcd_b200_get_stats(bcd_b200_handle* h, bcd_b200_stats* s)
+{
+	if(!h || !s) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	*s = h->stats;
+	return 0;
+}
+
+int bcd_b200_get_timings(bcd_b200_handle* h, bcd_b200_timings* t)
+{
+	if(!h || !t) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	*t = h->timings;
+	return 0;
+}
+
+int bcd_b200_debug_read_selection(bcd_b200_handle* h, uint32_t* masks, int32_t* counts)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(!h->ran) return fail(BCD_B200_ERR_STATE, "no run yet");
+	CU(cudaSetDevice(h->device));
+	const size_t npix = (size_t)h->g0.W * h->g0.H;
+	if(masks) CU(cudaMemcpy(masks, h->smask.p, npix * h->g0.Nw * 4, cudaMemcpyDeviceToHost));
+	if(counts) CU(cudaMemcpy(counts, h->counts.p, npix * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active)
+{
+	if(!h || !active) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	if(!h->ran) return fail(BCD_B200_ERR_STATE, "no run yet");
+	CU(cudaSetDevice(h->device));
+	CU(cudaMemcpy(active, h->active.p, (size_t)h->g0.W * h->g0.H, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int bcd_b200_denoise(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, int device,
+		bcd_b200_progress_fn progress, void* user)
+{
+	if(!out_rgb)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for output image");
+	int rc = checkImages(in);
+	if(rc) return rc;
+	rc = checkParams(p);
+	if(rc) return rc;
+	bcd_b200_handle* h = nullptr;
+	rc = bcd_b200_create(&h, device);
+	if(rc) return rc;
+	rc = bcd_b200_upload(h, in);
+	if(!rc) rc = bcd_b200_run(h, p, progress, user);
+	if(!rc) rc = bcd_b200_download(h, out_rgb);
+	bcd_b200_destroy(h);
+	return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,58 @@
+// Shared device/host helpers for the bcd_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace bcdk
+{
+
+// Geometry of one pyramid level as seen by one GPU. (Single GPU: the whole image; row tiles: a horizontal band
+// plus its halos — the kernels only ever see a W x H image and a range of owned patch-centre rows.)
+struct LevelGeom
+{
+	int W, H;        // image size at this level
+	int B;           // histogram depth (3 * nbOfBins)
+	int w, b;        // patch radius, search radius
+	int side;        // 2b+1
+	int Ns;          // side*side   (search window size)
+	int centre;      // (Ns-1)/2    (window index of the centre)
+	int J;           // (Ns+1)/2    (number of offsets delta >= 0 in raster order, j=0 is the centre)
+	int Jw;          // ceil(J/32)  words of the half mask M+
+	int Nw;          // ceil(Ns/32) words of the full mask S
+	int Pw;          // ceil((centre+1)/32) words of the marking input (bits before the centre + strong flag)
+	int np;          // (2w+1)^2    pixels per patch
+	int d;           // 3*np        colour patch dimension
+	int rowBeg, rowEnd; // owned patch-centre rows [rowBeg, rowEnd) (subset of the interior rows)
+};
+
+inline LevelGeom makeGeom(int W, int H, int B, int w, int b)
+{
+	LevelGeom g;
+	g.W = W; g.H = H; g.B = B; g.w = w; g.b = b;
+	g.side = 2 * b + 1;
+	g.Ns = g.side * g.side;
+	g.centre = (g.Ns - 1) / 2;
+	g.J = (g.Ns + 1) / 2;
+	g.Jw = (g.J + 31) / 32;
+	g.Nw = (g.Ns + 31) / 32;
+	g.Pw = (g.centre + 1 + 31) / 32;
+	g.np = (2 * w + 1) * (2 * w + 1);
+	g.d = 3 * g.np;
+	g.rowBeg = w;
+	g.rowEnd = H - w;
+	return g;
+}
+
+// offset j (0..J-1) -> (dy, dx), raster order after the centre: dy in [0,b], dx in [-b,b]
+__host__ __device__ inline void offsetOf(int j, int b, int& dy, int& dx)
+{
+	const int side = 2 * b + 1;
+	const int idx = b * side + b + j;
+	dy = idx / side - b;
+	dx = idx % side - b;
+}
+
+__host__ __device__ inline int divUp(int a, int b) { return (a + b - 1) / b; }
+
+} // namespace bcdk

@@ -1,0 +1,821 @@
+// K3 — the collaborative filter applied to every active patch centre of a level.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   DenoisingUnit::denoiseOnlyMainPatch            src/core/DenoisingUnit.cpp:455-481   -> k_fallback
+//   DenoisingUnit::computeNoiseCovPatchesMean      :400-419                             -> k_filter_stats
+//   pickColorPatchesFromColorImage / empiricalMean / centerPointCloud / empiricalCovarianceMatrix :483-536
+//                                                                                       -> k_filter_stats, k_filter_apply<1>
+//   substract/addCovMatPatchToMatrix :538-576, clampNegativeEigenValues :606-630, inverseSymmetricMatrix :578-604
+//     with Eigen::SelfAdjointEigenSolver<MatrixXf>::compute (ext/eigen/Eigen/src/Eigenvalues/
+//     SelfAdjointEigenSolver.h:395-445,486-548,808-864; Tridiagonalization.h:346-378,427-441)
+//                                                                                       -> k_eig_chain
+//   finalDenoisingMatrixMultiplication :656-670, multiplyCovMatPatchByVector :633-654   -> k_filter_apply<1|2>
+//   denoiseSelectedPatchesStep1/Step2 :421-453, aggregateOutputPatches :672-693         -> the 5-kernel chain below
+//
+// Per "full" pixel (|S(p)| >= d+1) the chain is
+//   stats  : X (n x d gather), Sigma_n, mu, C = cov(X) - Sigma_n                       -> A, mean, noise   (global)
+//   eig    : Minv = inverse( clamp+(A) + Sigma_n )                 (two eigendecompositions, matrix stays in smem)
+//   apply 1: Y_i = X_i - Sigma_n Minv (X_i - mu);  mu2, A = cov(Y) + Sigma_n           -> A, mean
+//   eig    : Minv = inverse(A)
+//   apply 2: Z_i = X_i - Sigma_n Minv (X_i - mu2); sum[q_i + o] += Z_i, count += 1     (vector float4 atomics)
+// The d x d matrices (d = 3(2w+1)^2 = 27 / 75 / 147) live in shared memory; X lives in shared memory when it fits
+// and in a per-CTA global scratch slot otherwise. Sums over the similar patches run in the reference's order
+// (ascending window index) with separate multiply and add (this file is compiled with --fmad=false).
+
+#include "common.cuh"
+#include "kernels.h"
+#include <cfloat>
+
+namespace bcdk
+{
+
+enum { XX = 0, YY = 1, ZZ = 2, YZ = 3, XZ = 4, XY = 5 }; // reference CovarianceMatrix.h:18-27
+
+// element (a, b) of the symmetric 3x3 block stored as xx,yy,zz,yz,xz,xy
+__device__ __forceinline__ int symIndex(int a, int b)
+{
+	if(a == b) return a;            // xx, yy, zz
+	const int s = a + b;            // (1,2)->3 yz ; (0,2)->2 xz ; (0,1)->1 xy
+	return s == 3 ? YZ : (s == 2 ? XZ : XY);
+}
+
+template <int NT>
+__device__ __forceinline__ float blockReduceSum(float v, float* red)
+{
+	for(int o = 16; o > 0; o >>= 1)
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	if(NT == 32)
+		return v;
+	__syncthreads();
+	if((threadIdx.x & 31) == 0)
+		red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	float t = 0.f;
+	for(int i = 0; i < NT / 32; ++i)
+		t += red[i];
+	return t;
+}
+
+template <int NT>
+__device__ __forceinline__ float blockReduceMax(float v, float* red)
+{
+	for(int o = 16; o > 0; o >>= 1)
+		v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+	if(NT == 32)
+		return v;
+	__syncthreads();
+	if((threadIdx.x & 31) == 0)
+		red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	float t = red[0];
+	for(int i = 1; i < NT / 32; ++i)
+		t = fmaxf(t, red[i]);
+	return t;
+}
+
+// Expand the ordered similar set S(p) into the list of window indices (ascending = the order
+// selectSimilarPatches pushes the centres). words: smem [Nw], prefix: smem [Nw+1]. Returns n (uniform).
+template <int NT>
+__device__ int expandSimilarList(const uint32_t* __restrict__ smaskP, const LevelGeom& g, uint32_t* words, int* prefix,
+		unsigned short* qlist)
+{
+	const int tid = threadIdx.x;
+	__syncthreads();
+	for(int i = tid; i < g.Nw; i += NT)
+		words[i] = smaskP[i];
+	__syncthreads();
+	if(tid == 0)
+	{
+		int acc = 0;
+		for(int i = 0; i < g.Nw; ++i)
+		{
+			prefix[i] = acc;
+			acc += __popc(words[i]);
+		}
+		prefix[g.Nw] = acc;
+	}
+	__syncthreads();
+	for(int idx = tid; idx < g.Ns; idx += NT)
+	{
+		const uint32_t wv = words[idx >> 5];
+		const int bit = idx & 31;
+		if((wv >> bit) & 1u)
+			qlist[prefix[idx >> 5] + __popc(wv & ((1u << bit) - 1u))] = (unsigned short)idx;
+	}
+	__syncthreads();
+	return prefix[g.Nw];
+}
+
+// X[i][jj] = colour of patch pixel k = jj/3 (row-major) channel jj%3 of the i-th similar patch (:483-498)
+template <int NT>
+__device__ void gatherPatches(const float* __restrict__ color, const LevelGeom& g, int px, int py,
+		const unsigned short* qlist, int n, float* X)
+{
+	const int d = g.d, pw = 2 * g.w + 1;
+	for(int e = threadIdx.x; e < n * d; e += NT)
+	{
+		const int i = e / d, jj = e - i * d;
+		const int k = jj / 3, ch = jj - 3 * k;
+		const int idx = qlist[i];
+		const int qy = py + idx / g.side - g.b + k / pw - g.w;
+		const int qx = px + idx % g.side - g.b + k % pw - g.w;
+		X[e] = __ldg(color + ((size_t)qy * g.W + qx) * 3 + ch);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3f: fallback — mean of the similar colour patches added to the main patch only. One warp per pixel.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(128)
+k_fallback(const float* __restrict__ color, const uint32_t* __restrict__ smask, const int* __restrict__ counts,
+		LevelGeom g, const int* __restrict__ list, const int* __restrict__ nList, float4* __restrict__ acc)
+{
+	const int lane = threadIdx.x & 31;
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int nwarps = (gridDim.x * blockDim.x) >> 5;
+	const int total = *nList;
+	const int d = g.d, pw = 2 * g.w + 1;
+	for(int s = warp; s < total; s += nwarps)
+	{
+		const int p = list[s];
+		const int py = p / g.W, px = p - py * g.W;
+		float a[MAXT];
+		int off[MAXT]; // offset of (patch pixel, channel) relative to the patch centre in the colour image
+#pragma unroll
+		for(int t = 0; t < MAXT; ++t)
+		{
+			a[t] = 0.f;
+			const int jj = lane + 32 * t;
+			const int k = jj / 3, ch = jj - 3 * k;
+			off[t] = ((k / pw - g.w) * g.W + (k % pw - g.w)) * 3 + ch;
+		}
+		for(int wd = 0; wd < g.Nw; ++wd)
+		{
+			uint32_t bits = smask[(size_t)p * g.Nw + wd];
+			while(bits)
+			{
+				const int bit = __ffs(bits) - 1;
+				bits &= bits - 1;
+				const int idx = wd * 32 + bit;
+				const int qy = py + idx / g.side - g.b, qx = px + idx % g.side - g.b;
+				const float* base = color + ((size_t)qy * g.W + qx) * 3;
+#pragma unroll
+				for(int t = 0; t < MAXT; ++t)
+					if(lane + 32 * t < d)
+						a[t] = __fadd_rn(a[t], __ldg(base + off[t]));
+			}
+		}
+		const float invn = __fdiv_rn(1.f, (float)counts[p]); // n == 0 -> inf, inf * 0 = NaN like the reference
+#pragma unroll
+		for(int t = 0; t < MAXT; ++t)
+		{
+			const int jj = lane + 32 * t;
+			if(jj < d)
+			{
+				const int k = jj / 3, ch = jj - 3 * k;
+				const size_t x = (size_t)(py + k / pw - g.w) * g.W + (px + k % pw - g.w);
+				float* dst = reinterpret_cast<float*>(acc + x);
+				atomicAdd(dst + ch, __fmul_rn(invn, a[t]));
+				if(ch == 0)
+					atomicAdd(dst + 3, 1.f);
+			}
+		}
+	}
+}
+
+cudaError_t launchFallback(const float* color, const uint32_t* smask, const int* counts, const LevelGeom& g,
+		const int* fallbackList, const int* nFallback, float4* acc, cudaStream_t st, int* launches)
+{
+	const int blocks = 148 * 16;
+	*launches += 1;
+	if(g.d <= 32)
+		k_fallback<1><<<blocks, 128, 0, st>>>(color, smask, counts, g, fallbackList, nFallback, acc);
+	else if(g.d <= 96)
+		k_fallback<3><<<blocks, 128, 0, st>>>(color, smask, counts, g, fallbackList, nFallback, acc);
+	else if(g.d <= 160)
+		k_fallback<5><<<blocks, 128, 0, st>>>(color, smask, counts, g, fallbackList, nFallback, acc);
+	else
+		return cudaErrorInvalidValue;
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory carve-up common to the stats / apply kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct FilterSmem
+{
+	float* X;             // [nmax][d] (or global scratch)
+	float* mean;          // [d]
+	float* noise;         // [np*6]
+	float* Minv;          // [d*d]  (apply kernels)
+	float* vec;           // [NG][3][dpad] per-group vectors (apply kernels)
+	float* red;           // [32]
+	uint32_t* words;      // [Nw]
+	int* prefix;          // [Nw+1]
+	unsigned short* qlist; // [Ns]
+};
+
+static size_t filterSmemBytes(const LevelGeom& g, bool xInSmem, bool withMinv, int ng)
+{
+	size_t f = 0;
+	if(xInSmem) f += (size_t)g.Ns * g.d;
+	f += g.d + g.np * 6 + 32;
+	if(withMinv) f += (size_t)g.d * g.d + (size_t)ng * 3 * g.d;
+	size_t bytes = f * 4 + (size_t)g.Nw * 4 + (size_t)(g.Nw + 1) * 4 + (size_t)g.Ns * 2;
+	return (bytes + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ FilterSmem carveFilterSmem(unsigned char* raw, const LevelGeom& g, float* xGlobal,
+		bool withMinv, int ng)
+{
+	FilterSmem s;
+	float* f = reinterpret_cast<float*>(raw);
+	if(xGlobal) s.X = xGlobal; else { s.X = f; f += (size_t)g.Ns * g.d; }
+	s.mean = f; f += g.d;
+	s.noise = f; f += g.np * 6;
+	s.red = f; f += 32;
+	s.Minv = nullptr; s.vec = nullptr;
+	if(withMinv) { s.Minv = f; f += (size_t)g.d * g.d; s.vec = f; f += (size_t)ng * 3 * g.d; }
+	s.words = reinterpret_cast<uint32_t*>(f);
+	s.prefix = reinterpret_cast<int*>(s.words + g.Nw);
+	s.qlist = reinterpret_cast<unsigned short*>(s.prefix + g.Nw + 1);
+	return s;
+}
+
+// mean over i (sequential, :500-509), centring in place (:511-520) and the lower triangle of the empirical
+// covariance (:522-536; products summed in patch order, then scaled by 1/(n-1)). sgn*Sigma_n is added on the
+// 3x3 diagonal blocks (:538-576) and the symmetric result is written to Aout (column-major d x d).
+template <int NT>
+__device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, const float* noise, float sgn,
+		float* __restrict__ Aout, float* __restrict__ meanOut)
+{
+	const int d = g.d, tid = threadIdx.x;
+	const float invn = __fdiv_rn(1.f, (float)n);
+	for(int jj = tid; jj < d; jj += NT)
+	{
+		float a = 0.f;
+		for(int i = 0; i < n; ++i)
+			a = __fadd_rn(a, X[i * d + jj]);
+		a = __fmul_rn(a, invn);
+		mean[jj] = a;
+		meanOut[jj] = a;
+	}
+	__syncthreads();
+	for(int e = tid; e < n * d; e += NT)
+		X[e] = __fsub_rn(X[e], mean[e % d]);
+	__syncthreads();
+	const float invn1 = __fdiv_rn(1.f, (float)(n - 1));
+	const int L = d * (d + 1) / 2;
+	for(int e = tid; e < L; e += NT)
+	{
+		int c = 0, r = e;
+		while(r >= d - c) { r -= d - c; ++c; }
+		r += c; // r >= c
+		float a = 0.f;
+		for(int i = 0; i < n; ++i)
+			a = __fadd_rn(a, __fmul_rn(X[i * d + r], X[i * d + c]));
+		a = __fmul_rn(a, invn1);
+		if(r / 3 == c / 3)
+			a = __fadd_rn(a, __fmul_rn(sgn, noise[(r / 3) * 6 + symIndex(r % 3, c % 3)]));
+		Aout[r + (size_t)c * d] = a;
+		Aout[c + (size_t)r * d] = a;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3a: stats
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov, const uint32_t* __restrict__ smask,
+		LevelGeom g, const int* __restrict__ list, int first, int count,
+		float* __restrict__ A, float* __restrict__ meanG, float* __restrict__ noiseG, float* xScratch)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	const int d = g.d, np = g.np, pw = 2 * g.w + 1, tid = threadIdx.x;
+	FilterSmem s = carveFilterSmem(smemRaw, g, xScratch ? xScratch + (size_t)blockIdx.x * g.Ns * d : nullptr, false, 0);
+	for(int slot = blockIdx.x; slot < count; slot += gridDim.x)
+	{
+		const int p = list[first + slot];
+		const int py = p / g.W, px = p - py * g.W;
+		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, s.words, s.prefix, s.qlist);
+		gatherPatches<NT>(color, g, px, py, s.qlist, n, s.X);
+		// Sigma_n[k] = (1/n) sum_i pixelCov(q_i + o_k)   (:400-419)
+		const float invn = __fdiv_rn(1.f, (float)n);
+		for(int e = tid; e < np * 6; e += NT)
+		{
+			const int k = e / 6, el = e - 6 * k;
+			const int oy = k / pw - g.w, ox = k % pw - g.w;
+			float a = 0.f;
+			for(int i = 0; i < n; ++i)
+			{
+				const int idx = s.qlist[i];
+				const int qy = py + idx / g.side - g.b + oy, qx = px + idx % g.side - g.b + ox;
+				a = __fadd_rn(a, __ldg(pixcov + ((size_t)qy * g.W + qx) * 6 + el));
+			}
+			a = __fmul_rn(a, invn);
+			s.noise[e] = a;
+			noiseG[(size_t)slot * np * 6 + e] = a;
+		}
+		__syncthreads();
+		meanCenterCov<NT>(s.X, n, g, s.mean, s.noise, -1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3b / K3c: apply.  STEP 1: Y in place, then mu2 and A = cov(Y) + Sigma_n.  STEP 2: Z scattered to the accumulator.
+// Groups of GS threads handle one similar patch at a time: t = -(Minv (X_i - mean)); out = Sigma_n t + X_i.
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, int GS, int STEP>
+__global__ void __launch_bounds__(NT)
+k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ smask, LevelGeom g,
+		const int* __restrict__ list, int first, int count,
+		float* __restrict__ A, const float* __restrict__ MinvG, float* __restrict__ meanG,
+		const float* __restrict__ noiseG, float4* __restrict__ acc, float* xScratch)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	constexpr int NG = NT / GS;
+	const int d = g.d, np = g.np, pw = 2 * g.w + 1, tid = threadIdx.x;
+	const int gi = tid / GS, gl = tid - gi * GS;
+	FilterSmem s = carveFilterSmem(smemRaw, g, xScratch ? xScratch + (size_t)blockIdx.x * g.Ns * d : nullptr, true, NG);
+	float* xcv = s.vec + (size_t)gi * 3 * d;
+	float* tv = xcv + d;
+	float* zv = tv + d;
+	for(int slot = blockIdx.x; slot < count; slot += gridDim.x)
+	{
+		const int p = list[first + slot];
+		const int py = p / g.W, px = p - py * g.W;
+		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, s.words, s.prefix, s.qlist);
+		gatherPatches<NT>(color, g, px, py, s.qlist, n, s.X);
+		for(int e = tid; e < d * d; e += NT)
+			s.Minv[e] = MinvG[(size_t)slot * d * d + e];
+		for(int e = tid; e < d; e += NT)
+			s.mean[e] = meanG[(size_t)slot * d + e];
+		for(int e = tid; e < np * 6; e += NT)
+			s.noise[e] = noiseG[(size_t)slot * np * 6 + e];
+		__syncthreads();
+		for(int i0 = 0; i0 < n; i0 += NG)
+		{
+			const int i = i0 + gi;
+			const bool valid = i < n;
+			float* Xi = s.X + (size_t)(valid ? i : 0) * d;
+			for(int c = gl; c < d; c += GS)
+				xcv[c] = __fsub_rn(Xi[c], s.mean[c]);
+			__syncthreads();
+			for(int r = gl; r < d; r += GS)
+			{
+				float a = 0.f;
+				for(int c = 0; c < d; ++c)
+					a = __fadd_rn(a, __fmul_rn(s.Minv[r + c * d], xcv[c]));
+				tv[r] = __fmul_rn(a, -1.f);
+			}
+			__syncthreads();
+			for(int jj = gl; jj < d; jj += GS)
+			{
+				const int k = jj / 3, a3 = jj - 3 * k;
+				const float* cb = s.noise + 6 * k;
+				const float* t3 = tv + 3 * k;
+				// multiplyCovMatPatchByVector :633-654 (left-to-right sums), then += noisy patch (:668)
+				float o = __fadd_rn(__fadd_rn(__fmul_rn(cb[symIndex(a3, 0)], t3[0]), __fmul_rn(cb[symIndex(a3, 1)], t3[1])),
+						__fmul_rn(cb[symIndex(a3, 2)], t3[2]));
+				o = __fadd_rn(o, Xi[jj]);
+				if(STEP == 1)
+				{
+					if(valid) Xi[jj] = o;
+				}
+				else
+					zv[jj] = o;
+			}
+			if(STEP == 2)
+			{
+				__syncthreads();
+				if(valid)
+				{
+					const int idx = s.qlist[i];
+					const int qy = py + idx / g.side - g.b, qx = px + idx % g.side - g.b;
+					for(int k = gl; k < np; k += GS)
+					{
+						const size_t x = (size_t)(qy + k / pw - g.w) * g.W + (qx + k % pw - g.w);
+						atomicAdd(acc + x, make_float4(zv[3 * k], zv[3 * k + 1], zv[3 * k + 2], 1.f));
+					}
+				}
+			}
+			// the next iteration writes xcv before its first barrier; zv/tv are rewritten only after that barrier
+		}
+		__syncthreads();
+		if(STEP == 1)
+		{
+			meanCenterCov<NT>(s.X, n, g, s.mean, s.noise, 1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
+			__syncthreads();
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3e: symmetric eigen-function chain in shared memory, one matrix per CTA of NT >= d threads.
+//   doClamp: M <- V max(0,L) V^T + Sigma_n  (clampNegativeEigenValues + addCovMatPatchToMatrix), then
+//   always : out <- V diag(1/max(eps,L)) V^T (inverseSymmetricMatrix).
+// The decomposition follows Eigen's SelfAdjointEigenSolver::compute step for step (scaling by max|coeff| of the
+// lower triangle, Householder tridiagonalisation in place, Q accumulated from the reflectors, implicit symmetric QR
+// with Wilkinson shift and the same deflation test, at most 30 n sweeps). Eigenvalue sorting is skipped because
+// V f(L) V^T does not depend on the order.
+// ---------------------------------------------------------------------------------------------------------------
+#define MAT(r, c) M[(r) + (c) * n]
+
+__device__ __forceinline__ void makeGivens(float p, float q, float& c, float& s)
+{
+	if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; }
+	else if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; }
+	else if(fabsf(p) > fabsf(q))
+	{
+		const float t = __fdiv_rn(q, p);
+		float u = __fsqrt_rn(__fadd_rn(1.f, __fmul_rn(t, t)));
+		if(p < 0.f) u = -u;
+		c = __fdiv_rn(1.f, u);
+		s = __fmul_rn(-t, c);
+	}
+	else
+	{
+		const float t = __fdiv_rn(p, q);
+		float u = __fsqrt_rn(__fadd_rn(1.f, __fmul_rn(t, t)));
+		if(q < 0.f) u = -u;
+		s = __fdiv_rn(-1.f, u);
+		c = __fmul_rn(-t, s);
+	}
+}
+
+struct EigSmem
+{
+	float *M, *O, *diag, *sub, *dW, *sW, *hco, *pv, *red;
+};
+
+template <int NT>
+__device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
+{
+	float* M = S.M;
+	const int tid = threadIdx.x;
+	// ---- scale the lower triangle into [-1,1], clear the strict upper triangle
+	float lmax = 0.f;
+	for(int e = tid; e < n * n; e += NT)
+	{
+		const int r = e % n, c = e / n;
+		if(r < c) M[e] = 0.f;
+		else lmax = fmaxf(lmax, fabsf(M[e]));
+	}
+	float scale = blockReduceMax<NT>(lmax, S.red);
+	if(scale == 0.f) scale = 1.f;
+	for(int e = tid; e < n * n; e += NT)
+		if(e % n >= e / n) M[e] = __fdiv_rn(M[e], scale);
+	__syncthreads();
+
+	// ---- Householder tridiagonalisation (lower triangle), Tridiagonalization.h:346-378
+	for(int i = 0; i < n - 1; ++i)
+	{
+		const int rs = n - i - 1;
+		float* v = &MAT(i + 1, i);
+		float part = 0.f;
+		for(int k = 1 + tid; k < rs; k += NT)
+			part += v[k] * v[k];
+		const float tailSq = blockReduceSum<NT>(part, S.red);
+		const float c0 = v[0];
+		float beta, h;
+		if(tailSq <= FLT_MIN)
+		{
+			h = 0.f;
+			beta = c0;
+			for(int k = 1 + tid; k < rs; k += NT) v[k] = 0.f;
+		}
+		else
+		{
+			beta = __fsqrt_rn(c0 * c0 + tailSq);
+			if(c0 >= 0.f) beta = -beta;
+			const float den = c0 - beta;
+			for(int k = 1 + tid; k < rs; k += NT) v[k] = __fdiv_rn(v[k], den);
+			h = __fdiv_rn(beta - c0, beta);
+		}
+		__syncthreads();
+		// p = A_sym (h v), v[0] == 1 implicitly
+		for(int r = tid; r < rs; r += NT)
+		{
+			float a = 0.f;
+			for(int c = 0; c < rs; ++c)
+			{
+				const float m = r >= c ? MAT(i + 1 + r, i + 1 + c) : MAT(i + 1 + c, i + 1 + r);
+				a += m * (h * (c == 0 ? 1.f : v[c]));
+			}
+			S.pv[r] = a;
+		}
+		__syncthreads();
+		part = 0.f;
+		for(int k = tid; k < rs; k += NT)
+			part += S.pv[k] * (k == 0 ? 1.f : v[k]);
+		const float dot = blockReduceSum<NT>(part, S.red);
+		const float f = h * -0.5f * dot;
+		__syncthreads();
+		for(int k = tid; k < rs; k += NT)
+			S.pv[k] += f * (k == 0 ? 1.f : v[k]);
+		__syncthreads();
+		for(int c = tid; c < rs; c += NT)
+		{
+			const float pc = S.pv[c], vc = c == 0 ? 1.f : v[c];
+			for(int r = c; r < rs; ++r)
+				MAT(i + 1 + r, i + 1 + c) -= (r == 0 ? 1.f : v[r]) * pc + S.pv[r] * vc;
+		}
+		__syncthreads();
+		if(tid == 0)
+		{
+			v[0] = beta;
+			S.hco[i] = h;
+		}
+		__syncthreads();
+	}
+	for(int k = tid; k < n; k += NT)
+	{
+		S.diag[k] = MAT(k, k);
+		if(k < n - 1) S.sub[k] = MAT(k + 1, k);
+	}
+	__syncthreads();
+	// ---- Q = H_0 ... H_{n-2} evaluated in place (HouseholderSequence.h:242-267, Householder.h:110-130)
+	for(int k = tid; k < n; k += NT)
+		MAT(k, k) = 1.f;
+	__syncthreads();
+	for(int k = n - 2; k >= 0; --k)
+	{
+		const int cs = n - k - 1;
+		const float tau = S.hco[k];
+		if(cs == 1)
+		{
+			if(tid == 0) MAT(k + 1, k + 1) *= 1.f - tau;
+		}
+		else if(tau != 0.f)
+		{
+			const float* ess = &MAT(k + 2, k);
+			for(int c = tid; c < cs; c += NT)
+			{
+				float* col = &MAT(k + 1, k + 1 + c);
+				float a = 0.f;
+				for(int r = 1; r < cs; ++r)
+					a += ess[r - 1] * col[r];
+				const float tmp = a + col[0];
+				col[0] -= tau * tmp;
+				for(int r = 1; r < cs; ++r)
+					col[r] -= tau * ess[r - 1] * tmp;
+			}
+		}
+		__syncthreads();
+		for(int r = k + 1 + tid; r < n; r += NT)
+			MAT(r, k) = 0.f;
+		__syncthreads();
+	}
+	// ---- implicit symmetric QR on the tridiagonal (SelfAdjointEigenSolver.h:486-530, :808-864)
+	{
+		int end = n - 1, start = 0, iter = 0;
+		const float precision = 2.f * FLT_EPSILON;
+		while(end > 0)
+		{
+			for(int i = tid; i < end; i += NT)
+			{
+				const float a = fabsf(S.sub[i]);
+				if(a <= (fabsf(S.diag[i]) + fabsf(S.diag[i + 1])) * precision || a <= FLT_MIN)
+					S.sub[i] = 0.f;
+			}
+			__syncthreads();
+			while(end > 0 && S.sub[end - 1] == 0.f) end--;
+			if(end <= 0) break;
+			if(++iter > 30 * n) break;
+			start = end - 1;
+			while(start > 0 && S.sub[start - 1] != 0.f) start--;
+
+			// one QR step on [start, end]; every thread tracks the scalars, thread 0 records them in dW/sW,
+			// thread r rotates row r of Q (n <= NT)
+			const float td = (S.diag[end - 1] - S.diag[end]) * 0.5f;
+			const float e = S.sub[end - 1];
+			float mu = S.diag[end];
+			if(td == 0.f) mu -= fabsf(e);
+			else
+			{
+				const float e2 = e * e;
+				const float ax = fabsf(td), ay = fabsf(e);
+				const float pmax = fmaxf(ax, ay), qp = __fdiv_rn(fminf(ax, ay), pmax);
+				const float hh = pmax * __fsqrt_rn(1.f + qp * qp); // numext::hypot, MathFunctions.h:351-374
+				if(e2 == 0.f) mu -= __fdiv_rn(e, td + (td > 0.f ? 1.f : -1.f)) * __fdiv_rn(e, hh);
+				else mu -= __fdiv_rn(e2, td + (td > 0.f ? hh : -hh));
+			}
+			float x = S.diag[start] - mu;
+			float z = S.sub[start];
+			float dk = S.diag[start], sk = S.sub[start], skm1 = 0.f;
+			const bool hasRow = tid < n;
+			float qk = hasRow ? MAT(tid, start) : 0.f;
+			for(int k = start; k < end; ++k)
+			{
+				float c, s;
+				makeGivens(x, z, c, s);
+				const float dk1 = S.diag[k + 1];
+				const float sdk = s * dk + c * sk;
+				const float dkp1 = s * sk + c * dk1;
+				const float ndk = c * (c * dk - s * sk) - s * (c * sk - s * dk1);
+				const float ndk1 = s * sdk + c * dkp1;
+				const float nsk = c * sdk - s * dkp1;
+				if(tid == 0)
+				{
+					S.dW[k] = ndk;
+					if(k > start) S.sW[k - 1] = c * skm1 - s * z;
+				}
+				x = nsk;
+				float nsk1 = 0.f;
+				if(k < end - 1)
+				{
+					const float sk1 = S.sub[k + 1];
+					z = -s * sk1;
+					nsk1 = c * sk1;
+				}
+				if(hasRow)
+				{
+					const float y = MAT(tid, k + 1);
+					MAT(tid, k) = c * qk - s * y;
+					qk = s * qk + c * y;
+				}
+				dk = ndk1;
+				skm1 = nsk;
+				sk = nsk1;
+			}
+			if(hasRow) MAT(tid, end) = qk;
+			if(tid == 0)
+			{
+				S.dW[end] = dk;
+				S.sW[end - 1] = skm1;
+			}
+			__syncthreads();
+			for(int k = start + tid; k <= end; k += NT)
+			{
+				S.diag[k] = S.dW[k];
+				if(k < end) S.sub[k] = S.sW[k];
+			}
+			__syncthreads();
+		}
+	}
+	// ---- O = V f(L) V^T  (tmp(k,c) = f_k V(c,k); out(r,c) = sum_k V(r,k) tmp(k,c), :593-603 / :621-629)
+	for(int k = tid; k < n; k += NT)
+	{
+		const float l = S.diag[k] * scale;
+		S.pv[k] = mode == 0 ? fmaxf(0.f, l) : __fdiv_rn(1.f, fmaxf(eps, l));
+	}
+	__syncthreads();
+	const int L = n * (n + 1) / 2;
+	for(int e = tid; e < L; e += NT)
+	{
+		int c = 0, r = e;
+		while(r >= n - c) { r -= n - c; ++c; }
+		r += c;
+		float a = 0.f;
+		for(int k = 0; k < n; ++k)
+			a += MAT(r, k) * (S.pv[k] * MAT(c, k));
+		S.O[r + c * n] = a;
+		S.O[c + r * n] = a;
+	}
+	__syncthreads();
+}
+#undef MAT
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
+		int n, int np, float eps, int doClamp)
+{
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	float* f = reinterpret_cast<float*>(smemRaw);
+	EigSmem S;
+	S.M = f; f += n * n;
+	S.O = f; f += n * n;
+	S.diag = f; f += n;
+	S.sub = f; f += n;
+	S.dW = f; f += n;
+	S.sW = f; f += n;
+	S.hco = f; f += n;
+	S.pv = f; f += n;
+	S.red = f; f += 32;
+	float* noise = f;
+	const int tid = threadIdx.x;
+	for(int slot = blockIdx.x; slot < count; slot += gridDim.x)
+	{
+		__syncthreads();
+		for(int e = tid; e < n * n; e += NT)
+			S.M[e] = A[(size_t)slot * n * n + e];
+		for(int e = tid; e < np * 6; e += NT)
+			noise[e] = noiseG[(size_t)slot * np * 6 + e];
+		__syncthreads();
+		if(doClamp)
+		{
+			eigFunction<NT>(S, n, 0, 0.f);
+			// M <- O + Sigma_n on the 3x3 diagonal blocks (:538-556)
+			for(int e = tid; e < n * n; e += NT)
+			{
+				const int r = e % n, c = e / n;
+				float v = S.O[e];
+				if(r / 3 == c / 3)
+					v = __fadd_rn(v, noise[(r / 3) * 6 + symIndex(r % 3, c % 3)]);
+				S.M[e] = v;
+			}
+			__syncthreads();
+		}
+		eigFunction<NT>(S, n, 1, eps);
+		for(int e = tid; e < n * n; e += NT)
+			MinvG[(size_t)slot * n * n + e] = S.O[e];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launcher of the chain for one chunk of the full list
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT, int GS>
+static cudaError_t runFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const LevelGeom& g,
+		float minEig, const int* fullList, int first, int count, const FilterBuffers& fb, float4* acc,
+		cudaStream_t st, int* launches, float* stageMs, cudaEvent_t* ev, int eigNT)
+{
+	const size_t smemLimit = 200 * 1024;
+	bool xInSmem = filterSmemBytes(g, true, true, NT / GS) <= smemLimit;
+	if(!xInSmem && !fb.xScratch)
+		return cudaErrorInvalidConfiguration;
+	float* xs = xInSmem ? nullptr : fb.xScratch;
+	const int grid = xInSmem ? count : (count < fb.gridCap ? count : fb.gridCap);
+	const size_t smStats = filterSmemBytes(g, xInSmem, false, 0);
+	const size_t smApply = filterSmemBytes(g, xInSmem, true, NT / GS);
+	const size_t smEig = ((size_t)2 * g.d * g.d + 6 * g.d + 32 + g.np * 6) * 4;
+	cudaError_t err;
+	auto kStats = k_filter_stats<NT>;
+	auto kA1 = k_filter_apply<NT, GS, 1>;
+	auto kA2 = k_filter_apply<NT, GS, 2>;
+	if((err = cudaFuncSetAttribute(kStats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smStats)) != cudaSuccess) return err;
+	if((err = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
+	if((err = cudaFuncSetAttribute(kA2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
+
+	auto launchEig = [&](int doClamp) -> cudaError_t {
+		const int eg = count;
+		if(eigNT == 32)
+		{
+			cudaFuncSetAttribute(k_eig_chain<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			k_eig_chain<32><<<eg, 32, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+		}
+		else if(eigNT == 96)
+		{
+			cudaFuncSetAttribute(k_eig_chain<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			k_eig_chain<96><<<eg, 96, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+		}
+		else
+		{
+			cudaFuncSetAttribute(k_eig_chain<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			k_eig_chain<160><<<eg, 160, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+		}
+		return cudaGetLastError();
+	};
+
+	if(ev) cudaEventRecord(ev[0], st);
+	kStats<<<grid, NT, smStats, st>>>(color, pixcov, smask, g, fullList, first, count, fb.A, fb.mean, fb.noise, xs);
+	if((err = cudaGetLastError()) != cudaSuccess) return err;
+	if(ev) cudaEventRecord(ev[1], st);
+	if((err = launchEig(1)) != cudaSuccess) return err;
+	if(ev) cudaEventRecord(ev[2], st);
+	kA1<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
+	if((err = cudaGetLastError()) != cudaSuccess) return err;
+	if(ev) cudaEventRecord(ev[3], st);
+	if((err = launchEig(0)) != cudaSuccess) return err;
+	if(ev) cudaEventRecord(ev[4], st);
+	kA2<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
+	if((err = cudaGetLastError()) != cudaSuccess) return err;
+	if(ev) cudaEventRecord(ev[5], st);
+	*launches += 5;
+	if(ev && stageMs)
+	{
+		if((err = cudaEventSynchronize(ev[5])) != cudaSuccess) return err;
+		float t01, t12, t23, t34, t45;
+		cudaEventElapsedTime(&t01, ev[0], ev[1]);
+		cudaEventElapsedTime(&t12, ev[1], ev[2]);
+		cudaEventElapsedTime(&t23, ev[2], ev[3]);
+		cudaEventElapsedTime(&t34, ev[3], ev[4]);
+		cudaEventElapsedTime(&t45, ev[4], ev[5]);
+		stageMs[0] += t01;
+		stageMs[1] += t12 + t34;
+		stageMs[2] += t23 + t45;
+	}
+	return cudaSuccess;
+}
+
+cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const int* counts,
+		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const FilterBuffers& fb,
+		float4* acc, cudaStream_t st, int* launches, float* stageMs, cudaEvent_t* ev)
+{
+	(void)counts;
+	if(count <= 0)
+		return cudaSuccess;
+	if(g.d <= 32)
+		return runFilterChunk<128, 32>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
+	if(g.d <= 96)
+		return runFilterChunk<192, 96>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 96);
+	if(g.d <= 160)
+		return runFilterChunk<160, 160>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 160);
+	return cudaErrorInvalidValue;
+}
+
+} // namespace bcdk

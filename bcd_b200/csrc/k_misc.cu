@@ -1,0 +1,229 @@
+// Streaming (HBM-bound) stages of the hot path: prepass, work lists, final aggregation, pyramid build and merge.
+// Compiled with --fmad=false so that every expression rounds exactly like the reference's scalar C++.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   Denoiser::computePixelCovFromSampleCov       src/core/Denoiser.cpp:357-373            -> k_pixel_cov
+//   Denoiser::finalAggregation                   src/core/Denoiser.cpp:434-470            -> k_finalize
+//   MultiscaleDenoiser::downscaleSum/Average/SampleCovarianceSum  MultiscaleDenoiser.cpp:243-334 -> k_downscale_*
+//   MultiscaleDenoiser::mergeOutputs (downscale, interpolate, lowPass) MultiscaleDenoiser.cpp:453-548 -> k_merge
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bcdk
+{
+
+__global__ void k_pixel_cov(const float* __restrict__ cov, const float* __restrict__ ns, size_t npix,
+		float* __restrict__ pixcov)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= npix * 6)
+		return;
+	const size_t p = i / 6;
+	const float inv = __fdiv_rn(1.f, ns[p]);
+	pixcov[i] = __fmul_rn(cov[i], inv);
+}
+
+cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches)
+{
+	const size_t n = npix * 6;
+	k_pixel_cov<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cov, ns, npix, pixcov);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// m = 0: every interior pixel is processed (the mask is never consulted, DenoisingUnit.cpp:165-166)
+__global__ void k_all_active(LevelGeom g, unsigned char* __restrict__ active)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	if(x >= g.W || y >= g.H)
+		return;
+	const bool interior = x >= g.w && x <= g.W - 1 - g.w && y >= g.w && y <= g.H - 1 - g.w;
+	active[(size_t)y * g.W + x] = interior ? 1 : 0;
+}
+
+cudaError_t launchAllActive(const LevelGeom& g, unsigned char* active, cudaStream_t st, int* launches)
+{
+	dim3 block(32, 8), grid(divUp(g.W, 32), divUp(g.H, 8));
+	k_all_active<<<grid, block, 0, st>>>(g, active);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// Work lists of the owned patch centres: full (|S| >= d+1, DenoisingUnit.cpp:182) and fallback.
+__global__ void k_build_lists(const int* __restrict__ counts, const unsigned char* __restrict__ active, LevelGeom g,
+		int* __restrict__ fullList, int* __restrict__ fallbackList, DeviceCounters* __restrict__ ctr)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	const bool in = x < g.W && y < g.H;
+	const bool interior = in && x >= g.w && x <= g.W - 1 - g.w && y >= g.rowBeg && y < g.rowEnd;
+	const size_t p = in ? (size_t)y * g.W + x : 0;
+	const int n = interior ? counts[p] : 0;
+	const bool strong = interior && n >= g.d + 1;
+	const bool act = interior && active[p] != 0;
+	const bool full = act && strong, fb = act && !strong;
+
+	const unsigned lane = (threadIdx.x + blockDim.x * threadIdx.y) & 31;
+	const unsigned mFull = __ballot_sync(0xffffffffu, full);
+	const unsigned mFb = __ballot_sync(0xffffffffu, fb);
+	const unsigned mInt = __ballot_sync(0xffffffffu, interior);
+	const unsigned mStrong = __ballot_sync(0xffffffffu, strong);
+	const unsigned mAct = __ballot_sync(0xffffffffu, act);
+	int nsum = full ? n : 0;
+	for(int o = 16; o > 0; o >>= 1)
+		nsum += __shfl_xor_sync(0xffffffffu, nsum, o);
+	int baseFull = 0, baseFb = 0;
+	if(lane == 0)
+	{
+		if(mFull) baseFull = atomicAdd(&ctr->nFull, __popc(mFull));
+		if(mFb) baseFb = atomicAdd(&ctr->nFallback, __popc(mFb));
+		if(mInt) atomicAdd(&ctr->interior, (unsigned long long)__popc(mInt));
+		if(mStrong) atomicAdd(&ctr->strong, (unsigned long long)__popc(mStrong));
+		if(mAct) atomicAdd(&ctr->active, (unsigned long long)__popc(mAct));
+		if(mFull) atomicAdd(&ctr->full, (unsigned long long)__popc(mFull));
+		if(mFb) atomicAdd(&ctr->fallback, (unsigned long long)__popc(mFb));
+		if(nsum) atomicAdd(&ctr->sum_n_full, (unsigned long long)nsum);
+	}
+	baseFull = __shfl_sync(0xffffffffu, baseFull, 0);
+	baseFb = __shfl_sync(0xffffffffu, baseFb, 0);
+	const unsigned below = (1u << lane) - 1u;
+	if(full)
+		fullList[baseFull + __popc(mFull & below)] = (int)p;
+	if(fb)
+		fallbackList[baseFb + __popc(mFb & below)] = (int)p;
+}
+
+cudaError_t launchBuildLists(const int* counts, const unsigned char* active, const LevelGeom& g,
+		int* fullList, int* fallbackList, DeviceCounters* ctr, cudaStream_t st, int* launches)
+{
+	dim3 block(32, 8), grid(divUp(g.W, 32), divUp(g.H, 8));
+	k_build_lists<<<grid, block, 0, st>>>(counts, active, g, fullList, fallbackList, ctr);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// out = (1/count) * sum; count == 0 gives inf * 0 = NaN exactly like Denoiser.cpp:463-466
+__global__ void k_finalize(const float4* __restrict__ acc, size_t npix, float* __restrict__ out)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= npix)
+		return;
+	const float4 a = acc[i];
+	const float ci = __fdiv_rn(1.f, a.w);
+	out[i * 3 + 0] = __fmul_rn(ci, a.x);
+	out[i * 3 + 1] = __fmul_rn(ci, a.y);
+	out[i * 3 + 2] = __fmul_rn(ci, a.z);
+}
+
+cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches)
+{
+	k_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(acc, npix, out);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pyramid
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int n) { return v <= 0 ? 0 : (v >= n ? n - 1 : v); }
+
+// mode 0: sum (histogram, nSamples)  1: 0.25 * sum (colour)
+__global__ void k_downscale(const float* __restrict__ in, int W, int H, int D, int mode, float* __restrict__ out)
+{
+	const int Wd = W / 2, Hd = H / 2;
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= (size_t)Wd * Hd * D)
+		return;
+	const int z = (int)(i % D);
+	const size_t pix = i / D;
+	const int c = (int)(pix % Wd), l = (int)(pix / Wd);
+	const int l1 = clampi(2 * l + 1, H), c1 = clampi(2 * c + 1, W);
+	const float v1 = in[((size_t)(2 * l) * W + 2 * c) * D + z];
+	const float v2 = in[((size_t)l1 * W + 2 * c) * D + z];
+	const float v3 = in[((size_t)(2 * l) * W + c1) * D + z];
+	const float v4 = in[((size_t)l1 * W + c1) * D + z];
+	const float s = v1 + v2 + v3 + v4;
+	out[i] = mode ? 0.25f * s : s;
+}
+
+__global__ void k_downscale_cov(const float* __restrict__ cov, const float* __restrict__ ns, int W, int H,
+		float* __restrict__ out)
+{
+	const int Wd = W / 2, Hd = H / 2;
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= (size_t)Wd * Hd * 6)
+		return;
+	const int z = (int)(i % 6);
+	const size_t pix = i / 6;
+	const int c = (int)(pix % Wd), l = (int)(pix / Wd);
+	const int l1 = clampi(2 * l + 1, H), c1 = clampi(2 * c + 1, W);
+	const size_t i1 = (size_t)(2 * l) * W + 2 * c, i2 = (size_t)l1 * W + 2 * c;
+	const size_t i3 = (size_t)(2 * l) * W + c1, i4 = (size_t)l1 * W + c1;
+	const float n1 = ns[i1], n2 = ns[i2], n3 = ns[i3], n4 = ns[i4];
+	const float nSum = n1 + n2 + n3 + n4;
+	const float sq = (1.f / 4.f) * (1.f / 4.f);
+	const float w1 = sq * nSum / n1, w2 = sq * nSum / n2, w3 = sq * nSum / n3, w4 = sq * nSum / n4;
+	out[i] = w1 * cov[i1 * 6 + z] + w2 * cov[i2 * 6 + z] + w3 * cov[i3 * 6 + z] + w4 * cov[i4 * 6 + z];
+}
+
+cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
+		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches)
+{
+	const size_t npd = (size_t)(W / 2) * (H / 2);
+	if(npd == 0)
+		return cudaSuccess;
+	auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+	k_downscale<<<blocks(npd * 3), 256, 0, st>>>(color, W, H, 3, 1, colorD);
+	k_downscale<<<blocks(npd), 256, 0, st>>>(ns, W, H, 1, 0, nsD);
+	k_downscale<<<blocks(npd * B), 256, 0, st>>>(hist, W, H, B, 0, histD);
+	k_downscale_cov<<<blocks(npd * 6), 256, 0, st>>>(cov, ns, W, H, covD);
+	*launches += 4;
+	return cudaGetLastError();
+}
+
+// interpolate (MultiscaleDenoiser.cpp:473-512) evaluated at one upscaled sample
+__device__ __forceinline__ float interpAt(const float* __restrict__ low, int Wl, int Hl, int L, int C, int z)
+{
+	const float mw = 9.f / 16.f, aw = 3.f / 16.f, dw = 1.f / 16.f;
+	const int l = L / 2, c = C / 2;
+	const int al = clampi(l + ((L % 2) * 2 - 1), Hl);
+	const int ac = clampi(c + ((C % 2) * 2 - 1), Wl);
+	const int lc = clampi(l, Hl), cc = clampi(c, Wl);
+	const float p1 = low[((size_t)lc * Wl + cc) * 3 + z];
+	const float p2 = low[((size_t)lc * Wl + ac) * 3 + z];
+	const float p3 = low[((size_t)al * Wl + cc) * 3 + z];
+	const float p4 = low[((size_t)al * Wl + ac) * 3 + z];
+	return mw * p1 + aw * (p2 + p3) + dw * p4;
+}
+
+// hi <- (hi - interpolate(downscale(hi))) + interpolate(lowOut)   (mergeOutputs :453-466)
+__global__ void k_merge(float* __restrict__ hi, int W, int H, const float* __restrict__ tmpLow,
+		const float* __restrict__ lowOut)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= (size_t)W * H * 3)
+		return;
+	const int z = (int)(i % 3);
+	const size_t pix = i / 3;
+	const int C = (int)(pix % W), L = (int)(pix / W);
+	const int Wl = W / 2, Hl = H / 2;
+	float v = hi[i];
+	v = v - interpAt(tmpLow, Wl, Hl, L, C, z);
+	v = v + interpAt(lowOut, Wl, Hl, L, C, z);
+	hi[i] = v;
+}
+
+cudaError_t launchMerge(float* hi, int W, int H, const float* lowOut, float* tmpLow, cudaStream_t st, int* launches)
+{
+	const size_t npd = (size_t)(W / 2) * (H / 2);
+	if(npd == 0)
+		return cudaSuccess;
+	k_downscale<<<(unsigned)((npd * 3 + 255) / 256), 256, 0, st>>>(hi, W, H, 3, 1, tmpLow);
+	k_merge<<<(unsigned)(((size_t)W * H * 3 + 255) / 256), 256, 0, st>>>(hi, W, H, tmpLow, lowOut);
+	*launches += 2;
+	return cudaGetLastError();
+}
+
+} // namespace bcdk

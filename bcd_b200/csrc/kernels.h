@@ -1,0 +1,56 @@
+// Host-side launchers of the bcd_b200 kernels (one per stage of the hot path; see DESIGN.md for the stage map).
+#pragma once
+#include "common.cuh"
+
+namespace bcdk
+{
+
+// accumulators of the data-dependent work counters (device resident)
+struct DeviceCounters
+{
+	unsigned long long interior, strong, active, full, fallback, sum_n_full;
+	int nFull, nFallback; // list lengths of the current level
+};
+
+// K0  Denoiser::computePixelCovFromSampleCov
+cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches);
+// K1a/b/c
+cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom& g, float* sP, unsigned char* cP,
+		cudaStream_t st, int* launches);
+cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,
+		uint32_t* mplus, cudaStream_t st, int* launches);
+cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre,
+		cudaStream_t st, int* launches);
+// K2  marking strategy in raster order over the owned rows. asBits: H x Wp bit-rows (column c at bit c + 32),
+// zero (or the upper row tile's hand-off) in the rows above rowBeg on entry; progress: >= ceil(rows/32) counters.
+inline int markingRowWords(int W) { return (W + 64 + 31) / 32 + 2; }
+cudaError_t launchMarking(const uint32_t* pre, const LevelGeom& g, float skipProb, uint32_t seed,
+		unsigned char* active, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches);
+cudaError_t launchAllActive(const LevelGeom& g, unsigned char* active, cudaStream_t st, int* launches);
+// work lists
+cudaError_t launchBuildLists(const int* counts, const unsigned char* active, const LevelGeom& g,
+		int* fullList, int* fallbackList, DeviceCounters* ctr, cudaStream_t st, int* launches);
+// K3f denoiseOnlyMainPatch
+cudaError_t launchFallback(const float* color, const uint32_t* smask, const int* counts, const LevelGeom& g,
+		const int* fallbackList, const int* nFallback, float4* acc, cudaStream_t st, int* launches);
+// K3 two-step Bayesian filter over a chunk [first, first+count) of the full list
+struct FilterBuffers
+{
+	float* A;      // chunk x d*d   (C - Sigma_n, later C2 + Sigma_n)
+	float* Minv;   // chunk x d*d
+	float* mean;   // chunk x d
+	float* noise;  // chunk x np*6
+	float* xScratch; // optional global scratch for X when it does not fit shared memory (gridCap x nsmax*d)
+	int gridCap;
+};
+cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const int* counts,
+		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const FilterBuffers& fb,
+		float4* acc, cudaStream_t st, int* launches, float* stageMs /*3: stats, eig, apply*/, cudaEvent_t* ev);
+// K4 finalAggregation
+cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches);
+// K5 pyramid down, K6 merge
+cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
+		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches);
+cudaError_t launchMerge(float* hi, int W, int H, const float* lowOut, float* tmpLow, cudaStream_t st, int* launches);
+
+} // namespace bcdk

@@ -1,0 +1,131 @@
+/*
+ * bcd_b200.h — C ABI of the B200-native Bayesian Collaborative Denoiser hot path.
+ *
+ * This is the drop-in boundary. The reference has no FFI layer: its boundary is the C++ class
+ * bcd::IDenoiser (reference include/bcd/core/IDenoiser.h:73-97) with the concrete bcd::Denoiser
+ * (include/bcd/core/Denoiser.h:25-44, src/core/Denoiser.cpp:84-212) and bcd::MultiscaleDenoiser
+ * (include/bcd/core/MultiscaleDenoiser.h:23-30, src/core/MultiscaleDenoiser.cpp:31-136). The re-authored,
+ * source-compatible C++ headers under include/bcd/core/ forward their denoise() to the entry points below, so a
+ * host renderer or bcd_cli keeps compiling unchanged and reaches the sm_100a kernels through plain pointers.
+ *
+ * Conventions
+ *   - all images are HWC-interleaved float32, idx = (line*W + col)*depth + k (reference DeepImage.hpp:385-396);
+ *     covariance channel order xx,yy,zz,yz,xz,xy (reference CovarianceMatrix.h:18-27);
+ *   - host pointers are borrowed for the duration of a call; nothing is freed by the library;
+ *   - every function returns 0 on success or a negative bcd_b200_status; bcd_b200_last_error() returns a
+ *     thread-local message. The library never calls exit() (the reference's CUDA path does: CudaUtils.h:18-30);
+ *   - a handle is not re-entrant; different handles may be used from different threads.
+ */
+#ifndef BCD_B200_H
+#define BCD_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCD_B200_ABI_VERSION 1
+
+typedef enum bcd_b200_status {
+	BCD_B200_OK = 0,
+	BCD_B200_ERR_INVALID_ARGUMENT = -1, /* null / empty / size-mismatched inputs (reference Denoiser.cpp:269-346 returns false) */
+	BCD_B200_ERR_CUDA = -2,             /* CUDA runtime failure, message in bcd_b200_last_error() */
+	BCD_B200_ERR_NO_DEVICE = -3,
+	BCD_B200_ERR_UNSUPPORTED = -4,      /* parameter combination the kernels are not built for */
+	BCD_B200_ERR_STATE = -5             /* call order violated (e.g. run before upload) */
+} bcd_b200_status;
+
+/* Replaces bcd::DenoiserInputs (reference IDenoiser.h:46-59) */
+typedef struct bcd_b200_images {
+	const float* color;    /* W*H*3 */
+	const float* nsamples; /* W*H   */
+	const float* hist;     /* W*H*hist_depth */
+	const float* cov;      /* W*H*6 (sample covariance) */
+	int32_t width;
+	int32_t height;
+	int32_t hist_depth;    /* 3 * nbOfBins, 60 with the default HistogramParameters */
+} bcd_b200_images;
+
+/* Replaces bcd::DenoiserParameters (reference IDenoiser.h:20-44) + MultiscaleDenoiser's nbOfScales */
+typedef struct bcd_b200_params {
+	float   tau;            /* m_histogramDistanceThreshold (1.0)   */
+	int32_t patch_radius;   /* m_patchRadius (1)                    */
+	int32_t search_radius;  /* m_searchWindowRadius (6)             */
+	float   min_eig;        /* m_minEigenValue (1e-8)               */
+	int32_t random_order;   /* m_useRandomPixelOrder: accepted and ignored — the kernels always realise the
+	                           sequential raster order (the reference's only deterministic order) */
+	float   skip_prob;      /* m_markedPixelsSkippingProbability: 1 = marking strategy (default), 0 = every pixel;
+	                           0<m<1 uses a counter-based hash instead of rand() (DenoisingUnit.cpp:168) */
+	int32_t nb_scales;      /* 1 = Denoiser, >1 = MultiscaleDenoiser(nb_scales) */
+	int32_t reserved;
+} bcd_b200_params;
+
+void bcd_b200_default_params(bcd_b200_params* p);
+
+/* Data-dependent work counters of the last run, summed over scales (bench.py prints them). */
+typedef struct bcd_b200_stats {
+	int64_t interior;    /* patch centres visited */
+	int64_t strong;      /* |S(p)| >= d+1 */
+	int64_t active;      /* not skipped by the marking strategy */
+	int64_t full;        /* two-step Bayesian filter */
+	int64_t fallback;    /* denoiseOnlyMainPatch */
+	int64_t sum_n_full;  /* sum of |S(p)| over full pixels */
+	int64_t kernel_launches;
+} bcd_b200_stats;
+
+/* Per-stage device time of the last run in milliseconds (CUDA events on the handle's stream), summed over scales. */
+enum { BCD_B200_STAGE_PREPASS = 0, BCD_B200_STAGE_PAIR = 1, BCD_B200_STAGE_SELECT = 2, BCD_B200_STAGE_MARKING = 3,
+       BCD_B200_STAGE_FALLBACK = 4, BCD_B200_STAGE_FILTER_STATS = 5, BCD_B200_STAGE_FILTER_EIG = 6,
+       BCD_B200_STAGE_FILTER_APPLY = 7, BCD_B200_STAGE_FINALIZE = 8, BCD_B200_STAGE_PYRAMID = 9,
+       BCD_B200_STAGE_COUNT = 10 };
+typedef struct bcd_b200_timings {
+	float stage_ms[BCD_B200_STAGE_COUNT];
+	float total_ms;
+} bcd_b200_timings;
+
+typedef void (*bcd_b200_progress_fn)(float progress01, void* user);
+
+const char* bcd_b200_last_error(void);
+int bcd_b200_abi_version(void);
+int bcd_b200_device_count(void);
+
+/* ---- one-shot entry: what bcd::Denoiser::denoise() / bcd::MultiscaleDenoiser::denoise() forward to -------------
+ * Replaces reference Denoiser.cpp:84-212 and MultiscaleDenoiser.cpp:31-136. Host buffers in, host buffer out
+ * (out_rgb = W*H*3, caller-allocated). Uses device `device` (0 if negative). */
+int bcd_b200_denoise(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, int device,
+                     bcd_b200_progress_fn progress, void* user);
+
+/* ---- handle API: device buffers (and streams) persist across frames ------------------------------------------- */
+typedef struct bcd_b200_handle bcd_b200_handle;
+
+int  bcd_b200_create(bcd_b200_handle** out, int device);
+void bcd_b200_destroy(bcd_b200_handle* h);
+/* optional: run on a caller-owned stream (cudaStream_t passed as void*); NULL restores the handle's own stream */
+int  bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream);
+/* host -> device copy of the four input images (pinned or pageable host memory) */
+int  bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in);
+/* same, but the pointers in `in` are DEVICE pointers that the handle borrows until the next upload/bind/destroy */
+int  bcd_b200_bind_device(bcd_b200_handle* h, const bcd_b200_images* in);
+/* whole hot path on the resident inputs; synchronous with respect to the host on return */
+int  bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress_fn progress, void* user);
+/* device -> host copy of the W*H*3 result */
+int  bcd_b200_download(bcd_b200_handle* h, float* out_rgb);
+/* device pointer of the W*H*3 result (valid until the next run/destroy) */
+int  bcd_b200_result_device_ptr(bcd_b200_handle* h, const float** out_dev);
+int  bcd_b200_get_stats(bcd_b200_handle* h, bcd_b200_stats* s);
+int  bcd_b200_get_timings(bcd_b200_handle* h, bcd_b200_timings* t);
+
+/* ---- stage-level read-backs used by the parity tests (level 0 of the last run) ---------------------------------
+ * masks: W*H*words uint32, bit index (dy+b)*(2b+1)+(dx+b) — the ordered similar set S(p) of
+ * DenoisingUnit::selectSimilarPatches (reference DenoisingUnit.cpp:196-219); counts: W*H int32;
+ * active: W*H uint8 (marking strategy outcome, DenoisingUnit.cpp:164-173,690). */
+int  bcd_b200_mask_words(int search_radius);
+int  bcd_b200_debug_read_selection(bcd_b200_handle* h, uint32_t* masks, int32_t* counts);
+int  bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCD_B200_H */

@@ -1,0 +1,111 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (bcd_b200/capi.py -> libbcd_b200.so), against
+  (1) the committed golden fixtures produced by the unmodified reference CPU path (tests/golden/make_golden.py),
+  (2) the C restatement's selection masks / counts / marking outcome, bit for bit.
+Tolerance: relative L-infinity (max|a-ref| / max|ref|) <= 1e-4 for the float output (north_star); 0 mismatching bits
+for the discrete stages.
+"""
+import numpy as np
+import pytest
+
+from conftest import inputs_of
+import oracles as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from bcd_b200 import capi
+    if capi.lib().bcd_b200_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return capi
+
+
+def _run(capi, inp, **kw):
+    h = capi.Handle(0)
+    try:
+        h.upload(**inp)
+        h.run(**kw)
+        out = h.download()
+        return h, out
+    except Exception:
+        h.close()
+        raise
+
+
+def test_selection_bit_exact(capi, crop_a):
+    h, _ = _run(capi, inputs_of(crop_a), m=0.0)
+    masks, counts = h.read_selection()
+    st = h.stats()
+    h.close()
+    ref_masks, ref_counts = crop_a["port_masks"], crop_a["port_counts"]
+    diff_bits = int(np.unpackbits((masks ^ ref_masks).view(np.uint8)).sum())
+    bad = np.argwhere(counts != ref_counts)
+    assert diff_bits == 0, "%d mismatching selection bits, first at %s" % (diff_bits, bad[:5].tolist())
+    assert (counts == ref_counts).all()
+    assert st["strong"] == int((ref_counts >= 28).sum())
+
+
+def test_marking_bit_exact(capi, crop_a):
+    h, _ = _run(capi, inputs_of(crop_a), m=1.0)
+    active = h.read_active()
+    st = h.stats()
+    h.close()
+    ref = crop_a["port_active_m1"]
+    bad = np.argwhere(active != ref)
+    assert bad.shape[0] == 0, "%d marking mismatches, first (row,col) %s" % (bad.shape[0], bad[:8].tolist())
+    strong = crop_a["port_counts"] >= 28
+    assert st["full"] == int((ref.astype(bool) & strong).sum())
+    assert st["fallback"] == int((ref.astype(bool) & ~strong).sum())
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("ref_s1_m0", dict(m=0.0, scales=1)),
+    ("ref_s1_m1", dict(m=1.0, scales=1)),
+    ("ref_s2_m0", dict(m=0.0, scales=2)),
+    ("ref_s3_m1", dict(m=1.0, scales=3)),
+])
+def test_end_to_end_crop_a(capi, crop_a, key, kw):
+    h, out = _run(capi, inputs_of(crop_a), **kw)
+    h.close()
+    err = O.rel_linf(out, crop_a[key])
+    assert err <= TOL, "%s: rel Linf %.3e" % (key, err)
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("ref_s2_m0", dict(m=0.0, scales=2)),
+    ("ref_s2_m1", dict(m=1.0, scales=2)),
+    ("ref_s1_m0_b4", dict(m=0.0, scales=1, b=4)),
+    ("ref_s1_m1_tau2", dict(m=1.0, scales=1, tau=2.0)),
+])
+def test_end_to_end_crop_b_odd_size(capi, crop_b, key, kw):
+    h, out = _run(capi, inputs_of(crop_b), **kw)
+    h.close()
+    err = O.rel_linf(out, crop_b[key])
+    assert err <= TOL, "%s: rel Linf %.3e" % (key, err)
+
+
+def test_wide_patch_w2(capi, crop_c):
+    h, out = _run(capi, inputs_of(crop_c), m=0.0, w=2, b=5)
+    st = h.stats()
+    h.close()
+    err = O.rel_linf(out, crop_c["ref_s1_m0_w2b3"])
+    assert err <= TOL, "w=2: rel Linf %.3e (stats %s)" % (err, st)
+
+
+def test_one_shot_entry_matches_handle(capi, crop_b):
+    inp = inputs_of(crop_b)
+    out1 = capi.denoise(**inp, m=0.0)
+    h, out2 = _run(capi, inp, m=0.0)
+    h.close()
+    assert O.rel_linf(out1, out2) <= 1e-5
+
+
+def test_invalid_inputs_are_rejected(capi, crop_c):
+    inp = inputs_of(crop_c)
+    with pytest.raises(capi.BcdError):
+        capi.denoise(**inp, b=0)
+    with pytest.raises(capi.BcdError):
+        capi.denoise(**inp, scales=0)
