@@ -1,0 +1,67 @@
+"""ctypes binding of libbcdcore_b200.so (include/bcd_b200_host.h): the C++ drop-in classes bcd::Denoiser /
+bcd::MultiscaleDenoiser driven like a host renderer would, the re-implemented bcd::SamplesAccumulator, and the
+seeded synthetic-input generator G(W,H,spp,seed,sigma) of SURVEY §8d used by bench.py and the tests."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbcdcore_b200.so")
+SYMBOLS = ["bcd_synth_generate", "bcd_host_accumulate", "bcd_host_cxx_denoise"]
+DEFAULT_SEED = 20170627
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `make`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        fp = C.c_void_p
+        L.bcd_synth_generate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_float, C.c_float,
+                                         C.c_int, C.c_int, fp, fp, fp, fp]
+        L.bcd_host_accumulate.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp]
+        L.bcd_host_cxx_denoise.argtypes = [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
+                                           C.c_int, C.c_float, C.c_int, C.c_int, fp, C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def synth(W, H, spp=64, seed=DEFAULT_SEED, sigma=0.6, nb_bins=20, gamma=2.2, max_value=2.5, row0=0, rows=None, out=None):
+    """G(W,H,spp,seed,sigma) -> dict(color (rows,W,3), nsamples (rows,W,1), hist (rows,W,3*nb_bins), cov (rows,W,6)).
+    `out` may hold preallocated arrays (e.g. numpy views of pinned torch tensors)."""
+    rows = H - row0 if rows is None else rows
+    if out is None:
+        out = dict(color=np.empty((rows, W, 3), np.float32), nsamples=np.empty((rows, W, 1), np.float32),
+                   hist=np.empty((rows, W, 3 * nb_bins), np.float32), cov=np.empty((rows, W, 6), np.float32))
+    lib().bcd_synth_generate(W, H, spp, seed, sigma, nb_bins, gamma, max_value, row0, rows,
+                             out["color"].ctypes.data, out["nsamples"].ctypes.data, out["hist"].ctypes.data,
+                             out["cov"].ctypes.data)
+    return out
+
+
+def accumulate(samples, nb_bins=20, gamma=2.2, max_value=2.5):
+    samples = np.ascontiguousarray(samples, np.float32)
+    H, W, spp, _ = samples.shape
+    out = dict(color=np.empty((H, W, 3), np.float32), nsamples=np.empty((H, W, 1), np.float32),
+               hist=np.empty((H, W, 3 * nb_bins), np.float32), cov=np.empty((H, W, 6), np.float32))
+    lib().bcd_host_accumulate(samples.ctypes.data, W, H, spp, nb_bins, gamma, max_value, out["color"].ctypes.data,
+                              out["nsamples"].ctypes.data, out["hist"].ctypes.data, out["cov"].ctypes.data)
+    return out
+
+
+def cxx_denoise(color, nsamples, hist, cov, tau=1.0, w=1, b=6, eps=1e-8, random_order=True, m=1.0, scales=1, device=0):
+    """Runs bcd::Denoiser / bcd::MultiscaleDenoiser (the C++ drop-in) -> (ok, out, progress_calls)."""
+    color = np.ascontiguousarray(color, np.float32)
+    H, W, _ = color.shape
+    ns = np.ascontiguousarray(nsamples, np.float32)
+    hist = np.ascontiguousarray(hist, np.float32)
+    cov = np.ascontiguousarray(cov, np.float32)
+    out = np.zeros((H, W, 3), np.float32)
+    calls = C.c_int(0)
+    ok = lib().bcd_host_cxx_denoise(color.ctypes.data, ns.ctypes.data, hist.ctypes.data, cov.ctypes.data, W, H,
+                                    hist.shape[2], tau, w, b, eps, int(random_order), m, scales, device,
+                                    out.ctypes.data, C.byref(calls))
+    return bool(ok), out, calls.value

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native BCD hot path (contract: see the task statement, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--m 1|0] [--size WxH] [--scales S]
+
+N = 1 workload (BASELINE.json `metric` / configs[2]): synthetic G(1920,1080,spp=64,seed=20170627) colour + histogram +
+covariance buffers, MultiscaleDenoiser s=3, defaults b=6, w=1, tau=1, m=1 (marking strategy, raster order).
+A "step" is one complete denoise of that frame.
+
+  value : Mpixels/s with the inputs already resident in HBM (bind_device; timed with CUDA events on the launching
+          stream, barrier + synchronize on both sides, max over ranks).
+  e2e   : the same metric through the C ABI handle calls a host renderer makes per frame — upload (pinned host ->
+          device) + run + download — all inside the timed region.
+  roofline     : dominant kernel (k_pair_terms_tiled, stage "pair") — algorithmic bytes / CUDA-event time vs the
+                 measured HBM peak (MEASURED_PEAKS.json); the binding roof of this kernel is FP32 issue, not HBM
+                 (SURVEY §8d), so `roofline_fp32` reports the bin-term rate against the FP32 pipe as well.
+  cpu_baseline : the UNMODIFIED reference CPU path (oracle/_ref, all host cores) on a bounded crop of the same frame.
+
+`--impl reference` times only that reference arm (rank 0), one bounded crop per step.
+N > 1: the frame is cut into row tiles, one rank per GPU (bcd_b200/tiles.py); see DESIGN.md §multi-GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/s denoised"
+UNIT = "Mpix/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=float, default=1.0, help="markedPixelsSkippingProbability (1 = default marking strategy)")
+    ap.add_argument("--size", default=None, help="WxH (default 1920x1080 at N=1, 4096x4096 at N>1)")
+    ap.add_argument("--scales", type=int, default=3)
+    ap.add_argument("--w", type=int, default=1)
+    ap.add_argument("--b", type=int, default=6)
+    ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-crop", type=int, default=384, help="side of the square crop the CPU reference is timed on")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_sample(inputs, crop, scales, m, w, b, cores=0):
+    """Times the unmodified reference (oracle/_ref) on a crop x crop window of the frame, all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles as O
+    H, W, _ = inputs["color"].shape
+    c = min(crop, H, W)
+    y0, x0 = (H - c) // 2, (W - c) // 2  # centred: straddles the albedo-texture boundary at x = W/2
+    sub = {k: np.ascontiguousarray(v[y0:y0 + c, x0:x0 + c]) for k, v in inputs.items()}
+    kind = "reference" if O.have_ref() else "port"
+    t = time.perf_counter()
+    if kind == "reference":
+        O.ref_denoise(**sub, cores=cores, m=m, scales=scales, w=w, b=b, random_order=False)
+        ncores = O.ref_lib().bcdref_max_threads()
+    else:
+        O.port_denoise(**sub, m=m, scales=scales, w=w, b=b)
+        ncores = 1
+    dt = time.perf_counter() - t
+    return {"value": c * c / dt / 1e6, "unit": UNIT, "cores": int(ncores), "kind": kind, "seconds": dt,
+            "sample": "%dx%d centre crop of the same synthetic frame, s=%d m=%g b=%d w=%d, raster order, %s" % (
+                c, c, scales, m, b, w, "OpenMP all cores" if kind == "reference" else "scalar C port")}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = a.gpus
+    size = a.size or ("1920x1080" if n_gpus == 1 else "4096x4096")
+    W, H = [int(v) for v in size.lower().split("x")]
+    workload = "G(%d,%d,spp=%d,seed=20170627) synthetic colour+histogram+covariance, MultiscaleDenoiser s=%d, b=%d w=%d tau=1 m=%g" % (
+        W, H, a.spp, a.scales, a.b, a.w, a.m)
+    config = {"workload": workload, "width": W, "height": H, "scales": a.scales, "search_radius": a.b, "patch_radius": a.w,
+              "skip_prob": a.m, "order": "raster (the reference's deterministic order)",
+              "l2_policy": "inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (W * H * 280 / 1e6),
+              "parallelism": "1 GPU" if n_gpus == 1 else "row tiles x%d (one rank per GPU)" % n_gpus}
+
+    from bcd_b200 import host
+
+    # ---------------------------------------------------------------------------------------------- reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        inp = host.synth(W, H, spp=a.spp)
+        times = []
+        info = None
+        for i in range(a.warmup + a.steps):
+            info = cpu_reference_sample(inp, a.cpu_crop, a.scales, a.m, a.w, a.b)
+            if i >= a.warmup:
+                times.append(info["seconds"])
+        c = min(a.cpu_crop, W, H)
+        val = c * c * len(times) / sum(times) / 1e6
+        info["value"] = val
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # --------------------------------------------------------------------------------------------------- our arm
+    import torch
+    from bcd_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if world > 1:
+        from bcd_b200 import tiles
+        return tiles.bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist)
+
+    # ---- inputs: generated straight into pinned host memory
+    B = 60
+    pin = dict(color=torch.empty((H, W, 3), dtype=torch.float32).pin_memory(),
+               nsamples=torch.empty((H, W, 1), dtype=torch.float32).pin_memory(),
+               hist=torch.empty((H, W, B), dtype=torch.float32).pin_memory(),
+               cov=torch.empty((H, W, 6), dtype=torch.float32).pin_memory())
+    t0 = time.time()
+    host.synth(W, H, spp=a.spp, out={k: v.numpy() for k, v in pin.items()})
+    gen_s = time.time() - t0
+    out_pin = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    dev = {k: v.cuda(non_blocking=True) for k, v in pin.items()}
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    h = capi.Handle(local_rank)
+    h.set_stream(stream.cuda_stream)
+    params = capi.make_params(w=a.w, b=a.b, m=a.m, scales=a.scales)
+    h2d = sum(v.numel() * 4 for v in pin.values())
+    d2h = out_pin.numel() * 4
+
+    def step_resident():
+        h.run(params)
+
+    def step_e2e():
+        h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, H, B)
+        h.run(params)
+        h.download_ptr(out_pin.data_ptr())
+
+    def timed(fn, bind):
+        if bind:
+            h.bind_device(dev["color"].data_ptr(), dev["nsamples"].data_ptr(), dev["hist"].data_ptr(), dev["cov"].data_ptr(), W, H, B)
+        for _ in range(a.warmup):
+            fn()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_acc, launches = {}, 0
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(a.steps):
+            fn()
+            for k, v in h.timings().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+            launches += h.stats()["kernel_launches"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        return e0.elapsed_time(e1), stage_acc, launches, clocks
+
+    ms_res, stages, launches, clocks = timed(step_resident, True)
+    stats = h.stats()
+    ms_e2e, _, _, clocks_e2e = timed(step_e2e, False)
+    result_ok = bool(np.isfinite(out_pin.numpy()[2:-2, 2:-2]).all())
+
+    value = W * H * a.steps / (ms_res * 1e-3) / 1e6
+    e2e_val = W * H * a.steps / (ms_e2e * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_pair_terms_tiled: every level launches it once)
+    pk, pk_src = peaks()
+    npix_all = sum((W >> k) * (H >> k) for k in range(a.scales))
+    pair_ms = stages["pair"] / a.steps                      # all levels, per step
+    J = ((2 * a.b + 1) ** 2 + 1) // 2
+    alg_bytes = npix_all * (B + 1) * 4                      # compulsory: histogram + nSamples read once (244 B/px)
+    achieved = alg_bytes / (pair_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "k_pair_terms_tiled (stage 'pair', %d launches/step)" % a.scales, "bound": "hbm",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                "peak_source": pk_src + " (burst copy figure; kernel timed alone by CUDA events)", "traffic": traffic,
+                "ms_per_launch_set": pair_ms,
+                "note": "FP32-issue-bound kernel: HBM fraction is low by construction (SURVEY 8d); see roofline_fp32"}
+    terms = npix_all * J * B                                # bin terms actually evaluated per step
+    fp32_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1900.0) * 1e6 / 1e12  # FMA TFLOP/s at the sampled clock
+    roofline_fp32 = {"bin_terms_per_s": terms / (pair_ms * 1e-3), "flop_equiv_per_term": 10,
+                     "achieved_tflops_equiv": terms * 10 / (pair_ms * 1e-3) / 1e12, "fp32_peak_tflops": fp32_peak,
+                     "frac": terms * 10 / (pair_ms * 1e-3) / 1e12 / fp32_peak}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / a.steps, "api": "bcd_b200_upload + bcd_b200_run + bcd_b200_download (pinned host buffers)"},
+            "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32,
+            "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()},
+            "work_counters": stats, "input_generation_s": gen_s, "output_finite": result_ok}
+    if not a.no_cpu_baseline:
+        cb = cpu_reference_sample({k: v.numpy() for k, v in pin.items()}, a.cpu_crop, a.scales, a.m, a.w, a.b)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    h.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,39 @@
+/*
+ * bcd_b200_host.h — small C entry points of libbcdcore_b200.so used by the Python tests and bench.py:
+ * the seeded synthetic-input generator G of SURVEY §8d (benchmark workload), the SamplesAccumulator path for raw
+ * sample dumps, and a C wrapper around bcd::Denoiser / bcd::MultiscaleDenoiser so that the C++ drop-in classes
+ * themselves can be exercised from ctypes.
+ */
+#ifndef BCD_B200_HOST_H
+#define BCD_B200_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* G(W, H, spp, seed, sigma): counter-based synthetic radiance + log-normal samples (+ fireflies), accumulated with
+ * bcd::SamplesAccumulator (weight 1; nb_bins, gamma, max_value as in HistogramParameters). Outputs are HWC float32:
+ * color W*H*3, nsamples W*H, hist W*H*3*nb_bins, cov W*H*6. Rows [row0, row0+rows) of the W x H image only (so row
+ * tiles can be generated independently). Returns 0. */
+int bcd_synth_generate(int width, int height, int spp, uint64_t seed, double sigma,
+                       int nb_bins, float gamma, float max_value, int row0, int rows,
+                       float* color, float* nsamples, float* hist, float* cov);
+
+/* raw samples [line][col][sample][rgb] -> statistics through bcd::SamplesAccumulator */
+int bcd_host_accumulate(const float* samples, int width, int height, int spp, int nb_bins, float gamma, float max_value,
+                        float* color, float* nsamples, float* hist, float* cov);
+
+/* bcd::Denoiser (nb_scales == 1) / bcd::MultiscaleDenoiser (nb_scales > 1) driven exactly like a host renderer
+ * would (setInputs / setOutputs / setParameters / setProgressCallback / denoise()). Returns 1 when denoise()
+ * returned true, 0 otherwise; *progress_calls receives the number of progress callbacks. */
+int bcd_host_cxx_denoise(const float* color, const float* nsamples, const float* hist, const float* cov,
+                         int width, int height, int hist_depth,
+                         float tau, int patch_radius, int search_radius, float min_eig, int random_order, float skip_prob,
+                         int nb_scales, int device, float* out_rgb, int* progress_calls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
