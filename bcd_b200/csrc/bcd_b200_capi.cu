@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -149,7 +150,7 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	STAGE(h, BCD_B200_STAGE_PREPASS, {
 		CU(launchPixelCov(L.cov, L.ns, npix, h->pixcov.as<float>(), st, &h->launches));
 		CU(cudaMemsetAsync(h->acc.p, 0, npix * sizeof(float4), st));
-		CU(cudaMemsetAsync(h->active.p, 0, npix, st));
+		CU(cudaMemsetAsync(h->active.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
 		CU(cudaMemsetAsync(h->ctr.p, 0, sizeof(DeviceCounters), st));
 	});
 	STAGE(h, BCD_B200_STAGE_PAIR, {
@@ -164,12 +165,12 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		if(p.skip_prob > 0.f)
 		{
 			CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
-			CU(launchMarking(h->pre.as<uint32_t>(), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<unsigned char>(),
+			CU(launchMarking(h->pre.as<uint32_t>(), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<uint32_t>(),
 					h->asBits.as<uint32_t>(), Wp, h->progress.as<unsigned int>(), st, &h->launches));
 		}
 		else
-			CU(launchAllActive(g, h->active.as<unsigned char>(), st, &h->launches));
-		CU(launchBuildLists(h->counts.as<int>(), h->active.as<unsigned char>(), g, h->fullList.as<int>(),
+			CU(launchAllActive(g, h->active.as<uint32_t>(), Wp, st, &h->launches));
+		CU(launchBuildLists(h->counts.as<int>(), h->active.as<uint32_t>(), Wp, g, h->fullList.as<int>(),
 				h->fallbackList.as<int>(), h->ctr.as<DeviceCounters>(), st, &h->launches));
 		CU(cudaMemcpyAsync(h->hostCtr, h->ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
 	});
@@ -251,7 +252,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	CU(h->smask.reserve(npix * g.Nw * 4));
 	CU(h->pre.reserve(npix * g.Pw * 4));
 	CU(h->counts.reserve(npix * 4));
-	CU(h->active.reserve(npix));
+	CU(h->active.reserve((size_t)g.H * markingRowWords(g.W) * 4));
 	CU(h->asBits.reserve((size_t)g.H * markingRowWords(g.W) * 4));
 	CU(h->progress.reserve((size_t)(divUp(g.H, 32) + 2) * 4));
 	CU(h->fullList.reserve(npix * 4));
@@ -381,6 +382,10 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 	CU(cudaSetDevice(device));
 	bcd_b200_handle* h = new bcd_b200_handle();
 	h->device = device;
+	{
+		const char* e = getenv("BCD_B200_DENSE_PAIR");
+		g_forceDensePair = e && e[0] == '1';
+	}
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));
 	e = cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking);
@@ -570,7 +575,15 @@ int bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active)
 	if(!h || !active) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
 	if(!h->ran) return fail(BCD_B200_ERR_STATE, "no run yet");
 	CU(cudaSetDevice(h->device));
-	CU(cudaMemcpy(active, h->active.p, (size_t)h->g0.W * h->g0.H, cudaMemcpyDeviceToHost));
+	const int Wp = markingRowWords(h->g0.W);
+	std::vector<uint32_t> bits((size_t)h->g0.H * Wp);
+	CU(cudaMemcpy(bits.data(), h->active.p, bits.size() * 4, cudaMemcpyDeviceToHost));
+	for(int y = 0; y < h->g0.H; ++y)
+		for(int x = 0; x < h->g0.W; ++x)
+		{
+			const int pos = x + MARK_PAD;
+			active[(size_t)y * h->g0.W + x] = (uint8_t)((bits[(size_t)y * Wp + (pos >> 5)] >> (pos & 31)) & 1u);
+		}
 	return 0;
 }
 

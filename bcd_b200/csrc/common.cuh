@@ -55,4 +55,13 @@ __host__ __device__ inline void offsetOf(int j, int b, int& dy, int& dx)
 
 __host__ __device__ inline int divUp(int a, int b) { return (a + b - 1) / b; }
 
+// Bit-rows (AS flags and active flags of the marking stage): row y starts at word y*Wp, column c is bit c + MARK_PAD.
+constexpr int MARK_PAD = 32;
+__host__ __device__ inline int markingRowWords(int W) { return (W + 2 * MARK_PAD + 31) / 32 + 2; }
+__device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)
+{
+	const int pos = x + MARK_PAD;
+	return (bits[(size_t)y * Wp + (pos >> 5)] >> (pos & 31)) & 1u;
+}
+
 } // namespace bcdk

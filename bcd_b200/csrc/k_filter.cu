@@ -424,25 +424,36 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 // ---------------------------------------------------------------------------------------------------------------
 #define MAT(r, c) M[(r) + (c) * n]
 
+// JacobiRotation::makeGivens (Jacobi.h:216-252): c = p/r, s = -q/r with r = sqrt(p^2+q^2) in every branch of the
+// reference (the branches only guard against overflow). The matrix is scaled into [-1,1], so p^2+q^2 cannot
+// overflow; the common range uses rsqrt + one Newton step (<= 1 ulp), tiny magnitudes take the reference's formulas.
 __device__ __forceinline__ void makeGivens(float p, float q, float& c, float& s)
 {
-	if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; }
-	else if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; }
+	if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; return; }
+	if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; return; }
+	const float h2 = fmaf(p, p, q * q);
+	if(h2 > 1e-30f)
+	{
+		float ri = rsqrtf(h2);
+		ri = ri * fmaf(-0.5f * h2, ri * ri, 1.5f);
+		c = p * ri;
+		s = -q * ri;
+	}
 	else if(fabsf(p) > fabsf(q))
 	{
 		const float t = __fdiv_rn(q, p);
-		float u = __fsqrt_rn(__fadd_rn(1.f, __fmul_rn(t, t)));
+		float u = __fsqrt_rn(fmaf(t, t, 1.f));
 		if(p < 0.f) u = -u;
 		c = __fdiv_rn(1.f, u);
-		s = __fmul_rn(-t, c);
+		s = -t * c;
 	}
 	else
 	{
 		const float t = __fdiv_rn(p, q);
-		float u = __fsqrt_rn(__fadd_rn(1.f, __fmul_rn(t, t)));
+		float u = __fsqrt_rn(fmaf(t, t, 1.f));
 		if(q < 0.f) u = -u;
 		s = __fdiv_rn(-1.f, u);
-		c = __fmul_rn(-t, s);
+		c = -t * s;
 	}
 }
 
@@ -613,15 +624,15 @@ __device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
 				float c, s;
 				makeGivens(x, z, c, s);
 				const float dk1 = S.diag[k + 1];
-				const float sdk = s * dk + c * sk;
-				const float dkp1 = s * sk + c * dk1;
-				const float ndk = c * (c * dk - s * sk) - s * (c * sk - s * dk1);
-				const float ndk1 = s * sdk + c * dkp1;
-				const float nsk = c * sdk - s * dkp1;
+				const float sdk = fmaf(s, dk, c * sk);
+				const float dkp1 = fmaf(s, sk, c * dk1);
+				const float ndk = fmaf(c, fmaf(c, dk, -s * sk), -s * fmaf(c, sk, -s * dk1));
+				const float ndk1 = fmaf(s, sdk, c * dkp1);
+				const float nsk = fmaf(c, sdk, -s * dkp1);
 				if(tid == 0)
 				{
 					S.dW[k] = ndk;
-					if(k > start) S.sW[k - 1] = c * skm1 - s * z;
+					if(k > start) S.sW[k - 1] = fmaf(c, skm1, -s * z);
 				}
 				x = nsk;
 				float nsk1 = 0.f;
@@ -634,8 +645,8 @@ __device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
 				if(hasRow)
 				{
 					const float y = MAT(tid, k + 1);
-					MAT(tid, k) = c * qk - s * y;
-					qk = s * qk + c * y;
+					MAT(tid, k) = fmaf(c, qk, -s * y);
+					qk = fmaf(s, qk, c * y);
 				}
 				dk = ndk1;
 				skm1 = nsk;
@@ -679,6 +690,93 @@ __device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
 }
 #undef MAT
 
+// inverseSymmetricMatrix (DenoisingUnit.cpp:578-604) when no eigenvalue needs clamping: V diag(1/l) V^T is then simply
+// A^-1. Fast path: Cholesky A = L L^T in S.O, L^-T in the (free) strict upper triangle of S.M, A^-1 = L^-T L^-1 back in
+// S.O. Accepted only if every pivot is positive and 1/||A^-1||_inf > 2 eps, which proves lambda_min(A) > eps, i.e. that
+// max(eps, lambda) == lambda for every eigenvalue; otherwise the caller runs the reference's eigen path on the intact
+// lower triangle of S.M. Returns true (uniformly) on success.
+#define MAT(r, c) M[(r) + (c) * n]
+#define OUT(r, c) O[(r) + (c) * n]
+template <int NT>
+__device__ bool choleskyInverse(const EigSmem& S, int n, float eps)
+{
+	float* M = S.M;
+	float* O = S.O;
+	const int tid = threadIdx.x;
+	for(int e = tid; e < n * n; e += NT)
+		O[e] = (e % n >= e / n) ? M[e] : 0.f;
+	__syncthreads();
+	bool ok = true;
+	for(int k = 0; k < n; ++k)
+	{
+		const float piv = OUT(k, k);
+		if(!(piv > 0.f) || !(piv < 3e38f)) { ok = false; break; } // uniform: every thread reads the same value
+		const float inv = rsqrtf(piv);
+		const float lkkInv = inv * fmaf(-0.5f * piv, inv * inv, 1.5f);
+		__syncthreads();
+		for(int r = k + tid; r < n; r += NT)
+			OUT(r, k) = r == k ? piv * lkkInv : OUT(r, k) * lkkInv;
+		__syncthreads();
+		for(int c = k + 1 + tid; c < n; c += NT)
+		{
+			const float lck = OUT(c, k);
+			for(int r = c; r < n; ++r)
+				OUT(r, c) = fmaf(-OUT(r, k), lck, OUT(r, c));
+		}
+		__syncthreads();
+	}
+	if(!ok)
+		return false;
+	// X = L^-1 by forward substitution, one column per thread; X(i,j) (i > j) stored at M(j,i), X(j,j) in pv[j]
+	for(int j = tid; j < n; j += NT)
+		S.pv[j] = __fdiv_rn(1.f, OUT(j, j));
+	__syncthreads();
+	for(int j = tid; j < n; j += NT)
+	{
+		const float xjj = S.pv[j];
+		for(int i = j + 1; i < n; ++i)
+		{
+			float a = OUT(i, j) * xjj;
+			for(int k = j + 1; k < i; ++k)
+				a = fmaf(OUT(i, k), MAT(j, k), a);
+			MAT(j, i) = -a * S.pv[i];
+		}
+	}
+	__syncthreads();
+	// A^-1(r,c) = sum_{k >= r} X(k,r) X(k,c)   (r >= c)
+	const int L = n * (n + 1) / 2;
+	for(int e = tid; e < L; e += NT)
+	{
+		int c = 0, r = e;
+		while(r >= n - c) { r -= n - c; ++c; }
+		r += c;
+		float a = S.pv[r] * (r == c ? S.pv[r] : MAT(c, r));
+		for(int k = r + 1; k < n; ++k)
+			a = fmaf(MAT(r, k), MAT(c, k), a);
+		OUT(r, c) = a;
+	}
+	__syncthreads();
+	for(int e = tid; e < n * n; e += NT)
+	{
+		const int r = e % n, c = e / n;
+		if(r < c) O[e] = OUT(c, r);
+	}
+	__syncthreads();
+	float rowMax = 0.f;
+	for(int r = tid; r < n; r += NT)
+	{
+		float a = 0.f;
+		for(int c = 0; c < n; ++c)
+			a += fabsf(OUT(r, c));
+		rowMax = fmaxf(rowMax, a);
+	}
+	const float norm = blockReduceMax<NT>(rowMax, S.red);
+	__syncthreads();
+	return norm < 0.5f / eps && norm == norm;
+}
+#undef MAT
+#undef OUT
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
@@ -720,7 +818,8 @@ k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float*
 			}
 			__syncthreads();
 		}
-		eigFunction<NT>(S, n, 1, eps);
+		if(!choleskyInverse<NT>(S, n, eps))
+			eigFunction<NT>(S, n, 1, eps);
 		for(int e = tid; e < n * n; e += NT)
 			MinvG[(size_t)slot * n * n + e] = S.O[e];
 	}

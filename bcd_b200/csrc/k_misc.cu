@@ -32,27 +32,8 @@ cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float
 	return cudaGetLastError();
 }
 
-// m = 0: every interior pixel is processed (the mask is never consulted, DenoisingUnit.cpp:165-166)
-__global__ void k_all_active(LevelGeom g, unsigned char* __restrict__ active)
-{
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int y = blockIdx.y * blockDim.y + threadIdx.y;
-	if(x >= g.W || y >= g.H)
-		return;
-	const bool interior = x >= g.w && x <= g.W - 1 - g.w && y >= g.w && y <= g.H - 1 - g.w;
-	active[(size_t)y * g.W + x] = interior ? 1 : 0;
-}
-
-cudaError_t launchAllActive(const LevelGeom& g, unsigned char* active, cudaStream_t st, int* launches)
-{
-	dim3 block(32, 8), grid(divUp(g.W, 32), divUp(g.H, 8));
-	k_all_active<<<grid, block, 0, st>>>(g, active);
-	*launches += 1;
-	return cudaGetLastError();
-}
-
 // Work lists of the owned patch centres: full (|S| >= d+1, DenoisingUnit.cpp:182) and fallback.
-__global__ void k_build_lists(const int* __restrict__ counts, const unsigned char* __restrict__ active, LevelGeom g,
+__global__ void k_build_lists(const int* __restrict__ counts, const uint32_t* __restrict__ actBits, int Wp, LevelGeom g,
 		int* __restrict__ fullList, int* __restrict__ fallbackList, DeviceCounters* __restrict__ ctr)
 {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -62,7 +43,7 @@ __global__ void k_build_lists(const int* __restrict__ counts, const unsigned cha
 	const size_t p = in ? (size_t)y * g.W + x : 0;
 	const int n = interior ? counts[p] : 0;
 	const bool strong = interior && n >= g.d + 1;
-	const bool act = interior && active[p] != 0;
+	const bool act = interior && testRowBit(actBits, Wp, y, x);
 	const bool full = act && strong, fb = act && !strong;
 
 	const unsigned lane = (threadIdx.x + blockDim.x * threadIdx.y) & 31;
@@ -95,11 +76,11 @@ __global__ void k_build_lists(const int* __restrict__ counts, const unsigned cha
 		fallbackList[baseFb + __popc(mFb & below)] = (int)p;
 }
 
-cudaError_t launchBuildLists(const int* counts, const unsigned char* active, const LevelGeom& g,
+cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,
 		int* fullList, int* fallbackList, DeviceCounters* ctr, cudaStream_t st, int* launches)
 {
 	dim3 block(32, 8), grid(divUp(g.W, 32), divUp(g.H, 8));
-	k_build_lists<<<grid, block, 0, st>>>(counts, active, g, fullList, fallbackList, ctr);
+	k_build_lists<<<grid, block, 0, st>>>(counts, actBits, Wp, g, fullList, fallbackList, ctr);
 	*launches += 1;
 	return cudaGetLastError();
 }

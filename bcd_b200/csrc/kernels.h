@@ -15,20 +15,20 @@ struct DeviceCounters
 // K0  Denoiser::computePixelCovFromSampleCov
 cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches);
 // K1a/b/c
+extern bool g_forceDensePair;
 cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom& g, float* sP, unsigned char* cP,
 		cudaStream_t st, int* launches);
 cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,
 		uint32_t* mplus, cudaStream_t st, int* launches);
 cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre,
 		cudaStream_t st, int* launches);
-// K2  marking strategy in raster order over the owned rows. asBits: H x Wp bit-rows (column c at bit c + 32),
-// zero (or the upper row tile's hand-off) in the rows above rowBeg on entry; progress: >= ceil(rows/32) counters.
-inline int markingRowWords(int W) { return (W + 64 + 31) / 32 + 2; }
+// K2  marking strategy in raster order over the owned rows. asBits / actBits: H x Wp bit-rows (common.cuh), zeroed by
+// the caller (asBits rows above rowBeg may instead hold the upper row tile's hand-off); progress: >= ceil(rows/32).
 cudaError_t launchMarking(const uint32_t* pre, const LevelGeom& g, float skipProb, uint32_t seed,
-		unsigned char* active, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches);
-cudaError_t launchAllActive(const LevelGeom& g, unsigned char* active, cudaStream_t st, int* launches);
+		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches);
+cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
 // work lists
-cudaError_t launchBuildLists(const int* counts, const unsigned char* active, const LevelGeom& g,
+cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,
 		int* fullList, int* fallbackList, DeviceCounters* ctr, cudaStream_t st, int* launches);
 // K3f denoiseOnlyMainPatch
 cudaError_t launchFallback(const float* color, const uint32_t* smask, const int* counts, const LevelGeom& g,

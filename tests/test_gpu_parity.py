@@ -109,3 +109,59 @@ def test_invalid_inputs_are_rejected(capi, crop_c):
         capi.denoise(**inp, b=0)
     with pytest.raises(capi.BcdError):
         capi.denoise(**inp, scales=0)
+
+
+@pytest.mark.parametrize("nb_bins", [7, 24, 22])  # B = 21 (sparse kernel, odd depth), 72 (dense tiled), 66 (generic)
+def test_other_histogram_depths(capi, nb_bins):
+    from bcd_b200 import host
+    inp = host.synth(56, 44, spp=24, nb_bins=nb_bins)
+    h, out = _run(capi, inp, m=1.0)
+    masks, counts = h.read_selection()
+    active = h.read_active()
+    h.close()
+    ref_masks, ref_counts = O.port_select(inp["hist"], inp["nsamples"])
+    assert int(np.unpackbits((masks ^ ref_masks).view(np.uint8)).sum()) == 0
+    assert np.array_equal(counts, ref_counts)
+    assert np.array_equal(active, O.port_marking(ref_masks, ref_counts))
+    assert O.rel_linf(out, O.port_denoise(**inp, m=1.0)) <= TOL
+
+
+def test_dense_pair_kernel_path(capi, crop_a, monkeypatch):
+    monkeypatch.setenv("BCD_B200_DENSE_PAIR", "1")
+    h, _ = _run(capi, inputs_of(crop_a), m=0.0)
+    masks, counts = h.read_selection()
+    h.close()
+    monkeypatch.setenv("BCD_B200_DENSE_PAIR", "0")
+    capi.Handle(0).close()  # reset the process-wide hook
+    assert int(np.unpackbits((masks ^ crop_a["port_masks"]).view(np.uint8)).sum()) == 0
+
+
+@pytest.mark.parametrize("b", [10, 3])
+def test_other_search_radii_bit_exact(capi, crop_b, b):
+    inp = inputs_of(crop_b)
+    h, out = _run(capi, inp, m=1.0, b=b)
+    masks, counts = h.read_selection()
+    active = h.read_active()
+    h.close()
+    ref_masks, ref_counts = O.port_select(inp["hist"], inp["nsamples"], b=b)
+    assert int(np.unpackbits((masks ^ ref_masks).view(np.uint8)).sum()) == 0
+    assert np.array_equal(active, O.port_marking(ref_masks, ref_counts, b=b))
+    assert O.rel_linf(out, O.port_denoise(**inp, m=1.0, b=b)) <= TOL
+
+
+def test_fractional_skip_probability_is_deterministic(capi, crop_b):
+    inp = inputs_of(crop_b)
+    h, out1 = _run(capi, inp, m=0.5)
+    s1 = h.stats()
+    h.close()
+    h, out2 = _run(capi, inp, m=0.5)
+    s2 = h.stats()
+    h.close()
+    assert s1 == s2 and O.rel_linf(out1, out2) <= 1e-5
+    h, _ = _run(capi, inp, m=1.0)
+    sm1 = h.stats()
+    h.close()
+    h, _ = _run(capi, inp, m=0.0)
+    sm0 = h.stats()
+    h.close()
+    assert sm1["active"] <= s1["active"] <= sm0["active"]
