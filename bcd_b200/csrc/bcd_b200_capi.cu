@@ -158,14 +158,15 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	});
 	STAGE(h, BCD_B200_STAGE_SELECT, {
 		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
+		CU(cudaMemsetAsync(h->pre.p, 0, (size_t)g.H * prePitchOf(g.W) * g.Pw * 4, st));
 		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, h->smask.as<uint32_t>(), h->counts.as<int>(),
-				h->pre.as<uint32_t>(), st, &h->launches));
+				h->pre.as<uint32_t>(), prePitchOf(g.W), st, &h->launches));
 	});
 	STAGE(h, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
 		{
 			CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
-			CU(launchMarking(h->pre.as<uint32_t>(), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<uint32_t>(),
+			CU(launchMarking(h->pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<uint32_t>(),
 					h->asBits.as<uint32_t>(), Wp, h->progress.as<unsigned int>(), st, &h->launches));
 		}
 		else
@@ -250,7 +251,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	CU(h->cP.reserve(npix * g.J));
 	CU(h->mplus.reserve(npix * g.Jw * 4));
 	CU(h->smask.reserve(npix * g.Nw * 4));
-	CU(h->pre.reserve(npix * g.Pw * 4));
+	CU(h->pre.reserve((size_t)g.H * prePitchOf(g.W) * g.Pw * 4 + 64));
 	CU(h->counts.reserve(npix * 4));
 	CU(h->active.reserve((size_t)g.H * markingRowWords(g.W) * 4));
 	CU(h->asBits.reserve((size_t)g.H * markingRowWords(g.W) * 4));
@@ -385,6 +386,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 	{
 		const char* e = getenv("BCD_B200_DENSE_PAIR");
 		g_forceDensePair = e && e[0] == '1';
+		e = getenv("BCD_B200_GENERIC_MARKING");
+		g_forceGenericMarking = e && e[0] == '1';
 	}
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));

@@ -57,7 +57,10 @@ __host__ __device__ inline int divUp(int a, int b) { return (a + b - 1) / b; }
 
 // Bit-rows (AS flags and active flags of the marking stage): row y starts at word y*Wp, column c is bit c + MARK_PAD.
 constexpr int MARK_PAD = 32;
-__host__ __device__ inline int markingRowWords(int W) { return (W + 2 * MARK_PAD + 31) / 32 + 2; }
+// (odd word count: lanes of the marking kernel read different rows at nearby word indices -> distinct banks)
+__host__ __device__ inline int markingRowWords(int W) { return ((W + 2 * MARK_PAD + 31) / 32 + 2) | 1; }
+// `pre` rows are pitched to a multiple of 4 pixels so that 4-pixel groups are 16-byte aligned (cp.async 16)
+__host__ __device__ inline int prePitchOf(int W) { return (W + 3) & ~3; }
 __device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)
 {
 	const int pos = x + MARK_PAD;
