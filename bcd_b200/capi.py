@@ -21,6 +21,10 @@ SYMBOLS = [
     "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_upload",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
+    # row-tile API (multi-GPU), wrapped by bcd_b200/tiles.py
+    "bcd_b200_tile_plan", "bcd_b200_tile_begin", "bcd_b200_tile_select", "bcd_b200_tile_mark", "bcd_b200_tile_filter",
+    "bcd_b200_tile_finalize", "bcd_b200_tile_merge", "bcd_b200_tile_xfer_bytes", "bcd_b200_tile_export",
+    "bcd_b200_tile_import", "bcd_b200_tile_end", "bcd_b200_tile_download",
 ]
 
 

@@ -99,6 +99,12 @@ struct bcd_b200_handle
 	size_t eventsUsed = 0;
 	int launches = 0;
 	DeviceCounters* hostCtr = nullptr; // pinned
+	// row-tile mode (multi-GPU): the resident inputs are rows [subRow0, subRow1) of an imageH-row frame and this
+	// handle produces the output rows [ownRow0, ownRow1) (frame coordinates)
+	bool tiled = false;
+	int imageH = 0, subRow0 = 0, subRow1 = 0, ownRow0 = 0, ownRow1 = 0;
+	bcd_b200_params runParams;
+	DeviceCounters levelCtr; // counters of the level being processed
 };
 
 namespace
@@ -137,20 +143,49 @@ int stageEnd(bcd_b200_handle* h)
 		if(rc_) return rc_; \
 	} while(0)
 
-int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+// Geometry of level k as seen by this handle. Single GPU: the whole level. Row tile: the local sub-image with the
+// owned patch-centre rows [rowBeg, rowEnd) and the rows [yLo, yHi) on which the selection stage has to run
+// (owned rows +- (b + w): S(p) of an owned p needs the half masks of the b rows above, whose pair terms reach w
+// further; the filter gathers colours b + w rows around the owned rows).
+LevelGeom levelGeom(const bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	const LevelBufs& L = h->levels[k];
+	LevelGeom g = makeGeom(L.W, L.H, h->B, p.patch_radius, p.search_radius);
+	if(h->tiled)
+	{
+		const int own0 = (h->ownRow0 - h->subRow0) >> k;
+		const int own1 = h->ownRow1 >= h->imageH ? L.H : (h->ownRow1 - h->subRow0) >> k;
+		g.rowBeg = std::max(g.w, own0);
+		g.rowEnd = std::min(L.H - g.w, own1);
+		g.yLo = std::max(0, own0 - (g.b + g.w));
+		g.yHi = std::min(L.H, own1 + (g.b + g.w));
+	}
+	return g;
+}
+
+void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1)
+{
+	const LevelBufs& L = h->levels[k];
+	if(!h->tiled) { own0 = 0; own1 = L.H; return; }
+	own0 = (h->ownRow0 - h->subRow0) >> k;
+	own1 = h->ownRow1 >= h->imageH ? L.H : (h->ownRow1 - h->subRow0) >> k;
+}
+
+// stage 1: prepass + distance/selection (K0, K1a-c); clears the accumulators and bit-rows of the level
+int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
-	LevelGeom g = makeGeom(L.W, L.H, h->B, p.patch_radius, p.search_radius);
+	const LevelGeom g = levelGeom(h, k, p);
 	if(k == 0)
 		h->g0 = g;
 	cudaStream_t st = h->stream;
 	const size_t npix = (size_t)g.W * g.H;
 	const int Wp = markingRowWords(g.W);
-
 	STAGE(h, BCD_B200_STAGE_PREPASS, {
 		CU(launchPixelCov(L.cov, L.ns, npix, h->pixcov.as<float>(), st, &h->launches));
 		CU(cudaMemsetAsync(h->acc.p, 0, npix * sizeof(float4), st));
 		CU(cudaMemsetAsync(h->active.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
+		CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
 		CU(cudaMemsetAsync(h->ctr.p, 0, sizeof(DeviceCounters), st));
 	});
 	STAGE(h, BCD_B200_STAGE_PAIR, {
@@ -158,17 +193,25 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	});
 	STAGE(h, BCD_B200_STAGE_SELECT, {
 		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
-		CU(cudaMemsetAsync(h->pre.p, 0, (size_t)g.H * prePitchOf(g.W) * g.Pw * 4, st));
+		const bool fastLayout = markingUsesFastLayout(g.b);
+		const int preWords = fastLayout ? fastMarkWords(g.b) : g.Pw;
+		CU(cudaMemsetAsync(h->pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, st));
 		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, h->smask.as<uint32_t>(), h->counts.as<int>(),
-				h->pre.as<uint32_t>(), prePitchOf(g.W), st, &h->launches));
+				h->pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches));
 	});
+	return 0;
+}
+
+// stage 2: marking strategy (K2) over the owned rows + work lists; reads the counters back (one host sync)
+int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	const LevelGeom g = levelGeom(h, k, p);
+	cudaStream_t st = h->stream;
+	const int Wp = markingRowWords(g.W);
 	STAGE(h, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
-		{
-			CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
 			CU(launchMarking(h->pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<uint32_t>(),
 					h->asBits.as<uint32_t>(), Wp, h->progress.as<unsigned int>(), st, &h->launches));
-		}
 		else
 			CU(launchAllActive(g, h->active.as<uint32_t>(), Wp, st, &h->launches));
 		CU(launchBuildLists(h->counts.as<int>(), h->active.as<uint32_t>(), Wp, g, h->fullList.as<int>(),
@@ -177,13 +220,23 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	});
 	CU(cudaStreamSynchronize(st));
 	const DeviceCounters c = *h->hostCtr;
+	h->levelCtr = c;
 	h->stats.interior += (int64_t)c.interior;
 	h->stats.strong += (int64_t)c.strong;
 	h->stats.active += (int64_t)c.active;
 	h->stats.full += (int64_t)c.full;
 	h->stats.fallback += (int64_t)c.fallback;
 	h->stats.sum_n_full += (int64_t)c.sum_n_full;
+	return 0;
+}
 
+// stage 3: fallback mean + two-step Bayesian filter, accumulated into acc
+int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	cudaStream_t st = h->stream;
+	const DeviceCounters c = h->levelCtr;
 	STAGE(h, BCD_B200_STAGE_FALLBACK, {
 		if(c.nFallback > 0)
 			CU(launchFallback(L.color, h->smask.as<uint32_t>(), h->counts.as<int>(), g, h->fallbackList.as<int>(),
@@ -212,9 +265,63 @@ int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		h->timings.stage_ms[BCD_B200_STAGE_FILTER_EIG] += ms[1];
 		h->timings.stage_ms[BCD_B200_STAGE_FILTER_APPLY] += ms[2];
 	}
+	return 0;
+}
+
+// stage 4: out = sum / count
+int levelFinalize(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
 	STAGE(h, BCD_B200_STAGE_FINALIZE, {
-		CU(launchFinalize(h->acc.as<float4>(), npix, L.out.as<float>(), st, &h->launches));
+		CU(launchFinalize(h->acc.as<float4>(), (size_t)g.W * g.H, L.out.as<float>(), h->stream, &h->launches));
 	});
+	return 0;
+}
+
+int levelMerge(bcd_b200_handle* h, int k)
+{
+	STAGE(h, BCD_B200_STAGE_PYRAMID, {
+		CU(launchMerge(h->levels[k].out.as<float>(), h->levels[k].W, h->levels[k].H, h->levels[k + 1].out.as<float>(),
+				h->tmpLow.as<float>(), h->stream, &h->launches));
+	});
+	return 0;
+}
+
+int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	int rc;
+	if((rc = levelSelect(h, k, p))) return rc;
+	if((rc = levelMark(h, k, p))) return rc;
+	if((rc = levelFilter(h, k, p))) return rc;
+	return levelFinalize(h, k, p);
+}
+
+int buildPyramid(bcd_b200_handle* h, int s)
+{
+	if(s > 1)
+		STAGE(h, BCD_B200_STAGE_PYRAMID, {
+			for(int k = 1; k < s; ++k)
+			{
+				const LevelBufs& Lp = h->levels[k - 1];
+				LevelBufs& L = h->levels[k];
+				CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
+						L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches));
+			}
+		});
+	return 0;
+}
+
+int collectTimings(bcd_b200_handle* h)
+{
+	for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
+	{
+		float ms = 0.f;
+		CU(cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]));
+		h->timings.stage_ms[h->eventStage[i / 2]] += ms;
+	}
+	CU(cudaEventElapsedTime(&h->timings.total_ms, h->evTotal[0], h->evTotal[1]));
+	h->stats.kernel_launches = h->launches;
 	return 0;
 }
 
@@ -251,7 +358,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	CU(h->cP.reserve(npix * g.J));
 	CU(h->mplus.reserve(npix * g.Jw * 4));
 	CU(h->smask.reserve(npix * g.Nw * 4));
-	CU(h->pre.reserve((size_t)g.H * prePitchOf(g.W) * g.Pw * 4 + 64));
+	CU(h->pre.reserve((size_t)g.H * prePitchOf(g.W) * std::max(g.Pw, fastMarkWords(g.b)) * 4 + 64));
 	CU(h->counts.reserve(npix * 4));
 	CU(h->active.reserve((size_t)g.H * markingRowWords(g.W) * 4));
 	CU(h->asBits.reserve((size_t)g.H * markingRowWords(g.W) * 4));
@@ -489,16 +596,10 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	CU(cudaEventRecord(h->evTotal[0], st));
 	if(progress) progress(0.f, user);
 	// pyramid build (MultiscaleDenoiser.cpp:41-48)
-	if(s > 1)
-		STAGE(h, BCD_B200_STAGE_PYRAMID, {
-			for(int k = 1; k < s; ++k)
-			{
-				const LevelBufs& Lp = h->levels[k - 1];
-				LevelBufs& L = h->levels[k];
-				CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
-						L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), st, &h->launches));
-			}
-		});
+	h->tiled = false;
+	h->runParams = *p;
+	rc = buildPyramid(h, s);
+	if(rc) return rc;
 	// coarsest to finest (MultiscaleDenoiser.cpp:79-134); progress mapped like :85,:103-112
 	const float total = float(((1 << (2 * s)) - 1) / 3);
 	for(int k = s - 1; k >= 0; --k)
@@ -506,10 +607,10 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 		rc = denoiseLevel(h, k, *p);
 		if(rc) return rc;
 		if(k < s - 1)
-			STAGE(h, BCD_B200_STAGE_PYRAMID, {
-				CU(launchMerge(h->levels[k].out.as<float>(), h->levels[k].W, h->levels[k].H, h->levels[k + 1].out.as<float>(),
-						h->tmpLow.as<float>(), st, &h->launches));
-			});
+		{
+			rc = levelMerge(h, k);
+			if(rc) return rc;
+		}
 		if(progress)
 		{
 			const int sdone = s - 1 - k;
@@ -518,14 +619,8 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	}
 	CU(cudaEventRecord(h->evTotal[1], st));
 	CU(cudaStreamSynchronize(st));
-	for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
-	{
-		float ms = 0.f;
-		CU(cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]));
-		h->timings.stage_ms[h->eventStage[i / 2]] += ms;
-	}
-	CU(cudaEventElapsedTime(&h->timings.total_ms, h->evTotal[0], h->evTotal[1]));
-	h->stats.kernel_launches = h->launches;
+	rc = collectTimings(h);
+	if(rc) return rc;
 	h->ran = true;
 	return 0;
 }
@@ -587,6 +682,184 @@ int bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active)
 			const int pos = x + MARK_PAD;
 			active[(size_t)y * h->g0.W + x] = (uint8_t)((bits[(size_t)y * Wp + (pos >> 5)] >> (pos & 31)) & 1u);
 		}
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// row-tile API
+// ---------------------------------------------------------------------------------------------------------------
+int bcd_b200_tile_plan(int image_width, int image_height, int tile_index, int tile_count, const bcd_b200_params* p,
+		bcd_b200_tile* out)
+{
+	int rc = checkParams(p);
+	if(rc) return rc;
+	if(!out || image_width <= 0 || image_height <= 0 || tile_count < 1 || tile_index < 0 || tile_index >= tile_count)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad tile request (%d of %d, %dx%d)", tile_index, tile_count, image_width, image_height);
+	const int align = 1 << (p->nb_scales - 1);            // band boundaries fall on the same rows at every level
+	const int halo = (p->search_radius + p->patch_radius) * align;
+	const int units = (image_height + align - 1) / align; // rows in units of `align`
+	auto boundary = [&](int t) { return (int)std::min<long long>((long long)image_height, ((long long)units * t / tile_count) * align); };
+	const int r0 = tile_index == 0 ? 0 : boundary(tile_index);
+	const int r1 = tile_index == tile_count - 1 ? image_height : boundary(tile_index + 1);
+	// every level must keep at least b+w owned rows (contributions never reach beyond the direct neighbour)
+	if(tile_count > 1 && ((r1 - r0) >> (p->nb_scales - 1)) < p->search_radius + p->patch_radius + 2)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "tile %d has too few rows (%d) for %d scales and b+w=%d", tile_index, r1 - r0,
+				p->nb_scales, p->search_radius + p->patch_radius);
+	out->image_width = image_width;
+	out->image_height = image_height;
+	out->own_row0 = r0;
+	out->own_row1 = r1;
+	out->sub_row0 = std::max(0, r0 - halo);
+	out->sub_row1 = std::min(image_height, r1 + halo);
+	out->tile_index = tile_index;
+	out->tile_count = tile_count;
+	return 0;
+}
+
+int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t)
+{
+	if(!h || !t) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / tile");
+	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "tile_begin called before upload/bind_device");
+	int rc = checkParams(p);
+	if(rc) return rc;
+	if(t->sub_row1 - t->sub_row0 != h->H || t->image_width != h->W)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "resident inputs are %dx%d but the tile needs %dx%d", h->W, h->H,
+				t->image_width, t->sub_row1 - t->sub_row0);
+	CU(cudaSetDevice(h->device));
+	rc = ensureBuffers(h, *p);
+	if(rc) return rc;
+	memset(&h->stats, 0, sizeof(h->stats));
+	memset(&h->timings, 0, sizeof(h->timings));
+	h->eventsUsed = 0;
+	h->launches = 0;
+	h->tiled = t->tile_count > 1;
+	h->imageH = t->image_height;
+	h->subRow0 = t->sub_row0; h->subRow1 = t->sub_row1;
+	h->ownRow0 = t->own_row0; h->ownRow1 = t->own_row1;
+	h->runParams = *p;
+	h->ran = false;
+	CU(cudaEventRecord(h->evTotal[0], h->stream));
+	return buildPyramid(h, p->nb_scales);
+}
+
+#define TILE_GUARD(h, level) \
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle"); \
+	if(level < 0 || level >= h->runParams.nb_scales) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad level %d", level); \
+	CU(cudaSetDevice(h->device));
+
+int bcd_b200_tile_select(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelSelect(h, level, h->runParams); }
+int bcd_b200_tile_mark(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMark(h, level, h->runParams); }
+int bcd_b200_tile_filter(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFilter(h, level, h->runParams); }
+int bcd_b200_tile_finalize(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFinalize(h, level, h->runParams); }
+int bcd_b200_tile_merge(bcd_b200_handle* h, int level)
+{
+	TILE_GUARD(h, level);
+	if(level >= h->runParams.nb_scales - 1) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "the coarsest level is not merged");
+	return levelMerge(h, level);
+}
+
+namespace
+{
+// rows (count, bytes per row, base pointer) of the strip; exportSide: rows sent to `side`; import: rows received
+struct Strip { char* base; size_t rowBytes; int rows; int exportRow[2]; int importRow[2]; };
+
+int stripOf(bcd_b200_handle* h, int level, int what, Strip& s)
+{
+	const bcd_b200_params& p = h->runParams;
+	const LevelBufs& L = h->levels[level];
+	int own0, own1;
+	tileOwnedRows(h, level, own0, own1);
+	const int bw = p.search_radius + p.patch_radius;
+	switch(what)
+	{
+	case BCD_B200_XFER_ACC_HALO: // partial sums accumulated outside my band go to their owner and are ADDED there
+		s.base = (char*)h->acc.p; s.rowBytes = (size_t)L.W * sizeof(float4); s.rows = bw;
+		s.exportRow[BCD_B200_SIDE_UP] = own0 - bw; s.exportRow[BCD_B200_SIDE_DOWN] = own1;
+		s.importRow[BCD_B200_SIDE_UP] = own0;      s.importRow[BCD_B200_SIDE_DOWN] = own1 - bw;
+		break;
+	case BCD_B200_XFER_AS_ROWS: // AS bit-rows of my last b owned rows feed the marking of the band below
+		s.base = (char*)h->asBits.p; s.rowBytes = (size_t)markingRowWords(L.W) * 4; s.rows = p.search_radius;
+		s.exportRow[BCD_B200_SIDE_UP] = own0;                    s.exportRow[BCD_B200_SIDE_DOWN] = own1 - p.search_radius;
+		s.importRow[BCD_B200_SIDE_UP] = own0 - p.search_radius;  s.importRow[BCD_B200_SIDE_DOWN] = own1;
+		break;
+	case BCD_B200_XFER_OUT_ROWS: // 2 output rows each way (downscale + interpolate of the merge reach 2 rows)
+		s.base = (char*)L.out.p; s.rowBytes = (size_t)L.W * 3 * sizeof(float); s.rows = 2;
+		s.exportRow[BCD_B200_SIDE_UP] = own0;      s.exportRow[BCD_B200_SIDE_DOWN] = own1 - 2;
+		s.importRow[BCD_B200_SIDE_UP] = own0 - 2;  s.importRow[BCD_B200_SIDE_DOWN] = own1;
+		break;
+	default:
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "unknown strip %d", what);
+	}
+	return 0;
+}
+}
+
+int bcd_b200_tile_xfer_bytes(bcd_b200_handle* h, int level, int what, size_t* bytes)
+{
+	TILE_GUARD(h, level);
+	if(!bytes) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null output");
+	Strip s;
+	int rc = stripOf(h, level, what, s);
+	if(rc) return rc;
+	*bytes = s.rowBytes * s.rows;
+	return 0;
+}
+
+int bcd_b200_tile_export(bcd_b200_handle* h, int level, int what, int side, void* dev_buf)
+{
+	TILE_GUARD(h, level);
+	if(!dev_buf || side < 0 || side > 1) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad export arguments");
+	Strip s;
+	int rc = stripOf(h, level, what, s);
+	if(rc) return rc;
+	const int row = s.exportRow[side];
+	if(row < 0 || row + s.rows > h->levels[level].H)
+		return fail(BCD_B200_ERR_STATE, "export strip rows [%d,%d) outside the resident band (no neighbour on that side?)", row, row + s.rows);
+	CU(cudaMemcpyAsync(dev_buf, s.base + (size_t)row * s.rowBytes, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->stream));
+	return 0;
+}
+
+int bcd_b200_tile_import(bcd_b200_handle* h, int level, int what, int side, const void* dev_buf)
+{
+	TILE_GUARD(h, level);
+	if(!dev_buf || side < 0 || side > 1) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad import arguments");
+	Strip s;
+	int rc = stripOf(h, level, what, s);
+	if(rc) return rc;
+	const int row = s.importRow[side];
+	if(row < 0 || row + s.rows > h->levels[level].H)
+		return fail(BCD_B200_ERR_STATE, "import strip rows [%d,%d) outside the resident band", row, row + s.rows);
+	char* dst = s.base + (size_t)row * s.rowBytes;
+	if(what == BCD_B200_XFER_ACC_HALO)
+		CU(launchAddStrip(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(dev_buf),
+				s.rowBytes * s.rows / sizeof(float4), h->stream, &h->launches));
+	else
+		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->stream));
+	return 0;
+}
+
+int bcd_b200_tile_end(bcd_b200_handle* h)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	CU(cudaSetDevice(h->device));
+	CU(cudaEventRecord(h->evTotal[1], h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	int rc = collectTimings(h);
+	if(rc) return rc;
+	h->ran = true;
+	return 0;
+}
+
+int bcd_b200_tile_download(bcd_b200_handle* h, float* out_rows)
+{
+	if(!h || !out_rows) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	if(!h->ran) return fail(BCD_B200_ERR_STATE, "tile_download called before tile_end");
+	CU(cudaSetDevice(h->device));
+	int own0, own1;
+	tileOwnedRows(h, 0, own0, own1);
+	const size_t rowBytes = (size_t)h->W * 3 * sizeof(float);
+	CU(cudaMemcpyAsync(out_rows, (char*)h->levels[0].out.p + (size_t)own0 * rowBytes, rowBytes * (own1 - own0), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
 	return 0;
 }
 

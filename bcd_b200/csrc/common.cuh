@@ -24,6 +24,7 @@ struct LevelGeom
 	int np;          // (2w+1)^2    pixels per patch
 	int d;           // 3*np        colour patch dimension
 	int rowBeg, rowEnd; // owned patch-centre rows [rowBeg, rowEnd) (subset of the interior rows)
+	int yLo, yHi;       // rows on which the selection stage (K1) runs; [0, H) unless this is a row tile
 };
 
 inline LevelGeom makeGeom(int W, int H, int B, int w, int b)
@@ -41,6 +42,8 @@ inline LevelGeom makeGeom(int W, int H, int B, int w, int b)
 	g.d = 3 * g.np;
 	g.rowBeg = w;
 	g.rowEnd = H - w;
+	g.yLo = 0;
+	g.yHi = H;
 	return g;
 }
 
@@ -59,6 +62,12 @@ __host__ __device__ inline int divUp(int a, int b) { return (a + b - 1) / b; }
 constexpr int MARK_PAD = 32;
 // (odd word count: lanes of the marking kernel read different rows at nearby word indices -> distinct banks)
 __host__ __device__ inline int markingRowWords(int W) { return ((W + 2 * MARK_PAD + 31) / 32 + 2) | 1; }
+// words per pixel of the fast marking layout `pre2` (b = 6: 4, b = 10: 12, b = 14: 16); see k_marking_fast
+__host__ __device__ inline int fastMarkWords(int b)
+{
+	const int fw = 2 * b + 4, fpw = fw <= 16 ? 2 : 1, nf = (b + fpw - 1) / fpw;
+	return (nf + 1 + 3) & ~3;
+}
 // `pre` rows are pitched to a multiple of 4 pixels so that 4-pixel groups are 16-byte aligned (cp.async 16)
 __host__ __device__ inline int prePitchOf(int W) { return (W + 3) & ~3; }
 __device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)

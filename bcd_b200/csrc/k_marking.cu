@@ -63,7 +63,7 @@ k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, f
 	const int r0 = g.rowBeg + band * 32;
 	const int r = r0 + lane;
 	const bool rowValid = r < g.rowEnd;
-	const uint32_t thr = skipProb >= 1.f ? 0xffffffffu : (uint32_t)(skipProb * 4294967296.f);
+	const uint32_t thr = (uint32_t)(fminf(skipProb, 0.99999994f) * 4294967296.f);
 	const bool always = skipProb >= 1.f;
 	const int centreBit = b * side + b;
 	const int lastLane = min(31, g.rowEnd - 1 - r0); // lane of the last valid row of the band
@@ -158,7 +158,7 @@ k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, f
 			strongBit = (pw[centreBit >> 5] >> (centreBit & 31)) & 1u;
 		}
 		const bool centre = valid && r >= w && r <= H - 1 - w && c >= w && c <= W - 1 - w;
-		const bool skipIfMarked = always || hash32((uint32_t)r, (uint32_t)c, seed) < thr;
+		const bool skipIfMarked = always || hash32((uint32_t)r, (uint32_t)c, seed) <= thr;
 		const bool act = centre && !(hit != 0u && skipIfMarked);
 		const uint32_t as = (act && strongBit) ? 1u : 0u;
 		if(valid)
@@ -197,29 +197,38 @@ k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, f
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fast kernel (b = 6, 10, 14): PX = 4 pixels per lane-step. Lane l handles columns C..C+3, C = 4 (t - 3 l): the
-// lane above is 12 columns ahead, which covers the b-column look-ahead of the last pixel of the block (b + 4 <= 12
-// needs b <= 8; for b = 10, 14 the skew grows to 4 and 5 steps). One funnel shift per row above yields the 2b+4
-// bits all four pixels need; the 4 x Pw `pre` words of the block arrive as Pw LDS.128 from a cp.async-fed tile
-// (16-byte copies: `pre` rows are pitched to a multiple of 4 pixels). The sequential part is only the same-row
-// chain (4 x ~5 dependent ALU ops); everything else is independent work for the single resident warp.
-// Total dependent steps ~ (W + 4 SKS H) / 4 instead of W + (b+2) H.
+// Fast kernel (b = 6, 10, 14): PX = 4 pixels per lane-step. Lane l handles columns C..C+3, C = 4 (t - SKS l): the lane
+// above is 4 SKS >= b + 4 columns ahead, which covers the b-column look-ahead of the last pixel of the block.
+// The single resident warp is latency-bound (every instruction waits ~4 cycles for its predecessor), so the kernel
+// is written for minimum instruction count per step:
+//   * the per-pixel input comes in the `pre2` layout written by k_symmetrize (fastMarkWords(b) words per pixel): the
+//     (2b+1)-bit mask of each row above, already shifted left by (x & 3) and packed FPW fields per word, so that
+//     hit(pixel i) = OR_a (win2[a] & pre2[i][a]) costs one LOP3 per word — win2 packs the funnel-shifted AS windows
+//     of FPW rows the same way (one PRMT per pair of rows for b = 6);
+//   * one LDS.128 per pixel (b = 6) feeds it, from a cp.async-fed double-buffered tile (16-byte copies);
+//   * the only sequential part is the same-row chain (4 x ~6 dependent ALU ops).
+// Total dependent steps ~ W/4 + SKS*H.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BT>
+template <int BT, bool ALWAYS>
 __global__ void __launch_bounds__(32)
-k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
+k_marking_fast(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
 		uint32_t* __restrict__ actBits, uint32_t* asBits, int Wp, unsigned int* progress)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
-	constexpr int b = BT, side = 2 * BT + 1;
+	constexpr int b = BT;
 	constexpr int PX = 4;
-	constexpr int SKS = (BT + PX + PX - 1) / PX + 0; // steps of skew: 4*SKS >= b + 4
-	constexpr int SKC = PX * SKS;                    // columns of skew
-	constexpr int PWT = (BT * side + BT + 1 + 31) / 32;
-	constexpr int CHS = 8;                           // steps per `pre` chunk (32 pixels per row)
-	constexpr int RS = CHS * PX * PWT + 4;           // tile row stride in words (== 4 mod 32: LDS.128 conflict-free)
-	constexpr int centreBit = BT * side + BT;
+	constexpr int SKS = (BT + PX + PX - 1) / PX; // steps of skew: 4*SKS >= b + 4
+	constexpr int SKC = PX * SKS;                // columns of skew
+	constexpr int FW = 2 * BT + 1 + 3;           // bits of a shifted row field
+	constexpr int FPW = FW <= 16 ? 2 : 1;        // fields per word
+	constexpr int NF = (BT + FPW - 1) / FPW;     // words holding the rows above
+	constexpr int PW2 = (NF + 1 + 3) & ~3;       // words per pixel (the word NF holds the same-row bits + strong flag)
+	constexpr int CHS = 8;                       // steps per chunk (32 pixels per row)
+	constexpr int RS = CHS * PX * PW2 + 4;       // tile row stride in words (== 4 mod 32: LDS.128 conflict-free)
+	constexpr int UNITS = CHS * PX * PW2 / 4;    // 16-byte units per tile row
+	constexpr int UPL = UNITS * (32 / CHS) / 32; // units per lane per step
 	static_assert(2 * BT + PX <= 32, "window must fit one funnel shift");
+	static_assert((UNITS * (32 / CHS)) % 32 == 0, "units must split evenly over the lanes");
 	const int W = g.W, H = g.H, w = g.w;
 	uint32_t* asS = smem;                                                // [(32 + b)][Wp]
 	uint32_t* preS = smem + (((size_t)(32 + b) * Wp + 3) & ~(size_t)3);  // [2][32][RS], 16-byte aligned
@@ -228,8 +237,8 @@ k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, floa
 	const int r0 = g.rowBeg + band * 32;
 	const int r = r0 + lane;
 	const bool rowValid = r < g.rowEnd;
-	const uint32_t thr = skipProb >= 1.f ? 0xffffffffu : (uint32_t)(skipProb * 4294967296.f);
-	const bool always = skipProb >= 1.f;
+	const bool rowCentre = rowValid && r >= w && r <= H - 1 - w;
+	const uint32_t thr = (uint32_t)(fminf(skipProb, 0.99999994f) * 4294967296.f);
 	const int lastLane = min(31, g.rowEnd - 1 - r0);
 	const int nBlocks = (W + PX - 1) / PX;
 	const int tEnd = nBlocks + SKS * 31;
@@ -238,29 +247,32 @@ k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, floa
 	for(int e = lane; e < (32 + b) * Wp; e += 32)
 		asS[e] = 0u;
 
-	// chunk q of row l covers pixels [32 q - SKC l, +32): 8*PWT 16-byte units per row
-	auto issueRows = [&](int q, int lFirst, int nRows)
+	// per-lane constants of the prefetch: unit u = lane + 32 i of the 4 rows issued per step
+	int uRow[UPL], uWord[UPL];
+#pragma unroll
+	for(int i = 0; i < UPL; ++i)
 	{
-		constexpr int UNITS = CHS * PX * PWT / 4; // per row
-		for(int u = lane; u < nRows * UNITS; u += 32)
+		const int u = lane + 32 * i;
+		uRow[i] = u / UNITS;
+		uWord[i] = 4 * (u % UNITS);
+	}
+	// rows [lFirst, lFirst + 4) of chunk q: row l covers pixels [32 q - SKC l, +32)
+	auto issueRows = [&](int q, int lFirst)
+	{
+#pragma unroll
+		for(int i = 0; i < UPL; ++i)
 		{
-			const int l = lFirst + u / UNITS, v = u - (u / UNITS) * UNITS;
+			const int l = lFirst + uRow[i];
 			const int rr = r0 + l;
-			const int c = CHS * PX * q - SKC * l + (4 * v) / PWT;   // pixel of the first word of this unit
-			const int wordInRow = 4 * v;                            // word offset inside the 32-pixel segment
-			const bool ok = rr < g.rowEnd && c >= 0 && c < prePitch;
-			// a unit never straddles the segment: offsets below are in words relative to the segment start
-			const int segStart = CHS * PX * q - SKC * l;
-			const uint32_t* src = ok ? pre + ((size_t)rr * prePitch + segStart) * PWT + wordInRow : pre;
-			uint32_t* dst = preS + (size_t)(q & 1) * 32 * RS + (size_t)l * RS + wordInRow;
-			// the segment may start left of the image or end right of the pitch: whole units only when the first
-			// and last word are inside
-			const int cLast = segStart + (wordInRow + 3) / PWT;
-			const bool inside = ok && segStart + wordInRow / PWT >= 0 && cLast < prePitch;
-			__pipeline_memcpy_async(dst, inside ? src : pre, 16, inside ? 0 : 16);
+			const int px = CHS * PX * q - SKC * l + uWord[i] / PW2; // a unit never straddles a pixel: PW2 % 4 == 0
+			const bool inside = rr < g.rowEnd && px >= 0 && px < prePitch;
+			const uint32_t* src = inside ? pre2 + ((size_t)rr * prePitch + px) * PW2 + (uWord[i] % PW2) : pre2;
+			uint32_t* dst = preS + (size_t)(q & 1) * 32 * RS + (size_t)l * RS + uWord[i];
+			__pipeline_memcpy_async(dst, src, 16, inside ? 0 : 16);
 		}
 	};
-	issueRows(0, 0, 32);
+	for(int l0 = 0; l0 < 32; l0 += 32 / CHS)
+		issueRows(0, l0);
 	__pipeline_commit();
 	__pipeline_wait_prior(0);
 	__syncwarp();
@@ -270,7 +282,6 @@ k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, floa
 	int copiedWords = 0, flushedWords = 0;
 	const volatile unsigned int* prevProgress = progress + (band > 0 ? band - 1 : 0);
 	const size_t rowBase = (size_t)(rowValid ? r : 0);
-	constexpr uint32_t sideMask = (1u << side) - 1u;
 
 	for(int t = 0; t < tEnd; ++t)
 	{
@@ -282,15 +293,15 @@ k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, floa
 				__pipeline_wait_prior(0);
 				__syncwarp();
 			}
-			// predecessor rows: lane 0 will reach column 4 (t + CHS) - 1 + b within this chunk
+			// predecessor rows: lane 0 reaches column 4 (t + CHS) - 1 + b within this chunk
 			const int lastCol = PX * (t + CHS) - 1 + b;
 			const int needWords = min(Wp, ((lastCol + MARK_PAD) >> 5) + 1);
-			const unsigned int needCols = (unsigned int)min(W, (needWords << 5) - MARK_PAD);
-			if(band > 0 && lane == 0)
-				while(*prevProgress < needCols) { __nanosleep(64); }
-			__syncwarp();
 			if(needWords > copiedWords)
 			{
+				const unsigned int needCols = (unsigned int)min(W, (needWords << 5) - MARK_PAD);
+				if(band > 0 && lane == 0)
+					while(*prevProgress < needCols) { __nanosleep(32); }
+				__syncwarp();
 				__threadfence();
 				const int nw = needWords - copiedWords;
 				for(int e = lane; e < b * nw; e += 32)
@@ -307,64 +318,53 @@ k_marking_fast(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, floa
 			}
 		}
 		if(q + 1 < nChunks)
-			issueRows(q + 1, s * (32 / CHS), 32 / CHS);
+			issueRows(q + 1, s * (32 / CHS));
 		if(s == CHS - 1)
 			__pipeline_commit();
 
 		const int C = PX * (t - SKS * lane);
 		const bool valid = rowValid && C >= 0 && C < W;
-		// 4 pixels x PWT words of `pre`
-		uint32_t pw[PX * PWT];
+		const uint4* src = reinterpret_cast<const uint4*>(preS + (size_t)(q & 1) * 32 * RS + (size_t)lane * RS + s * PX * PW2);
+		uint32_t win2[NF];
 		{
-			const uint4* src = reinterpret_cast<const uint4*>(preS + (size_t)(q & 1) * 32 * RS + (size_t)lane * RS + s * PX * PWT);
-#pragma unroll
-			for(int i = 0; i < PWT; ++i)
-			{
-				const uint4 v = src[i];
-				pw[4 * i + 0] = v.x; pw[4 * i + 1] = v.y; pw[4 * i + 2] = v.z; pw[4 * i + 3] = v.w;
-			}
-		}
-		uint32_t hitAbove[PX];
-#pragma unroll
-		for(int i = 0; i < PX; ++i) hitAbove[i] = 0u;
-		if(valid)
-		{
-			const int posLo = C - b + MARK_PAD;
+			const int posLo = (valid ? C : 0) - b + MARK_PAD;
 			const int wi = posLo >> 5, sh = posLo & 31;
+			uint32_t win[BT];
 #pragma unroll
 			for(int k = 1; k <= BT; ++k)
 			{
 				const uint32_t* rowAbove = asS + (size_t)(lane + b - k) * Wp;
-				const uint32_t win = __funnelshift_r(rowAbove[wi], rowAbove[wi + 1], sh); // columns C-b .. C-b+31
+				win[k - 1] = __funnelshift_r(rowAbove[wi], rowAbove[wi + 1], sh); // columns C-b .. C-b+31
+			}
 #pragma unroll
-				for(int i = 0; i < PX; ++i)
-				{
-					constexpr int dummy = 0; (void)dummy;
-					const int off = (BT - k) * side;
-					const int w0 = off >> 5, so = off & 31;
-					const uint32_t lo = pw[i * PWT + w0];
-					const uint32_t hi = (w0 + 1 < PWT) ? pw[i * PWT + w0 + 1] : 0u;
-					const uint32_t sm = __funnelshift_r(lo, hi, so) & sideMask;
-					hitAbove[i] |= (win >> i) & sm;
-				}
+			for(int a = 0; a < NF; ++a)
+			{
+				if(FPW == 2)
+					win2[a] = (2 * a + 1 < BT) ? __byte_perm(win[2 * a], win[(2 * a + 1 < BT) ? 2 * a + 1 : 2 * a], 0x5410) : (win[2 * a] & 0xffffu);
+				else
+					win2[a] = win[a];
 			}
 		}
 		uint32_t asNibble = 0u, actNibble = 0u;
 #pragma unroll
 		for(int i = 0; i < PX; ++i)
 		{
+			uint32_t pw[PW2];
+#pragma unroll
+			for(int v4 = 0; v4 < PW2 / 4; ++v4)
+			{
+				const uint4 v = src[i * (PW2 / 4) + v4];
+				pw[4 * v4 + 0] = v.x; pw[4 * v4 + 1] = v.y; pw[4 * v4 + 2] = v.z; pw[4 * v4 + 3] = v.w;
+			}
+			uint32_t hit = pw[NF] & ownHist & ((1u << BT) - 1u); // same row: bits 0..b-1 = columns c-b..c-1
+#pragma unroll
+			for(int a = 0; a < NF; ++a)
+				hit |= win2[a] & pw[a];
 			const int c = C + i;
-			const int off = BT * side;
-			const int w0 = off >> 5, so = off & 31;
-			const uint32_t lo = pw[i * PWT + w0];
-			const uint32_t hi = (w0 + 1 < PWT) ? pw[i * PWT + w0 + 1] : 0u;
-			const uint32_t smSame = __funnelshift_r(lo, hi, so) & ((1u << BT) - 1u);
-			const uint32_t strongBit = (pw[i * PWT + (centreBit >> 5)] >> (centreBit & 31)) & 1u;
-			const bool centre = valid && r >= w && r <= H - 1 - w && c >= w && c <= W - 1 - w;
-			const bool skipIfMarked = always || hash32((uint32_t)r, (uint32_t)c, seed) < thr;
-			const uint32_t hit = hitAbove[i] | (smSame & ownHist);
+			const bool centre = rowCentre && valid && c >= w && c <= W - 1 - w;
+			const bool skipIfMarked = ALWAYS || hash32((uint32_t)r, (uint32_t)c, seed) <= thr;
 			const bool act = centre && !(hit != 0u && skipIfMarked);
-			const uint32_t as = (act && strongBit) ? 1u : 0u;
+			const uint32_t as = (act && ((pw[NF] >> 16) & 1u)) ? 1u : 0u;
 			ownHist = (ownHist >> 1) | (as << (BT - 1));
 			asNibble |= as << i;
 			actNibble |= (act ? 1u : 0u) << i;
@@ -430,6 +430,8 @@ cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaS
 
 bool g_forceGenericMarking = false; // test hook (BCD_B200_GENERIC_MARKING=1)
 
+bool markingUsesFastLayout(int b) { return (b == 6 || b == 10 || b == 14) && !g_forceGenericMarking; }
+
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches)
 {
@@ -443,9 +445,14 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 	const size_t asWords = ((size_t)(32 + g.b) * Wp + 3) & ~(size_t)3;
 #define LAUNCH_FAST(BT) \
 	do { \
-		const size_t smem = (asWords + (size_t)2 * 32 * (8 * 4 * g.Pw + 4)) * 4; \
-		if((err = cudaFuncSetAttribute(k_marking_fast<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
-		k_marking_fast<BT><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
+		const size_t smem = (asWords + (size_t)2 * 32 * (8 * 4 * fastMarkWords(BT) + 4)) * 4; \
+		if(skipProb >= 1.f) { \
+			if((err = cudaFuncSetAttribute(k_marking_fast<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+			k_marking_fast<BT, true><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
+		} else { \
+			if((err = cudaFuncSetAttribute(k_marking_fast<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+			k_marking_fast<BT, false><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
+		} \
 	} while(0)
 	if(g.b == 6 && !g_forceGenericMarking) LAUNCH_FAST(6);
 	else if(g.b == 10 && !g_forceGenericMarking) LAUNCH_FAST(10);

@@ -85,6 +85,27 @@ cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp,
 	return cudaGetLastError();
 }
 
+// row tiles: partial {sum, count} rows accumulated by the neighbouring tile are added to the owner's rows
+__global__ void k_add_strip(float4* __restrict__ acc, const float4* __restrict__ strip, size_t n)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n)
+		return;
+	float4 a = acc[i];
+	const float4 s = strip[i];
+	a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+	acc[i] = a;
+}
+
+cudaError_t launchAddStrip(float4* acc, const float4* strip, size_t n, cudaStream_t st, int* launches)
+{
+	if(n == 0)
+		return cudaSuccess;
+	k_add_strip<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(acc, strip, n);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
 // out = (1/count) * sum; count == 0 gives inf * 0 = NaN exactly like Denoiser.cpp:463-466
 __global__ void k_finalize(const float4* __restrict__ acc, size_t npix, float* __restrict__ out)
 {

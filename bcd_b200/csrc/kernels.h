@@ -20,11 +20,12 @@ cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom&
 		cudaStream_t st, int* launches);
 cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,
 		uint32_t* mplus, cudaStream_t st, int* launches);
-cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre, int prePitch,
+cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre, int prePitch, bool fastLayout,
 		cudaStream_t st, int* launches);
 // K2  marking strategy in raster order over the owned rows. asBits / actBits: H x Wp bit-rows (common.cuh), zeroed by
 // the caller (asBits rows above rowBeg may instead hold the upper row tile's hand-off); progress: >= ceil(rows/32).
 extern bool g_forceGenericMarking;
+bool markingUsesFastLayout(int b); // k_symmetrize must then write the `pre2` layout
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches);
 cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
@@ -47,6 +48,8 @@ struct FilterBuffers
 cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const int* counts,
 		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const FilterBuffers& fb,
 		float4* acc, cudaStream_t st, int* launches, float* stageMs /*3: stats, eig, apply*/, cudaEvent_t* ev);
+// halo strip added into the accumulator (row tiles)
+cudaError_t launchAddStrip(float4* acc, const float4* strip, size_t n, cudaStream_t st, int* launches);
 // K4 finalAggregation
 cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches);
 // K5 pyramid down, K6 merge

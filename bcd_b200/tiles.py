@@ -1,0 +1,308 @@
+"""Row-tiled multi-GPU driver of the hot path: one process per GPU, the frame cut into
+horizontal bands, no collective — only neighbour send/recv of small strips between the stages of each pyramid level.
+
+The stage functions and the strips are the row-tile API of the C ABI (include/bcd_b200.h, `bcd_b200_tile_*`); this
+module only sequences them and moves the strips:
+
+    per level, coarsest first:
+        select                                       (independent on every rank: the dominant cost)
+        [m > 0]  AS rows: recv from rank-1 -> mark -> send to rank+1      (the raster-order marking is a chain)
+        filter                                       (independent)
+        accumulator halo: isend/irecv with both neighbours, add           ((b+w) rows x W x 16 B each way)
+        finalize; output rows: isend/irecv (2 rows); [level < s-1] merge; output rows again
+
+`LoopbackExchange` runs all tiles inside one process (tiles processed stage by stage, strips handed over directly);
+it is what the single-GPU parity test uses to check that tiles reproduce the full-frame result.
+`DistExchange` uses torch.distributed point-to-point ops (NCCL on GPUs, gloo in the CPU tests).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+ACC_HALO, AS_ROWS, OUT_ROWS = 0, 1, 2
+UP, DOWN = 0, 1
+
+
+class Tile(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("image_width", "image_height", "own_row0", "own_row1", "sub_row0", "sub_row1",
+                                         "tile_index", "tile_count")]
+
+
+def _lib():
+    L = capi.lib()
+    if not getattr(L, "_tiles_ready", False):
+        L.bcd_b200_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(capi.Params), C.POINTER(Tile)]
+        L.bcd_b200_tile_begin.argtypes = [C.c_void_p, C.POINTER(capi.Params), C.POINTER(Tile)]
+        for n in ("select", "mark", "filter", "finalize", "merge"):
+            getattr(L, "bcd_b200_tile_" + n).argtypes = [C.c_void_p, C.c_int]
+        L.bcd_b200_tile_xfer_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.bcd_b200_tile_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.bcd_b200_tile_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.bcd_b200_tile_end.argtypes = [C.c_void_p]
+        L.bcd_b200_tile_download.argtypes = [C.c_void_p, C.c_void_p]
+        L._tiles_ready = True
+    return L
+
+
+def plan(W, H, index, count, params):
+    """Rows of tile `index` of `count` (pure host arithmetic, no GPU needed) -> Tile."""
+    t = Tile()
+    capi._check(_lib().bcd_b200_tile_plan(W, H, index, count, C.byref(params), C.byref(t)))
+    return t
+
+
+class TileWorker:
+    """One tile = one capi.Handle in row-tile mode. Strips travel as 1-D uint8 torch tensors on `device`."""
+
+    def __init__(self, handle, params, tile, torch_device):
+        import torch
+        self.torch = torch
+        self.h, self.params, self.tile, self.device = handle, params, tile, torch_device
+        self.has = {UP: tile.tile_index > 0, DOWN: tile.tile_index < tile.tile_count - 1}
+
+    def begin(self):
+        capi._check(_lib().bcd_b200_tile_begin(self.h._h, C.byref(self.params), C.byref(self.tile)))
+
+    def stage(self, name, level):
+        capi._check(getattr(_lib(), "bcd_b200_tile_" + name)(self.h._h, level))
+
+    def strip_bytes(self, level, what):
+        n = C.c_size_t()
+        capi._check(_lib().bcd_b200_tile_xfer_bytes(self.h._h, level, what, C.byref(n)))
+        return n.value
+
+    def export(self, level, what, side):
+        buf = self.torch.empty(self.strip_bytes(level, what), dtype=self.torch.uint8, device=self.device)
+        capi._check(_lib().bcd_b200_tile_export(self.h._h, level, what, side, C.c_void_p(buf.data_ptr())))
+        return buf
+
+    def import_(self, level, what, side, buf):
+        capi._check(_lib().bcd_b200_tile_import(self.h._h, level, what, side, C.c_void_p(buf.data_ptr())))
+
+    def end(self):
+        capi._check(_lib().bcd_b200_tile_end(self.h._h))
+
+    def download(self, out=None):
+        rows = self.tile.own_row1 - self.tile.own_row0
+        if out is None:
+            out = np.empty((rows, self.tile.image_width, 3), np.float32)
+        capi._check(_lib().bcd_b200_tile_download(self.h._h, C.c_void_p(out.ctypes.data if isinstance(out, np.ndarray) else out)))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------ exchanges
+class DistExchange:
+    """Neighbour exchange over torch.distributed (one tile per rank)."""
+
+    def __init__(self, dist, rank, world):
+        self.dist, self.rank, self.world = dist, rank, world
+
+    def swap(self, send):
+        """send: {UP: tensor|None, DOWN: tensor|None} -> received {UP: tensor|None, DOWN: tensor|None}."""
+        import torch
+        ops, recv = [], {UP: None, DOWN: None}
+        for side, peer in ((UP, self.rank - 1), (DOWN, self.rank + 1)):
+            if send.get(side) is None or peer < 0 or peer >= self.world:
+                continue
+            recv[side] = torch.empty_like(send[side])
+            ops.append(self.dist.P2POp(self.dist.isend, send[side], peer))
+            ops.append(self.dist.P2POp(self.dist.irecv, recv[side], peer))
+        if ops:
+            for r in self.dist.batch_isend_irecv(ops):
+                r.wait()
+        return recv
+
+    def recv_from_up(self, like):
+        self.dist.recv(like, src=self.rank - 1)
+        return like
+
+    def send_down(self, buf):
+        self.dist.send(buf, dst=self.rank + 1)
+
+
+def run_tile(worker, ex):
+    """Drives one tile through all levels with a DistExchange (every rank calls this)."""
+    import torch
+    p = worker.params
+    s = p.nb_scales
+    worker.begin()
+    for k in range(s - 1, -1, -1):
+        worker.stage("select", k)
+        if p.skip_prob > 0 and worker.has[UP]:
+            buf = torch.empty(worker.strip_bytes(k, AS_ROWS), dtype=torch.uint8, device=worker.device)
+            worker.import_(k, AS_ROWS, UP, ex.recv_from_up(buf))
+        worker.stage("mark", k)
+        if p.skip_prob > 0 and worker.has[DOWN]:
+            ex.send_down(worker.export(k, AS_ROWS, DOWN))
+        worker.stage("filter", k)
+        _swap_and_import(worker, ex, k, ACC_HALO)
+        worker.stage("finalize", k)
+        _swap_and_import(worker, ex, k, OUT_ROWS)
+        if k < s - 1:
+            worker.stage("merge", k)
+            _swap_and_import(worker, ex, k, OUT_ROWS)
+    worker.end()
+
+
+def _swap_and_import(worker, ex, level, what):
+    send = {side: (worker.export(level, what, side) if worker.has[side] else None) for side in (UP, DOWN)}
+    recv = ex.swap(send)
+    for side in (UP, DOWN):
+        if recv[side] is not None:
+            worker.import_(level, what, side, recv[side])
+
+
+def run_tiles_loopback(workers):
+    """All tiles of a frame inside this process (e.g. several handles on one GPU): same stage order as run_tile,
+    strips handed over directly. Used by the single-GPU parity test of the tiling."""
+    p = workers[0].params
+    s = p.nb_scales
+    n = len(workers)
+
+    def swap_all(level, what):
+        sent = [{side: (w.export(level, what, side) if w.has[side] else None) for side in (UP, DOWN)} for w in workers]
+        for i, w in enumerate(workers):
+            if w.has[UP]:
+                w.import_(level, what, UP, sent[i - 1][DOWN])
+            if w.has[DOWN]:
+                w.import_(level, what, DOWN, sent[i + 1][UP])
+
+    for w in workers:
+        w.begin()
+    for k in range(s - 1, -1, -1):
+        for w in workers:
+            w.stage("select", k)
+        for i, w in enumerate(workers):  # the marking chain, top to bottom
+            if p.skip_prob > 0 and i > 0:
+                w.import_(k, AS_ROWS, UP, workers[i - 1].export(k, AS_ROWS, DOWN))
+            w.stage("mark", k)
+        for w in workers:
+            w.stage("filter", k)
+        swap_all(k, ACC_HALO)
+        for w in workers:
+            w.stage("finalize", k)
+        swap_all(k, OUT_ROWS)
+        if k < s - 1:
+            for w in workers:
+                w.stage("merge", k)
+            swap_all(k, OUT_ROWS)
+    for w in workers:
+        w.end()
+    assert n == workers[0].tile.tile_count
+
+
+def make_worker(inputs_full, params, index, count, device_index=0, stream_ptr=None):
+    """Uploads the rows of tile `index` of a full-frame dict(color,nsamples,hist,cov) and returns its TileWorker."""
+    import torch
+    H, W, _ = inputs_full["color"].shape
+    t = plan(W, H, index, count, params)
+    sub = {k: np.ascontiguousarray(v[t.sub_row0:t.sub_row1]) for k, v in inputs_full.items()}
+    h = capi.Handle(device_index)
+    if stream_ptr is not None:
+        h.set_stream(stream_ptr)
+    h.upload(**sub)
+    return TileWorker(h, params, t, torch.device("cuda", device_index))
+
+
+# ---------------------------------------------------------------------------------------------------------- bench
+def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist):
+    """bench.py's N > 1 arm: one row tile per rank; barrier + synchronize on both sides, max over ranks."""
+    import json
+    import time
+    import torch
+    from . import host
+    import bench as B  # clocks sampler / constants of the N=1 arm
+
+    dev = torch.device("cuda", local_rank)
+    params = capi.make_params(w=a.w, b=a.b, m=a.m, scales=a.scales)
+    t = plan(W, H, rank, world, params)
+    rows = t.sub_row1 - t.sub_row0
+    Bd = 60
+    pin = dict(color=torch.empty((rows, W, 3), dtype=torch.float32).pin_memory(),
+               nsamples=torch.empty((rows, W, 1), dtype=torch.float32).pin_memory(),
+               hist=torch.empty((rows, W, Bd), dtype=torch.float32).pin_memory(),
+               cov=torch.empty((rows, W, 6), dtype=torch.float32).pin_memory())
+    t0 = time.time()
+    host.synth(W, H, spp=a.spp, row0=t.sub_row0, rows=rows, out={k: v.numpy() for k, v in pin.items()})
+    gen_s = time.time() - t0
+    own_rows = t.own_row1 - t.own_row0
+    out_pin = torch.empty((own_rows, W, 3), dtype=torch.float32).pin_memory()
+    devt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    h = capi.Handle(local_rank)
+    h.set_stream(stream.cuda_stream)
+    worker = TileWorker(h, params, t, dev)
+    ex = DistExchange(dist, rank, world)
+
+    def step_resident():
+        run_tile(worker, ex)
+
+    def step_e2e():
+        h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd)
+        run_tile(worker, ex)
+        worker.download(out_pin.data_ptr())
+
+    def timed(fn, bind):
+        if bind:
+            h.bind_device(devt["color"].data_ptr(), devt["nsamples"].data_ptr(), devt["hist"].data_ptr(), devt["cov"].data_ptr(), W, rows, Bd)
+        for _ in range(a.warmup):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sampler = B.ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_acc, launches = {}, 0
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(a.steps):
+            fn()
+            for k, v in h.timings().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+            launches += h.stats()["kernel_launches"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        clocks = sampler.stop()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ln = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        return float(ms.item()), stage_acc, int(ln.item()), clocks
+
+    ms_res, stages, launches, clocks = timed(step_resident, True)
+    stats = h.stats()
+    ms_e2e, _, _, _ = timed(step_e2e, False)
+    st = torch.tensor([float(stats[k]) for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full")], device=dev, dtype=torch.float64)
+    dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    pair = torch.tensor([stages["pair"] / a.steps], device=dev)
+    dist.all_reduce(pair, op=dist.ReduceOp.MAX)
+    h2d = torch.tensor([float(sum(v.numel() * 4 for v in pin.values())), float(out_pin.numel() * 4)], device=dev)
+    dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        value = W * H * a.steps / (ms_res * 1e-3) / 1e6
+        e2e_val = W * H * a.steps / (ms_e2e * 1e-3) / 1e6
+        pk, pk_src = B.peaks()
+        npix_all = sum((W >> k) * (H >> k) for k in range(a.scales))
+        alg_bytes = npix_all * (Bd + 1) * 4 / world          # per GPU
+        achieved = alg_bytes / (float(pair.item()) * 1e-3) / 1e9
+        line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": B.UNIT, "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
+                        "ms_per_step": ms_e2e / a.steps, "api": "per rank: bcd_b200_upload(tile rows) + tile stages + bcd_b200_tile_download"},
+                "gpu_launches": launches,
+                "roofline": {"kernel": "k_pair_terms_sparse (per GPU, slowest rank)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                             "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
+                             "note": "FP32-issue-bound kernel; see the N=1 line for the FP32 figure"},
+                "stage_ms_per_step_rank0": {k: v / a.steps for k, v in stages.items()},
+                "work_counters": dict(zip(("interior", "strong", "active", "full", "fallback", "sum_n_full"), [int(v) for v in st.tolist()])),
+                "input_generation_s": gen_s}
+        print(json.dumps(line))
+    h.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

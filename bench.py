@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m", type=float, default=1.0, help="markedPixelsSkippingProbability (1 = default marking strategy)")
-    ap.add_argument("--size", default=None, help="WxH (default 1920x1080 at N=1, 4096x4096 at N>1)")
+    ap.add_argument("--size", default=None, help="WxH (default 1920x1080 for every N; the 4K scaling series uses --size 4096x4096)")
     ap.add_argument("--scales", type=int, default=3)
     ap.add_argument("--w", type=int, default=1)
     ap.add_argument("--b", type=int, default=6)
@@ -141,7 +141,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = a.gpus
-    size = a.size or ("1920x1080" if n_gpus == 1 else "4096x4096")
+    size = a.size or "1920x1080"
     W, H = [int(v) for v in size.lower().split("x")]
     workload = "G(%d,%d,spp=%d,seed=20170627) synthetic colour+histogram+covariance, MultiscaleDenoiser s=%d, b=%d w=%d tau=1 m=%g" % (
         W, H, a.spp, a.scales, a.b, a.w, a.m)

@@ -117,6 +117,55 @@ int  bcd_b200_result_device_ptr(bcd_b200_handle* h, const float** out_dev);
 int  bcd_b200_get_stats(bcd_b200_handle* h, bcd_b200_stats* s);
 int  bcd_b200_get_timings(bcd_b200_handle* h, bcd_b200_timings* t);
 
+/* ---- row-tile API (multi-GPU: one handle per GPU, one process per GPU) ---------------------------------------------
+ * The frame is cut into horizontal bands. Tile t of n produces the output rows [own_row0, own_row1) and keeps the
+ * input rows [sub_row0, sub_row1) resident (its band plus (b+w)*2^(s-1) halo rows, so that every pyramid level has
+ * its b+w halo rows and the local pyramid equals the global one restricted to the band). The caller uploads/binds
+ * exactly those sub_row1 - sub_row0 rows as the handle's inputs, then drives the stages level by level, coarsest
+ * first, exchanging the small strips named below with the neighbouring ranks between stages (bcd_b200/tiles.py does
+ * this with torch.distributed send/recv):
+ *
+ *   tile_begin                      pyramid build (local)
+ *   for level = s-1 .. 0:
+ *     tile_select(level)            K0 + K1 on the band (+ halo rows)
+ *     [m > 0] import AS_ROWS from the upper neighbour -> tile_mark(level) -> export AS_ROWS to the lower neighbour
+ *     tile_filter(level)            fallback + two-step filter into the local accumulator
+ *     export ACC_HALO (up, down) -> neighbours -> import (adds)      the only data-path exchange: (b+w) rows x W x 16 B
+ *     tile_finalize(level)
+ *     export OUT_ROWS (up, down) -> neighbours -> import             2 rows of the level's output
+ *     [level < s-1] tile_merge(level), then OUT_ROWS again (the merged rows feed the next finer level)
+ *   tile_download                   owned rows of level 0
+ *
+ * No collective is needed: replaces nothing in the reference (it has no multi-GPU path). */
+typedef struct bcd_b200_tile {
+	int32_t image_width, image_height; /* full frame */
+	int32_t own_row0, own_row1;        /* output rows produced by this tile (frame coordinates) */
+	int32_t sub_row0, sub_row1;        /* input rows resident in the handle (frame coordinates) */
+	int32_t tile_index, tile_count;
+} bcd_b200_tile;
+
+enum { BCD_B200_XFER_ACC_HALO = 0, BCD_B200_XFER_AS_ROWS = 1, BCD_B200_XFER_OUT_ROWS = 2 };
+enum { BCD_B200_SIDE_UP = 0, BCD_B200_SIDE_DOWN = 1 };
+
+/* pure host arithmetic (no device needed): rows of tile `tile_index` of `tile_count` for an image_height-row frame */
+int  bcd_b200_tile_plan(int image_width, int image_height, int tile_index, int tile_count, const bcd_b200_params* p,
+                        bcd_b200_tile* out);
+int  bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t);
+int  bcd_b200_tile_select(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_mark(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_filter(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_finalize(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_merge(bcd_b200_handle* h, int level);
+/* size in bytes of the strip `what` of `level` (identical on both sides of a tile boundary) */
+int  bcd_b200_tile_xfer_bytes(bcd_b200_handle* h, int level, int what, size_t* bytes);
+/* copy the strip facing neighbour `side` into dev_buf (device memory, async on the handle's stream) */
+int  bcd_b200_tile_export(bcd_b200_handle* h, int level, int what, int side, void* dev_buf);
+/* take the strip received from neighbour `side`: ACC_HALO is added into the owned rows, AS_ROWS / OUT_ROWS are
+ * copied into the halo rows */
+int  bcd_b200_tile_import(bcd_b200_handle* h, int level, int what, int side, const void* dev_buf);
+int  bcd_b200_tile_end(bcd_b200_handle* h);                 /* synchronises, collects stats/timings */
+int  bcd_b200_tile_download(bcd_b200_handle* h, float* out_rows /* (own_row1-own_row0) * W * 3 */);
+
 /* ---- stage-level read-backs used by the parity tests (level 0 of the last run) ---------------------------------
  * masks: W*H*words uint32, bit index (dy+b)*(2b+1)+(dx+b) — the ordered similar set S(p) of
  * DenoisingUnit::selectSimilarPatches (reference DenoisingUnit.cpp:196-219); counts: W*H int32;

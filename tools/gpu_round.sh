@@ -3,16 +3,16 @@
 set -x
 mkdir -p gpurun_out
 nproc > gpurun_out/nproc.txt
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee gpurun_out/smoke.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_m1.json 2> gpurun_out/bench_m1.err
-python bench.py --m 0 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_m0.json 2> gpurun_out/bench_m0.err
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee gpurun_out/smoke.log
+timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_m1.json 2> gpurun_out/bench_m1.err
+timeout 300 python bench.py --m 0 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_m0.json 2> gpurun_out/bench_m0.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_m1.csv \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_pair_terms -s 2 -c 1 -f -o gpurun_out/prof_pair \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_pair.log 2>&1
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_pair.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_eig_chain -s 4 -c 1 -f -o gpurun_out/prof_eig \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_eig.log 2>&1
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_eig.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_marking -s 2 -c 1 -f -o gpurun_out/prof_mark \
-    python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_mark.log 2>&1
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_mark.log 2>&1
 ls -la gpurun_out
