@@ -11,7 +11,7 @@ A "step" is one complete denoise of that frame.
           stream, barrier + synchronize on both sides, max over ranks).
   e2e   : the same metric through the C ABI handle calls a host renderer makes per frame — upload (pinned host ->
           device) + run + download — all inside the timed region.
-  roofline     : dominant kernel (k_pair_terms_tiled, stage "pair") — algorithmic bytes / CUDA-event time vs the
+  roofline     : dominant kernel (k_pair_terms_sparse, stage "pair") — algorithmic bytes / CUDA-event time vs the
                  measured HBM peak (MEASURED_PEAKS.json); the binding roof of this kernel is FP32 issue, not HBM
                  (SURVEY §8d), so `roofline_fp32` reports the bin-term rate against the FP32 pipe as well.
   cpu_baseline : the UNMODIFIED reference CPU path (oracle/_ref, all host cores) on a bounded crop of the same frame.
@@ -262,7 +262,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "k_pair_terms_tiled (stage 'pair', %d launches/step)" % a.scales, "bound": "hbm",
+    roofline = {"kernel": "k_pair_terms_sparse (stage 'pair', %d launches/step)" % a.scales, "bound": "hbm",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "peak_source": pk_src + " (burst copy figure; kernel timed alone by CUDA events)", "traffic": traffic,
                 "ms_per_launch_set": pair_ms,
