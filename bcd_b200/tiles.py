@@ -194,7 +194,8 @@ def run_tiles_loopback(workers):
 
 
 def make_worker(inputs_full, params, index, count, device_index=0, stream_ptr=None):
-    """Uploads the rows of tile `index` of a full-frame dict(color,nsamples,hist,cov) and returns its TileWorker."""
+    """Uploads the rows of tile `index` of a full-frame dict(color,nsamples,hist,cov) and returns its TileWorker.
+    Workers that exchange strips must share one stream (pass the cuda_stream of an explicit torch.cuda.Stream)."""
     import torch
     H, W, _ = inputs_full["color"].shape
     t = plan(W, H, index, count, params)
@@ -207,7 +208,7 @@ def make_worker(inputs_full, params, index, count, device_index=0, stream_ptr=No
 
 
 # ---------------------------------------------------------------------------------------------------------- bench
-def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist):
+def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_stdout_fd=None):
     """bench.py's N > 1 arm: one row tile per rank; barrier + synchronize on both sides, max over ranks."""
     import json
     import time
@@ -231,7 +232,10 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist):
     out_pin = torch.empty((own_rows, W, 3), dtype=torch.float32).pin_memory()
     devt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream shared by torch/NCCL and the handle: the legacy default stream has handle 0,
+    # which bcd_b200_set_stream reads as "use the handle's own stream" and would leave the strips unordered
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     h = capi.Handle(local_rank)
     h.set_stream(stream.cuda_stream)
     worker = TileWorker(h, params, t, dev)
@@ -301,7 +305,12 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist):
                 "stage_ms_per_step_rank0": {k: v / a.steps for k, v in stages.items()},
                 "work_counters": dict(zip(("interior", "strong", "active", "full", "fallback", "sum_n_full"), [int(v) for v in st.tolist()])),
                 "input_generation_s": gen_s}
-        print(json.dumps(line))
+        import os
+        import sys
+        sys.stdout.flush()
+        if saved_stdout_fd is not None:
+            os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     h.close()
     dist.barrier()
     dist.destroy_process_group()

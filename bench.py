@@ -183,12 +183,17 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # libraries (NCCL's version banner) may write to fd 1; rank 0's stdout must carry exactly ONE JSON line, so fd 1
+        # is pointed at stderr until that line is printed (tiles.bench_tiled restores it)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if world > 1:
         from bcd_b200 import tiles
-        return tiles.bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist)
+        return tiles.bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_stdout)
 
     # ---- inputs: generated straight into pinned host memory
     B = 60
@@ -203,7 +208,8 @@ def main():
     dev = {k: v.cuda(non_blocking=True) for k, v in pin.items()}
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # explicit stream shared by the torch events and the handle
+    torch.cuda.set_stream(stream)
     h = capi.Handle(local_rank)
     h.set_stream(stream.cuda_stream)
     params = capi.make_params(w=a.w, b=a.b, m=a.m, scales=a.scales)

@@ -19,10 +19,13 @@ def _full(capi, inp, **kw):
 
 
 def _tiled(capi, tiles, inp, count, **kw):
+    import torch
     params = capi.make_params(**kw)
-    workers = [tiles.make_worker(inp, params, i, count) for i in range(count)]
-    tiles.run_tiles_loopback(workers)
-    out = np.concatenate([w.download() for w in workers], axis=0)
+    stream = torch.cuda.Stream()  # all tiles exchange strips on one stream
+    with torch.cuda.stream(stream):
+        workers = [tiles.make_worker(inp, params, i, count, stream_ptr=stream.cuda_stream) for i in range(count)]
+        tiles.run_tiles_loopback(workers)
+        out = np.concatenate([w.download() for w in workers], axis=0)
     st = {}
     for w in workers:
         for k, v in w.h.stats().items():

@@ -18,6 +18,8 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     W, H = 640, 64 * world + 96
     ok = True
     for kw in (dict(m=1.0, scales=3), dict(m=0.0, scales=2)):
@@ -26,7 +28,7 @@ def main():
         rows = t.sub_row1 - t.sub_row0
         sub = host.synth(W, H, spp=24, row0=t.sub_row0, rows=rows)
         h = capi.Handle(lr)
-        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        h.set_stream(stream.cuda_stream)
         h.upload(**sub)
         worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr))
         tiles.run_tile(worker, tiles.DistExchange(dist, rank, world))
@@ -45,6 +47,7 @@ def main():
         if rank == 0:
             full = host.synth(W, H, spp=24)
             hf = capi.Handle(lr)
+            hf.set_stream(stream.cuda_stream)
             hf.upload(**full)
             hf.run(params)
             ref = hf.download()
