@@ -18,7 +18,7 @@ STAGE_NAMES = ["prepass", "pair", "select", "marking", "fallback", "filter_stats
 # every symbol include/bcd_b200.h declares (tests/test_capi_symbols.py cross-checks this list against the header)
 SYMBOLS = [
     "bcd_b200_default_params", "bcd_b200_last_error", "bcd_b200_abi_version", "bcd_b200_device_count",
-    "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_upload",
+    "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_set_streams", "bcd_b200_upload",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
     # row-tile API (multi-GPU), wrapped by bcd_b200/tiles.py
@@ -74,6 +74,7 @@ def lib():
         L.bcd_b200_destroy.argtypes = [C.c_void_p]
         L.bcd_b200_destroy.restype = None
         L.bcd_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_set_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_upload.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_bind_device.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
@@ -142,6 +143,9 @@ class Handle:
 
     def set_stream(self, cuda_stream_ptr):
         _check(lib().bcd_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_streams(self, main_ptr, aux_ptr):
+        _check(lib().bcd_b200_set_streams(self._h, C.c_void_p(main_ptr), C.c_void_p(aux_ptr)))
 
     def upload(self, color, nsamples, hist, cov):
         img, keep = _host_images(color, nsamples, hist, cov)

@@ -73,6 +73,11 @@ struct LevelBufs
 	const float *color = nullptr, *ns = nullptr, *hist = nullptr, *cov = nullptr; // inputs of this level
 	DevBuf ownColor, ownNs, ownHist, ownCov;                                         // storage when owned
 	DevBuf out;                                                                      // W*H*3
+	// per-level state of the hot path (kept per level so that the stages of different levels can overlap)
+	DevBuf smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr;
+	DeviceCounters* hostCtr = nullptr; // pinned read-back of ctr
+	DeviceCounters counters;           // host copy used to size the filter launches
+	cudaEvent_t evSel = nullptr, evMark = nullptr;
 };
 
 } // namespace
@@ -85,8 +90,11 @@ struct bcd_b200_handle
 	bool haveInputs = false;
 	std::vector<LevelBufs> levels; // [0] = full resolution
 	// scratch shared by all levels (sized for level 0)
-	DevBuf sP, cP, mplus, smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr, tmpLow;
-	DevBuf fA, fMinv, fMean, fNoise, fX;
+	DevBuf sP, cP, mplus, tmpLow;          // scratch of the selection stage / merge (levels run it one after the other)
+	DevBuf fA, fMinv, fMean, fNoise, fX;   // scratch of the filter chain (chunked)
+	// marking (K2) runs on a second, high-priority stream so that the latency-bound raster-order chain of level k
+	// overlaps the selection of level k-1 and the filters of the coarser levels on the main stream
+	cudaStream_t ownAux = nullptr, aux = nullptr;
 	int filterChunk = 0;
 	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
 	bool ran = false;
@@ -98,19 +106,17 @@ struct bcd_b200_handle
 	cudaEvent_t evTotal[2] = {nullptr, nullptr};
 	size_t eventsUsed = 0;
 	int launches = 0;
-	DeviceCounters* hostCtr = nullptr; // pinned
 	// row-tile mode (multi-GPU): the resident inputs are rows [subRow0, subRow1) of an imageH-row frame and this
 	// handle produces the output rows [ownRow0, ownRow1) (frame coordinates)
 	bool tiled = false;
 	int imageH = 0, subRow0 = 0, subRow1 = 0, ownRow0 = 0, ownRow1 = 0;
 	bcd_b200_params runParams;
-	DeviceCounters levelCtr; // counters of the level being processed
 };
 
 namespace
 {
 
-int stageBegin(bcd_b200_handle* h, int stage)
+int stageBegin(bcd_b200_handle* h, int stage, cudaStream_t st)
 {
 	if(h->eventsUsed + 2 > h->events.size())
 	{
@@ -123,25 +129,26 @@ int stageBegin(bcd_b200_handle* h, int stage)
 		h->eventStage.push_back(stage);
 	}
 	h->eventStage[h->eventsUsed / 2] = stage;
-	CU(cudaEventRecord(h->events[h->eventsUsed], h->stream));
+	CU(cudaEventRecord(h->events[h->eventsUsed], st));
 	return 0;
 }
 
-int stageEnd(bcd_b200_handle* h)
+int stageEnd(bcd_b200_handle* h, cudaStream_t st)
 {
-	CU(cudaEventRecord(h->events[h->eventsUsed + 1], h->stream));
+	CU(cudaEventRecord(h->events[h->eventsUsed + 1], st));
 	h->eventsUsed += 2;
 	return 0;
 }
 
-#define STAGE(h, stage, ...) \
+#define STAGE_ON(h, st_, stage, ...) \
 	do { \
-		int rc_ = stageBegin(h, stage); \
+		int rc_ = stageBegin(h, stage, st_); \
 		if(rc_) return rc_; \
 		__VA_ARGS__; \
-		rc_ = stageEnd(h); \
+		rc_ = stageEnd(h, st_); \
 		if(rc_) return rc_; \
 	} while(0)
+#define STAGE(h, stage, ...) STAGE_ON(h, (h)->stream, stage, __VA_ARGS__)
 
 // Geometry of level k as seen by this handle. Single GPU: the whole level. Row tile: the local sub-image with the
 // owned patch-centre rows [rowBeg, rowEnd) and the rows [yLo, yHi) on which the selection stage has to run
@@ -171,7 +178,7 @@ void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1)
 	own1 = h->ownRow1 >= h->imageH ? L.H : (h->ownRow1 - h->subRow0) >> k;
 }
 
-// stage 1: prepass + distance/selection (K0, K1a-c); clears the accumulators and bit-rows of the level
+// stage 1 (main stream): prepass + distance/selection (K0, K1a-c); clears the accumulators and bit-rows of the level
 int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
@@ -182,11 +189,11 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	const size_t npix = (size_t)g.W * g.H;
 	const int Wp = markingRowWords(g.W);
 	STAGE(h, BCD_B200_STAGE_PREPASS, {
-		CU(launchPixelCov(L.cov, L.ns, npix, h->pixcov.as<float>(), st, &h->launches));
-		CU(cudaMemsetAsync(h->acc.p, 0, npix * sizeof(float4), st));
-		CU(cudaMemsetAsync(h->active.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
-		CU(cudaMemsetAsync(h->asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
-		CU(cudaMemsetAsync(h->ctr.p, 0, sizeof(DeviceCounters), st));
+		CU(launchPixelCov(L.cov, L.ns, npix, L.pixcov.as<float>(), st, &h->launches));
+		CU(cudaMemsetAsync(L.acc.p, 0, npix * sizeof(float4), st));
+		CU(cudaMemsetAsync(L.active.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
+		CU(cudaMemsetAsync(L.asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
+		CU(cudaMemsetAsync(L.ctr.p, 0, sizeof(DeviceCounters), st));
 	});
 	STAGE(h, BCD_B200_STAGE_PAIR, {
 		CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
@@ -195,32 +202,43 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
 		const bool fastLayout = markingUsesFastLayout(g.b);
 		const int preWords = fastLayout ? fastMarkWords(g.b) : g.Pw;
-		CU(cudaMemsetAsync(h->pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, st));
-		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, h->smask.as<uint32_t>(), h->counts.as<int>(),
-				h->pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches));
+		CU(cudaMemsetAsync(L.pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, st));
+		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, L.smask.as<uint32_t>(), L.counts.as<int>(),
+				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches));
 	});
+	CU(cudaEventRecord(L.evSel, st));
 	return 0;
 }
 
-// stage 2: marking strategy (K2) over the owned rows + work lists; reads the counters back (one host sync)
-int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+// stage 2a (aux stream): marking strategy (K2) over the owned rows + work lists; asynchronous
+int levelMarkEnqueue(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
+	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
-	cudaStream_t st = h->stream;
+	cudaStream_t st = h->aux;
 	const int Wp = markingRowWords(g.W);
-	STAGE(h, BCD_B200_STAGE_MARKING, {
+	CU(cudaStreamWaitEvent(st, L.evSel, 0));
+	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
-			CU(launchMarking(h->pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, h->active.as<uint32_t>(),
-					h->asBits.as<uint32_t>(), Wp, h->progress.as<unsigned int>(), st, &h->launches));
+			CU(launchMarking(L.pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, L.active.as<uint32_t>(),
+					L.asBits.as<uint32_t>(), Wp, L.progress.as<unsigned int>(), st, &h->launches));
 		else
-			CU(launchAllActive(g, h->active.as<uint32_t>(), Wp, st, &h->launches));
-		CU(launchBuildLists(h->counts.as<int>(), h->active.as<uint32_t>(), Wp, g, h->fullList.as<int>(),
-				h->fallbackList.as<int>(), h->ctr.as<DeviceCounters>(), st, &h->launches));
-		CU(cudaMemcpyAsync(h->hostCtr, h->ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+			CU(launchAllActive(g, L.active.as<uint32_t>(), Wp, st, &h->launches));
+		CU(launchBuildLists(L.counts.as<int>(), L.active.as<uint32_t>(), Wp, g, L.fullList.as<int>(),
+				L.fallbackList.as<int>(), L.ctr.as<DeviceCounters>(), st, &h->launches));
+		CU(cudaMemcpyAsync(L.hostCtr, L.ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
 	});
-	CU(cudaStreamSynchronize(st));
-	const DeviceCounters c = *h->hostCtr;
-	h->levelCtr = c;
+	CU(cudaEventRecord(L.evMark, st));
+	return 0;
+}
+
+// stage 2b (host): wait for the work counters of the level (the only host synchronisation per level)
+int levelMarkWait(bcd_b200_handle* h, int k)
+{
+	LevelBufs& L = h->levels[k];
+	CU(cudaEventSynchronize(L.evMark));
+	const DeviceCounters c = *L.hostCtr;
+	L.counters = c;
 	h->stats.interior += (int64_t)c.interior;
 	h->stats.strong += (int64_t)c.strong;
 	h->stats.active += (int64_t)c.active;
@@ -230,17 +248,25 @@ int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
-// stage 3: fallback mean + two-step Bayesian filter, accumulated into acc
+int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	int rc = levelMarkEnqueue(h, k, p);
+	if(rc) return rc;
+	return levelMarkWait(h, k);
+}
+
+// stage 3 (main stream): fallback mean + two-step Bayesian filter, accumulated into acc
 int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
 	cudaStream_t st = h->stream;
-	const DeviceCounters c = h->levelCtr;
+	const DeviceCounters c = L.counters;
+	CU(cudaStreamWaitEvent(st, L.evMark, 0));
 	STAGE(h, BCD_B200_STAGE_FALLBACK, {
 		if(c.nFallback > 0)
-			CU(launchFallback(L.color, h->smask.as<uint32_t>(), h->counts.as<int>(), g, h->fallbackList.as<int>(),
-					&h->ctr.as<DeviceCounters>()->nFallback, h->acc.as<float4>(), st, &h->launches));
+			CU(launchFallback(L.color, L.smask.as<uint32_t>(), L.counts.as<int>(), g, L.fallbackList.as<int>(),
+					&L.ctr.as<DeviceCounters>()->nFallback, L.acc.as<float4>(), st, &h->launches));
 	});
 	if(c.nFull > 0)
 	{
@@ -255,8 +281,8 @@ int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		for(int first = 0; first < c.nFull; first += h->filterChunk)
 		{
 			const int count = std::min(h->filterChunk, c.nFull - first);
-			cudaError_t e = launchFilterChunk(L.color, h->pixcov.as<float>(), h->smask.as<uint32_t>(), h->counts.as<int>(), g,
-					p.min_eig, h->fullList.as<int>(), first, count, fb, h->acc.as<float4>(), st, &h->launches, ms, h->fev);
+			cudaError_t e = launchFilterChunk(L.color, L.pixcov.as<float>(), L.smask.as<uint32_t>(), L.counts.as<int>(), g,
+					p.min_eig, L.fullList.as<int>(), first, count, fb, L.acc.as<float4>(), st, &h->launches, ms, h->fev);
 			if(e != cudaSuccess)
 				return fail(e == cudaErrorInvalidConfiguration ? BCD_B200_ERR_UNSUPPORTED : BCD_B200_ERR_CUDA,
 						"filter chunk failed: %s", cudaGetErrorString(e));
@@ -268,13 +294,13 @@ int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
-// stage 4: out = sum / count
+// stage 4 (main stream): out = sum / count
 int levelFinalize(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
 	STAGE(h, BCD_B200_STAGE_FINALIZE, {
-		CU(launchFinalize(h->acc.as<float4>(), (size_t)g.W * g.H, L.out.as<float>(), h->stream, &h->launches));
+		CU(launchFinalize(L.acc.as<float4>(), (size_t)g.W * g.H, L.out.as<float>(), h->stream, &h->launches));
 	});
 	return 0;
 }
@@ -286,15 +312,6 @@ int levelMerge(bcd_b200_handle* h, int k)
 				h->tmpLow.as<float>(), h->stream, &h->launches));
 	});
 	return 0;
-}
-
-int denoiseLevel(bcd_b200_handle* h, int k, const bcd_b200_params& p)
-{
-	int rc;
-	if((rc = levelSelect(h, k, p))) return rc;
-	if((rc = levelMark(h, k, p))) return rc;
-	if((rc = levelFilter(h, k, p))) return rc;
-	return levelFinalize(h, k, p);
 }
 
 int buildPyramid(bcd_b200_handle* h, int s)
@@ -357,18 +374,31 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	CU(h->sP.reserve(npix * g.J * sizeof(float)));
 	CU(h->cP.reserve(npix * g.J));
 	CU(h->mplus.reserve(npix * g.Jw * 4));
-	CU(h->smask.reserve(npix * g.Nw * 4));
-	CU(h->pre.reserve((size_t)g.H * prePitchOf(g.W) * std::max(g.Pw, fastMarkWords(g.b)) * 4 + 64));
-	CU(h->counts.reserve(npix * 4));
-	CU(h->active.reserve((size_t)g.H * markingRowWords(g.W) * 4));
-	CU(h->asBits.reserve((size_t)g.H * markingRowWords(g.W) * 4));
-	CU(h->progress.reserve((size_t)(divUp(g.H, 32) + 2) * 4));
-	CU(h->fullList.reserve(npix * 4));
-	CU(h->fallbackList.reserve(npix * 4));
-	CU(h->acc.reserve(npix * sizeof(float4)));
-	CU(h->pixcov.reserve(npix * 6 * sizeof(float)));
-	CU(h->ctr.reserve(sizeof(DeviceCounters)));
 	CU(h->tmpLow.reserve(std::max<size_t>((size_t)(g.W / 2) * (g.H / 2) * 3 * sizeof(float), 16)));
+	for(int k = 0; k < nl; ++k)
+	{
+		LevelBufs& L = h->levels[k];
+		const LevelGeom gk = makeGeom(L.W, L.H, h->B, p.patch_radius, p.search_radius);
+		const size_t np = std::max<size_t>((size_t)L.W * L.H, 1);
+		const size_t rowWords = (size_t)std::max(L.H, 1) * markingRowWords(L.W);
+		CU(L.smask.reserve(np * gk.Nw * 4));
+		CU(L.pre.reserve((size_t)std::max(L.H, 1) * prePitchOf(L.W) * std::max(gk.Pw, fastMarkWords(gk.b)) * 4 + 64));
+		CU(L.counts.reserve(np * 4));
+		CU(L.active.reserve(rowWords * 4));
+		CU(L.asBits.reserve(rowWords * 4));
+		CU(L.progress.reserve((size_t)(divUp(std::max(L.H, 1), 32) + 2) * 4));
+		CU(L.fullList.reserve(np * 4));
+		CU(L.fallbackList.reserve(np * 4));
+		CU(L.acc.reserve(np * sizeof(float4)));
+		CU(L.pixcov.reserve(np * 6 * sizeof(float)));
+		CU(L.ctr.reserve(sizeof(DeviceCounters)));
+		if(!L.hostCtr)
+			CU(cudaMallocHost(&L.hostCtr, sizeof(DeviceCounters)));
+		if(!L.evSel)
+			CU(cudaEventCreateWithFlags(&L.evSel, cudaEventDisableTiming));
+		if(!L.evMark)
+			CU(cudaEventCreateWithFlags(&L.evMark, cudaEventDisableTiming));
+	}
 	// filter chunk: bounded scratch (two d x d matrices per slot)
 	const size_t perSlot = (size_t)2 * g.d * g.d * 4;
 	size_t chunk = (size_t)(768u << 20) / perSlot;
@@ -383,8 +413,6 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	const size_t xBytes = (size_t)g.Ns * g.d * 4;
 	if(xBytes + (size_t)g.d * g.d * 4 + 8 * 1024 > 190 * 1024)
 		CU(h->fX.reserve(xBytes * 148 * 2));
-	if(!h->hostCtr)
-		CU(cudaMallocHost(&h->hostCtr, sizeof(DeviceCounters)));
 	for(int i = 0; i < 6; ++i)
 		if(!h->fev[i]) CU(cudaEventCreate(&h->fev[i]));
 	for(int i = 0; i < 2; ++i)
@@ -505,6 +533,18 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		return fail(BCD_B200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
 	}
 	h->stream = h->ownStream;
+	{
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		e = cudaStreamCreateWithPriority(&h->ownAux, cudaStreamNonBlocking, hi);
+		if(e != cudaSuccess)
+		{
+			cudaStreamDestroy(h->ownStream);
+			delete h;
+			return fail(BCD_B200_ERR_CUDA, "cudaStreamCreateWithPriority failed: %s", cudaGetErrorString(e));
+		}
+		h->aux = h->ownAux;
+	}
 	*out = h;
 	return 0;
 }
@@ -514,17 +554,22 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	if(!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
+	cudaStreamSynchronize(h->aux);
 	for(auto& L : h->levels)
 	{
-		L.ownColor.release(); L.ownNs.release(); L.ownHist.release(); L.ownCov.release(); L.out.release();
+		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
+				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr};
+		for(DevBuf* b : lb) b->release();
+		if(L.hostCtr) cudaFreeHost(L.hostCtr);
+		if(L.evSel) cudaEventDestroy(L.evSel);
+		if(L.evMark) cudaEventDestroy(L.evMark);
 	}
-	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->smask, &h->counts, &h->pre, &h->active, &h->asBits, &h->progress,
-			&h->fullList, &h->fallbackList, &h->acc, &h->pixcov, &h->ctr, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX};
+	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX};
 	for(DevBuf* b : bufs) b->release();
 	for(cudaEvent_t e : h->events) cudaEventDestroy(e);
 	for(int i = 0; i < 6; ++i) if(h->fev[i]) cudaEventDestroy(h->fev[i]);
 	for(int i = 0; i < 2; ++i) if(h->evTotal[i]) cudaEventDestroy(h->evTotal[i]);
-	if(h->hostCtr) cudaFreeHost(h->hostCtr);
+	if(h->ownAux) cudaStreamDestroy(h->ownAux);
 	if(h->ownStream) cudaStreamDestroy(h->ownStream);
 	delete h;
 }
@@ -533,6 +578,14 @@ int bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
 	h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->ownStream;
+	return 0;
+}
+
+int bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	h->stream = main_stream ? reinterpret_cast<cudaStream_t>(main_stream) : h->ownStream;
+	h->aux = aux_stream ? reinterpret_cast<cudaStream_t>(aux_stream) : h->ownAux;
 	return 0;
 }
 
@@ -600,12 +653,25 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	h->runParams = *p;
 	rc = buildPyramid(h, s);
 	if(rc) return rc;
-	// coarsest to finest (MultiscaleDenoiser.cpp:79-134); progress mapped like :85,:103-112
-	const float total = float(((1 << (2 * s)) - 1) / 3);
+	// Coarsest to finest (MultiscaleDenoiser.cpp:79-134). The selection of every level is enqueued first on the main
+	// stream; the marking chain of level k runs on the aux stream as soon as its selection is done, i.e. under the
+	// selection of level k-1 and under the filters of the coarser levels; filters and merges follow on the main stream.
 	for(int k = s - 1; k >= 0; --k)
 	{
-		rc = denoiseLevel(h, k, *p);
+		rc = levelSelect(h, k, *p);
 		if(rc) return rc;
+	}
+	for(int k = s - 1; k >= 0; --k)
+	{
+		rc = levelMarkEnqueue(h, k, *p);
+		if(rc) return rc;
+	}
+	const float total = float(((1 << (2 * s)) - 1) / 3); // progress mapped like MultiscaleDenoiser.cpp:85,103-112
+	for(int k = s - 1; k >= 0; --k)
+	{
+		if((rc = levelMarkWait(h, k))) return rc;
+		if((rc = levelFilter(h, k, *p))) return rc;
+		if((rc = levelFinalize(h, k, *p))) return rc;
 		if(k < s - 1)
 		{
 			rc = levelMerge(h, k);
@@ -663,8 +729,8 @@ int bcd_b200_debug_read_selection(bcd_b200_handle* h, uint32_t* masks, int32_t* 
 	if(!h->ran) return fail(BCD_B200_ERR_STATE, "no run yet");
 	CU(cudaSetDevice(h->device));
 	const size_t npix = (size_t)h->g0.W * h->g0.H;
-	if(masks) CU(cudaMemcpy(masks, h->smask.p, npix * h->g0.Nw * 4, cudaMemcpyDeviceToHost));
-	if(counts) CU(cudaMemcpy(counts, h->counts.p, npix * 4, cudaMemcpyDeviceToHost));
+	if(masks) CU(cudaMemcpy(masks, h->levels[0].smask.p, npix * h->g0.Nw * 4, cudaMemcpyDeviceToHost));
+	if(counts) CU(cudaMemcpy(counts, h->levels[0].counts.p, npix * 4, cudaMemcpyDeviceToHost));
 	return 0;
 }
 
@@ -675,7 +741,7 @@ int bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active)
 	CU(cudaSetDevice(h->device));
 	const int Wp = markingRowWords(h->g0.W);
 	std::vector<uint32_t> bits((size_t)h->g0.H * Wp);
-	CU(cudaMemcpy(bits.data(), h->active.p, bits.size() * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(bits.data(), h->levels[0].active.p, bits.size() * 4, cudaMemcpyDeviceToHost));
 	for(int y = 0; y < h->g0.H; ++y)
 		for(int x = 0; x < h->g0.W; ++x)
 		{
@@ -773,12 +839,12 @@ int stripOf(bcd_b200_handle* h, int level, int what, Strip& s)
 	switch(what)
 	{
 	case BCD_B200_XFER_ACC_HALO: // partial sums accumulated outside my band go to their owner and are ADDED there
-		s.base = (char*)h->acc.p; s.rowBytes = (size_t)L.W * sizeof(float4); s.rows = bw;
+		s.base = (char*)L.acc.p; s.rowBytes = (size_t)L.W * sizeof(float4); s.rows = bw;
 		s.exportRow[BCD_B200_SIDE_UP] = own0 - bw; s.exportRow[BCD_B200_SIDE_DOWN] = own1;
 		s.importRow[BCD_B200_SIDE_UP] = own0;      s.importRow[BCD_B200_SIDE_DOWN] = own1 - bw;
 		break;
 	case BCD_B200_XFER_AS_ROWS: // AS bit-rows of my last b owned rows feed the marking of the band below
-		s.base = (char*)h->asBits.p; s.rowBytes = (size_t)markingRowWords(L.W) * 4; s.rows = p.search_radius;
+		s.base = (char*)L.asBits.p; s.rowBytes = (size_t)markingRowWords(L.W) * 4; s.rows = p.search_radius;
 		s.exportRow[BCD_B200_SIDE_UP] = own0;                    s.exportRow[BCD_B200_SIDE_DOWN] = own1 - p.search_radius;
 		s.importRow[BCD_B200_SIDE_UP] = own0 - p.search_radius;  s.importRow[BCD_B200_SIDE_DOWN] = own1;
 		break;
@@ -815,7 +881,8 @@ int bcd_b200_tile_export(bcd_b200_handle* h, int level, int what, int side, void
 	const int row = s.exportRow[side];
 	if(row < 0 || row + s.rows > h->levels[level].H)
 		return fail(BCD_B200_ERR_STATE, "export strip rows [%d,%d) outside the resident band (no neighbour on that side?)", row, row + s.rows);
-	CU(cudaMemcpyAsync(dev_buf, s.base + (size_t)row * s.rowBytes, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->stream));
+	cudaStream_t xs = what == BCD_B200_XFER_AS_ROWS ? h->aux : h->stream; // the marking chain lives on the aux stream
+	CU(cudaMemcpyAsync(dev_buf, s.base + (size_t)row * s.rowBytes, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, xs));
 	return 0;
 }
 
@@ -833,6 +900,12 @@ int bcd_b200_tile_import(bcd_b200_handle* h, int level, int what, int side, cons
 	if(what == BCD_B200_XFER_ACC_HALO)
 		CU(launchAddStrip(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(dev_buf),
 				s.rowBytes * s.rows / sizeof(float4), h->stream, &h->launches));
+	else if(what == BCD_B200_XFER_AS_ROWS)
+	{
+		// the bit-rows are cleared by the selection stage on the main stream: order the copy after it
+		CU(cudaStreamWaitEvent(h->aux, h->levels[level].evSel, 0));
+		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->aux));
+	}
 	else
 		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->stream));
 	return 0;

@@ -56,11 +56,16 @@ def plan(W, H, index, count, params):
 class TileWorker:
     """One tile = one capi.Handle in row-tile mode. Strips travel as 1-D uint8 torch tensors on `device`."""
 
-    def __init__(self, handle, params, tile, torch_device):
+    def __init__(self, handle, params, tile, torch_device, main_stream=None, aux_stream=None):
+        """main_stream / aux_stream: torch.cuda.Stream objects shared with the exchange (NCCL orders its transfers
+        against the current torch stream, so the strips of the marking chain must be moved under `aux_stream`)."""
         import torch
         self.torch = torch
         self.h, self.params, self.tile, self.device = handle, params, tile, torch_device
         self.has = {UP: tile.tile_index > 0, DOWN: tile.tile_index < tile.tile_count - 1}
+        self.main_stream = main_stream if main_stream is not None else torch.cuda.Stream(device=torch_device)
+        self.aux_stream = aux_stream if aux_stream is not None else torch.cuda.Stream(device=torch_device, priority=-1)
+        handle.set_streams(self.main_stream.cuda_stream, self.aux_stream.cuda_stream)
 
     def begin(self):
         capi._check(_lib().bcd_b200_tile_begin(self.h._h, C.byref(self.params), C.byref(self.tile)))
@@ -127,23 +132,26 @@ def run_tile(worker, ex):
     import torch
     p = worker.params
     s = p.nb_scales
-    worker.begin()
-    for k in range(s - 1, -1, -1):
-        worker.stage("select", k)
-        if p.skip_prob > 0 and worker.has[UP]:
-            buf = torch.empty(worker.strip_bytes(k, AS_ROWS), dtype=torch.uint8, device=worker.device)
-            worker.import_(k, AS_ROWS, UP, ex.recv_from_up(buf))
-        worker.stage("mark", k)
-        if p.skip_prob > 0 and worker.has[DOWN]:
-            ex.send_down(worker.export(k, AS_ROWS, DOWN))
-        worker.stage("filter", k)
-        _swap_and_import(worker, ex, k, ACC_HALO)
-        worker.stage("finalize", k)
-        _swap_and_import(worker, ex, k, OUT_ROWS)
-        if k < s - 1:
-            worker.stage("merge", k)
+    with torch.cuda.stream(worker.main_stream):
+        worker.begin()
+        for k in range(s - 1, -1, -1):  # every selection first: the marking chain below overlaps it
+            worker.stage("select", k)
+        for k in range(s - 1, -1, -1):
+            with torch.cuda.stream(worker.aux_stream):
+                if p.skip_prob > 0 and worker.has[UP]:
+                    buf = torch.empty(worker.strip_bytes(k, AS_ROWS), dtype=torch.uint8, device=worker.device)
+                    worker.import_(k, AS_ROWS, UP, ex.recv_from_up(buf))
+                worker.stage("mark", k)  # blocks the host until this rank's part of the chain is done
+                if p.skip_prob > 0 and worker.has[DOWN]:
+                    ex.send_down(worker.export(k, AS_ROWS, DOWN))
+            worker.stage("filter", k)
+            _swap_and_import(worker, ex, k, ACC_HALO)
+            worker.stage("finalize", k)
             _swap_and_import(worker, ex, k, OUT_ROWS)
-    worker.end()
+            if k < s - 1:
+                worker.stage("merge", k)
+                _swap_and_import(worker, ex, k, OUT_ROWS)
+        worker.end()
 
 
 def _swap_and_import(worker, ex, level, what):
@@ -174,6 +182,7 @@ def run_tiles_loopback(workers):
     for k in range(s - 1, -1, -1):
         for w in workers:
             w.stage("select", k)
+    for k in range(s - 1, -1, -1):
         for i, w in enumerate(workers):  # the marking chain, top to bottom
             if p.skip_prob > 0 and i > 0:
                 w.import_(k, AS_ROWS, UP, workers[i - 1].export(k, AS_ROWS, DOWN))
@@ -193,18 +202,17 @@ def run_tiles_loopback(workers):
     assert n == workers[0].tile.tile_count
 
 
-def make_worker(inputs_full, params, index, count, device_index=0, stream_ptr=None):
+def make_worker(inputs_full, params, index, count, device_index=0, main_stream=None, aux_stream=None):
     """Uploads the rows of tile `index` of a full-frame dict(color,nsamples,hist,cov) and returns its TileWorker.
-    Workers that exchange strips must share one stream (pass the cuda_stream of an explicit torch.cuda.Stream)."""
+    Workers that exchange strips in one process must share their two streams (explicit torch.cuda.Stream objects)."""
     import torch
     H, W, _ = inputs_full["color"].shape
     t = plan(W, H, index, count, params)
     sub = {k: np.ascontiguousarray(v[t.sub_row0:t.sub_row1]) for k, v in inputs_full.items()}
     h = capi.Handle(device_index)
-    if stream_ptr is not None:
-        h.set_stream(stream_ptr)
+    worker = TileWorker(h, params, t, torch.device("cuda", device_index), main_stream, aux_stream)
     h.upload(**sub)
-    return TileWorker(h, params, t, torch.device("cuda", device_index))
+    return worker
 
 
 # ---------------------------------------------------------------------------------------------------------- bench
@@ -235,10 +243,10 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
     # an explicit (non-default) stream shared by torch/NCCL and the handle: the legacy default stream has handle 0,
     # which bcd_b200_set_stream reads as "use the handle's own stream" and would leave the strips unordered
     stream = torch.cuda.Stream(device=dev)
+    aux = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
     h = capi.Handle(local_rank)
-    h.set_stream(stream.cuda_stream)
-    worker = TileWorker(h, params, t, dev)
+    worker = TileWorker(h, params, t, dev, stream, aux)
     ex = DistExchange(dist, rank, world)
 
     def step_resident():

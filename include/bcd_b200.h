@@ -104,6 +104,9 @@ int  bcd_b200_create(bcd_b200_handle** out, int device);
 void bcd_b200_destroy(bcd_b200_handle* h);
 /* optional: run on a caller-owned stream (cudaStream_t passed as void*); NULL restores the handle's own stream */
 int  bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream);
+/* main + auxiliary stream: the marking stage (and its AS_ROWS strips in row-tile mode) runs on the auxiliary stream so
+ * that it overlaps the selection of the next finer level; NULL keeps the handle's own (high-priority) stream */
+int  bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream);
 /* host -> device copy of the four input images (pinned or pageable host memory) */
 int  bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in);
 /* same, but the pointers in `in` are DEVICE pointers that the handle borrows until the next upload/bind/destroy */

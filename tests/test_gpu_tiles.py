@@ -21,9 +21,9 @@ def _full(capi, inp, **kw):
 def _tiled(capi, tiles, inp, count, **kw):
     import torch
     params = capi.make_params(**kw)
-    stream = torch.cuda.Stream()  # all tiles exchange strips on one stream
+    stream, aux = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)  # all tiles exchange strips on shared streams
     with torch.cuda.stream(stream):
-        workers = [tiles.make_worker(inp, params, i, count, stream_ptr=stream.cuda_stream) for i in range(count)]
+        workers = [tiles.make_worker(inp, params, i, count, main_stream=stream, aux_stream=aux) for i in range(count)]
         tiles.run_tiles_loopback(workers)
         out = np.concatenate([w.download() for w in workers], axis=0)
     st = {}

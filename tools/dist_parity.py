@@ -18,7 +18,7 @@ def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    stream = torch.cuda.Stream()
+    stream, aux = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     torch.cuda.set_stream(stream)
     W, H = 640, 64 * world + 96
     ok = True
@@ -28,9 +28,8 @@ def main():
         rows = t.sub_row1 - t.sub_row0
         sub = host.synth(W, H, spp=24, row0=t.sub_row0, rows=rows)
         h = capi.Handle(lr)
-        h.set_stream(stream.cuda_stream)
+        worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr), stream, aux)
         h.upload(**sub)
-        worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr))
         tiles.run_tile(worker, tiles.DistExchange(dist, rank, world))
         mine = torch.from_numpy(worker.download()).cuda()
         sizes = [tiles.plan(W, H, i, world, params) for i in range(world)]
