@@ -209,7 +209,7 @@ struct FilterSmem
 	float* mean;          // [d]
 	float* noise;         // [np*6]
 	float* Minv;          // [d*d]  (apply kernels)
-	float* vec;           // [NG][3][dpad] per-group vectors (apply kernels)
+	float* vec;           // [NG][3][d] float4 per-group vectors (apply kernels), 16-byte aligned
 	float* red;           // [32]
 	uint32_t* words;      // [Nw]
 	int* prefix;          // [Nw+1]
@@ -221,7 +221,7 @@ static size_t filterSmemBytes(const LevelGeom& g, bool xInSmem, bool withMinv, i
 	size_t f = 0;
 	if(xInSmem) f += (size_t)g.Ns * g.d;
 	f += g.d + g.np * 6 + 32;
-	if(withMinv) f += (size_t)g.d * g.d + (size_t)ng * 3 * g.d;
+	if(withMinv) f += (size_t)g.d * g.d + (size_t)ng * 12 * g.d + 4;
 	size_t bytes = f * 4 + (size_t)g.Nw * 4 + (size_t)(g.Nw + 1) * 4 + (size_t)g.Ns * 2;
 	return (bytes + 15) & ~(size_t)15;
 }
@@ -236,7 +236,12 @@ __device__ __forceinline__ FilterSmem carveFilterSmem(unsigned char* raw, const 
 	s.noise = f; f += g.np * 6;
 	s.red = f; f += 32;
 	s.Minv = nullptr; s.vec = nullptr;
-	if(withMinv) { s.Minv = f; f += (size_t)g.d * g.d; s.vec = f; f += (size_t)ng * 3 * g.d; }
+	if(withMinv)
+	{
+		s.Minv = f; f += (size_t)g.d * g.d;
+		f = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(f) + 15) & ~(uintptr_t)15); // float4 vectors
+		s.vec = f; f += (size_t)ng * 12 * g.d;
+	}
 	s.words = reinterpret_cast<uint32_t*>(f);
 	s.prefix = reinterpret_cast<int*>(s.words + g.Nw);
 	s.qlist = reinterpret_cast<unsigned short*>(s.prefix + g.Nw + 1);
@@ -274,7 +279,7 @@ __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, 
 		r += c; // r >= c
 		float a = 0.f;
 		for(int i = 0; i < n; ++i)
-			a = __fadd_rn(a, __fmul_rn(X[i * d + r], X[i * d + c]));
+			a = fmaf(X[i * d + r], X[i * d + c], a); // products summed in patch order (fused: rounding-level difference)
 		a = __fmul_rn(a, invn1);
 		if(r / 3 == c / 3)
 			a = __fadd_rn(a, __fmul_rn(sgn, noise[(r / 3) * 6 + symIndex(r % 3, c % 3)]));
@@ -337,12 +342,13 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	constexpr int NG = NT / GS;
+	constexpr int PB = 4; // similar patches per group iteration: one Minv load feeds 4 FMAs (register blocking)
 	const int d = g.d, np = g.np, pw = 2 * g.w + 1, tid = threadIdx.x;
 	const int gi = tid / GS, gl = tid - gi * GS;
 	FilterSmem s = carveFilterSmem(smemRaw, g, xScratch ? xScratch + (size_t)blockIdx.x * g.Ns * d : nullptr, true, NG);
-	float* xcv = s.vec + (size_t)gi * 3 * d;
-	float* tv = xcv + d;
-	float* zv = tv + d;
+	float4* xcv4 = reinterpret_cast<float4*>(s.vec) + (size_t)gi * 3 * d; // [d] centred patches (4 at a time)
+	float4* tv4 = xcv4 + d;                                                 // [d] -(Minv xc)
+	float4* zv4 = tv4 + d;                                                  // [d] outputs (step 2)
 	for(int slot = blockIdx.x; slot < count; slot += gridDim.x)
 	{
 		const int p = list[first + slot];
@@ -356,53 +362,77 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 		for(int e = tid; e < np * 6; e += NT)
 			s.noise[e] = noiseG[(size_t)slot * np * 6 + e];
 		__syncthreads();
-		for(int i0 = 0; i0 < n; i0 += NG)
+		for(int i0 = 0; i0 < n; i0 += NG * PB)
 		{
-			const int i = i0 + gi;
-			const bool valid = i < n;
-			float* Xi = s.X + (size_t)(valid ? i : 0) * d;
+			const int ib = i0 + gi * PB;                    // first patch of this group
+			const int nv = min(max(n - ib, 0), PB);         // valid patches of this group
+			const float* X0 = s.X + (size_t)min(ib, n - 1) * d;
+			const float* X1 = s.X + (size_t)min(ib + 1, n - 1) * d;
+			const float* X2 = s.X + (size_t)min(ib + 2, n - 1) * d;
+			const float* X3 = s.X + (size_t)min(ib + 3, n - 1) * d;
 			for(int c = gl; c < d; c += GS)
-				xcv[c] = __fsub_rn(Xi[c], s.mean[c]);
+			{
+				const float m = s.mean[c];
+				xcv4[c] = make_float4(__fsub_rn(X0[c], m), __fsub_rn(X1[c], m), __fsub_rn(X2[c], m), __fsub_rn(X3[c], m));
+			}
 			__syncthreads();
 			for(int r = gl; r < d; r += GS)
 			{
-				float a = 0.f;
+				float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 				for(int c = 0; c < d; ++c)
-					a = __fadd_rn(a, __fmul_rn(s.Minv[r + c * d], xcv[c]));
-				tv[r] = __fmul_rn(a, -1.f);
+				{
+					const float m = s.Minv[r + c * d];
+					const float4 v = xcv4[c];
+					a0 = fmaf(m, v.x, a0); a1 = fmaf(m, v.y, a1); a2 = fmaf(m, v.z, a2); a3 = fmaf(m, v.w, a3);
+				}
+				tv4[r] = make_float4(-a0, -a1, -a2, -a3);
 			}
 			__syncthreads();
 			for(int jj = gl; jj < d; jj += GS)
 			{
-				const int k = jj / 3, a3 = jj - 3 * k;
+				const int k = jj / 3, a3i = jj - 3 * k;
 				const float* cb = s.noise + 6 * k;
-				const float* t3 = tv + 3 * k;
+				const float c0 = cb[symIndex(a3i, 0)], c1 = cb[symIndex(a3i, 1)], c2 = cb[symIndex(a3i, 2)];
+				const float4 t0 = tv4[3 * k], t1 = tv4[3 * k + 1], t2 = tv4[3 * k + 2];
 				// multiplyCovMatPatchByVector :633-654 (left-to-right sums), then += noisy patch (:668)
-				float o = __fadd_rn(__fadd_rn(__fmul_rn(cb[symIndex(a3, 0)], t3[0]), __fmul_rn(cb[symIndex(a3, 1)], t3[1])),
-						__fmul_rn(cb[symIndex(a3, 2)], t3[2]));
-				o = __fadd_rn(o, Xi[jj]);
+				float4 o;
+				o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.x), __fmul_rn(c1, t1.x)), __fmul_rn(c2, t2.x)), X0[jj]);
+				o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.y), __fmul_rn(c1, t1.y)), __fmul_rn(c2, t2.y)), X1[jj]);
+				o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.z), __fmul_rn(c1, t1.z)), __fmul_rn(c2, t2.z)), X2[jj]);
+				o.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c0, t0.w), __fmul_rn(c1, t1.w)), __fmul_rn(c2, t2.w)), X3[jj]);
 				if(STEP == 1)
 				{
-					if(valid) Xi[jj] = o;
+					// in place: every group owns its PB rows; rows are distinct when valid
+					float* Xw = s.X + (size_t)ib * d + jj;
+					if(nv > 0) Xw[0] = o.x;
+					if(nv > 1) Xw[d] = o.y;
+					if(nv > 2) Xw[2 * d] = o.z;
+					if(nv > 3) Xw[3 * d] = o.w;
 				}
 				else
-					zv[jj] = o;
+					zv4[jj] = o;
 			}
 			if(STEP == 2)
 			{
 				__syncthreads();
-				if(valid)
+				for(int e = gl; e < nv * np; e += GS)
 				{
-					const int idx = s.qlist[i];
+					const int pi = e / np, k = e - pi * np;
+					const int idx = s.qlist[ib + pi];
 					const int qy = py + idx / g.side - g.b, qx = px + idx % g.side - g.b;
-					for(int k = gl; k < np; k += GS)
-					{
-						const size_t x = (size_t)(qy + k / pw - g.w) * g.W + (qx + k % pw - g.w);
-						atomicAdd(acc + x, make_float4(zv[3 * k], zv[3 * k + 1], zv[3 * k + 2], 1.f));
-					}
+					const size_t x = (size_t)(qy + k / pw - g.w) * g.W + (qx + k % pw - g.w);
+					const float4 zr = zv4[3 * k], zg = zv4[3 * k + 1], zb = zv4[3 * k + 2];
+					const float r = pi == 0 ? zr.x : pi == 1 ? zr.y : pi == 2 ? zr.z : zr.w;
+					const float gg = pi == 0 ? zg.x : pi == 1 ? zg.y : pi == 2 ? zg.z : zg.w;
+					const float bb = pi == 0 ? zb.x : pi == 1 ? zb.y : pi == 2 ? zb.z : zb.w;
+					atomicAdd(acc + x, make_float4(r, gg, bb, 1.f));
 				}
 			}
-			// the next iteration writes xcv before its first barrier; zv/tv are rewritten only after that barrier
+			// STEP 1: rows written above are read again (as X0..X3) only by their own group, in the next slot's
+			// gather or in meanCenterCov after the barrier below. The next iteration rewrites xcv4 before its first
+			// barrier (its readers passed the second barrier), tv4/zv4 only after that barrier.
+			if(STEP == 1)
+				__syncthreads(); // X0..X3 of a short last group alias row n-1, which another group may be writing
 		}
 		__syncthreads();
 		if(STEP == 1)

@@ -13,6 +13,10 @@ ncu --set full --clock-control none --import-source on -k regex:k_pair_terms -s 
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_pair.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_eig_chain -s 4 -c 1 -f -o gpurun_out/prof_eig \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_eig.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_patch_select -s 2 -c 1 -f -o gpurun_out/prof_sel \
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_sel.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_filter_apply -s 4 -c 1 -f -o gpurun_out/prof_apply \
+    timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_apply.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_marking -s 2 -c 1 -f -o gpurun_out/prof_mark \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_mark.log 2>&1
 ls -la gpurun_out
