@@ -73,11 +73,11 @@ __device__ __forceinline__ float blockReduceMax(float v, float* red)
 	return t;
 }
 
-// Expand the ordered similar set S(p) into the list of window indices (ascending = the order
-// selectSimilarPatches pushes the centres). words: smem [Nw], prefix: smem [Nw+1]. Returns n (uniform).
+// Expand the ordered similar set S(p) into the list of the similar patch centres' pixel indices (ascending window
+// index = the order selectSimilarPatches pushes the centres). words: smem [Nw], prefix: smem [Nw+1]. Returns n.
 template <int NT>
-__device__ int expandSimilarList(const uint32_t* __restrict__ smaskP, const LevelGeom& g, uint32_t* words, int* prefix,
-		unsigned short* qlist)
+__device__ int expandSimilarList(const uint32_t* __restrict__ smaskP, const LevelGeom& g, int px, int py, uint32_t* words,
+		int* prefix, int* qbase)
 {
 	const int tid = threadIdx.x;
 	__syncthreads();
@@ -100,27 +100,29 @@ __device__ int expandSimilarList(const uint32_t* __restrict__ smaskP, const Leve
 		const uint32_t wv = words[idx >> 5];
 		const int bit = idx & 31;
 		if((wv >> bit) & 1u)
-			qlist[prefix[idx >> 5] + __popc(wv & ((1u << bit) - 1u))] = (unsigned short)idx;
+		{
+			const int dy = idx / g.side, dx = idx - dy * g.side;
+			qbase[prefix[idx >> 5] + __popc(wv & ((1u << bit) - 1u))] = (py + dy - g.b) * g.W + (px + dx - g.b);
+		}
 	}
 	__syncthreads();
 	return prefix[g.Nw];
 }
 
-// X[i][jj] = colour of patch pixel k = jj/3 (row-major) channel jj%3 of the i-th similar patch (:483-498)
+// X[i][jj] = colour of patch pixel k = jj/3 (row-major) channel jj%3 of the i-th similar patch (:483-498).
+// Thread t owns component jj = t % d for the patches i = t / d, t / d + NT / d, ... (no division in the loop).
 template <int NT>
-__device__ void gatherPatches(const float* __restrict__ color, const LevelGeom& g, int px, int py,
-		const unsigned short* qlist, int n, float* X)
+__device__ void gatherPatches(const float* __restrict__ color, const LevelGeom& g, const int* qbase, int n, float* X)
 {
 	const int d = g.d, pw = 2 * g.w + 1;
-	for(int e = threadIdx.x; e < n * d; e += NT)
-	{
-		const int i = e / d, jj = e - i * d;
-		const int k = jj / 3, ch = jj - 3 * k;
-		const int idx = qlist[i];
-		const int qy = py + idx / g.side - g.b + k / pw - g.w;
-		const int qx = px + idx % g.side - g.b + k % pw - g.w;
-		X[e] = __ldg(color + ((size_t)qy * g.W + qx) * 3 + ch);
-	}
+	const int groups = NT / d;
+	const int jj = threadIdx.x % d, i0 = threadIdx.x / d;
+	if(i0 >= groups)
+		return;
+	const int k = jj / 3, ch = jj - 3 * k;
+	const int off = ((k / pw - g.w) * g.W + (k % pw - g.w)) * 3 + ch;
+	for(int i = i0; i < n; i += groups)
+		X[i * d + jj] = __ldg(color + (size_t)qbase[i] * 3 + off);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -213,7 +215,7 @@ struct FilterSmem
 	float* red;           // [32]
 	uint32_t* words;      // [Nw]
 	int* prefix;          // [Nw+1]
-	unsigned short* qlist; // [Ns]
+	int* qbase;           // [Ns] pixel index of every similar patch centre
 };
 
 static size_t filterSmemBytes(const LevelGeom& g, bool xInSmem, bool withMinv, int ng)
@@ -222,7 +224,7 @@ static size_t filterSmemBytes(const LevelGeom& g, bool xInSmem, bool withMinv, i
 	if(xInSmem) f += (size_t)g.Ns * g.d;
 	f += g.d + g.np * 6 + 32;
 	if(withMinv) f += (size_t)g.d * g.d + (size_t)ng * 12 * g.d + 4;
-	size_t bytes = f * 4 + (size_t)g.Nw * 4 + (size_t)(g.Nw + 1) * 4 + (size_t)g.Ns * 2;
+	size_t bytes = f * 4 + (size_t)g.Nw * 4 + (size_t)(g.Nw + 1) * 4 + (size_t)g.Ns * 4;
 	return (bytes + 15) & ~(size_t)15;
 }
 
@@ -244,7 +246,7 @@ __device__ __forceinline__ FilterSmem carveFilterSmem(unsigned char* raw, const 
 	}
 	s.words = reinterpret_cast<uint32_t*>(f);
 	s.prefix = reinterpret_cast<int*>(s.words + g.Nw);
-	s.qlist = reinterpret_cast<unsigned short*>(s.prefix + g.Nw + 1);
+	s.qbase = s.prefix + g.Nw + 1;
 	return s;
 }
 
@@ -267,8 +269,15 @@ __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, 
 		meanOut[jj] = a;
 	}
 	__syncthreads();
-	for(int e = tid; e < n * d; e += NT)
-		X[e] = __fsub_rn(X[e], mean[e % d]);
+	{
+		const int groups = NT / d, jj = tid % d, i0 = tid / d;
+		if(i0 < groups)
+		{
+			const float m = mean[jj];
+			for(int i = i0; i < n; i += groups)
+				X[i * d + jj] = __fsub_rn(X[i * d + jj], m);
+		}
+	}
 	__syncthreads();
 	const float invn1 = __fdiv_rn(1.f, (float)(n - 1));
 	const int L = d * (d + 1) / 2;
@@ -304,21 +313,17 @@ k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov
 	{
 		const int p = list[first + slot];
 		const int py = p / g.W, px = p - py * g.W;
-		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, s.words, s.prefix, s.qlist);
-		gatherPatches<NT>(color, g, px, py, s.qlist, n, s.X);
+		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, px, py, s.words, s.prefix, s.qbase);
+		gatherPatches<NT>(color, g, s.qbase, n, s.X);
 		// Sigma_n[k] = (1/n) sum_i pixelCov(q_i + o_k)   (:400-419)
 		const float invn = __fdiv_rn(1.f, (float)n);
 		for(int e = tid; e < np * 6; e += NT)
 		{
 			const int k = e / 6, el = e - 6 * k;
-			const int oy = k / pw - g.w, ox = k % pw - g.w;
+			const int off6 = ((k / pw - g.w) * g.W + (k % pw - g.w)) * 6 + el;
 			float a = 0.f;
 			for(int i = 0; i < n; ++i)
-			{
-				const int idx = s.qlist[i];
-				const int qy = py + idx / g.side - g.b + oy, qx = px + idx % g.side - g.b + ox;
-				a = __fadd_rn(a, __ldg(pixcov + ((size_t)qy * g.W + qx) * 6 + el));
-			}
+				a = __fadd_rn(a, __ldg(pixcov + (size_t)s.qbase[i] * 6 + off6));
 			a = __fmul_rn(a, invn);
 			s.noise[e] = a;
 			noiseG[(size_t)slot * np * 6 + e] = a;
@@ -353,8 +358,8 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 	{
 		const int p = list[first + slot];
 		const int py = p / g.W, px = p - py * g.W;
-		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, s.words, s.prefix, s.qlist);
-		gatherPatches<NT>(color, g, px, py, s.qlist, n, s.X);
+		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, px, py, s.words, s.prefix, s.qbase);
+		gatherPatches<NT>(color, g, s.qbase, n, s.X);
 		for(int e = tid; e < d * d; e += NT)
 			s.Minv[e] = MinvG[(size_t)slot * d * d + e];
 		for(int e = tid; e < d; e += NT)
@@ -418,9 +423,7 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 				for(int e = gl; e < nv * np; e += GS)
 				{
 					const int pi = e / np, k = e - pi * np;
-					const int idx = s.qlist[ib + pi];
-					const int qy = py + idx / g.side - g.b, qx = px + idx % g.side - g.b;
-					const size_t x = (size_t)(qy + k / pw - g.w) * g.W + (qx + k % pw - g.w);
+					const size_t x = (size_t)(s.qbase[ib + pi] + (k / pw - g.w) * g.W + (k % pw - g.w));
 					const float4 zr = zv4[3 * k], zg = zv4[3 * k + 1], zb = zv4[3 * k + 2];
 					const float r = pi == 0 ? zr.x : pi == 1 ? zr.y : pi == 2 ? zr.z : zr.w;
 					const float gg = pi == 0 ? zg.x : pi == 1 ? zg.y : pi == 2 ? zg.z : zg.w;
