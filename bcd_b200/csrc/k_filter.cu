@@ -457,22 +457,38 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 // ---------------------------------------------------------------------------------------------------------------
 #define MAT(r, c) M[(r) + (c) * n]
 
+__device__ __forceinline__ float ldsF(uint32_t addr)
+{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void stsF(uint32_t addr, float v)
+{
+	asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+
 // JacobiRotation::makeGivens (Jacobi.h:216-252): c = p/r, s = -q/r with r = sqrt(p^2+q^2) in every branch of the
 // reference (the branches only guard against overflow). The matrix is scaled into [-1,1], so p^2+q^2 cannot
-// overflow; the common range uses rsqrt + one Newton step (<= 1 ulp), tiny magnitudes take the reference's formulas.
+// overflow; the common range uses rsqrt + one Newton step (<= 1 ulp) with the exact +-1 / 0 values of the
+// reference's q == 0 and p == 0 cases patched in by selects; tiny magnitudes take the reference's formulas.
 __device__ __forceinline__ void makeGivens(float p, float q, float& c, float& s)
 {
-	if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; return; }
-	if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; return; }
 	const float h2 = fmaf(p, p, q * q);
 	if(h2 > 1e-30f)
 	{
-		float ri = rsqrtf(h2);
+		float ri;
+		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ri) : "f"(h2));
 		ri = ri * fmaf(-0.5f * h2, ri * ri, 1.5f);
 		c = p * ri;
 		s = -q * ri;
+		if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; }
+		if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; }
+		return;
 	}
-	else if(fabsf(p) > fabsf(q))
+	if(q == 0.f) { c = p < 0.f ? -1.f : 1.f; s = 0.f; return; }
+	if(p == 0.f) { c = 0.f; s = q < 0.f ? 1.f : -1.f; return; }
+	if(fabsf(p) > fabsf(q))
 	{
 		const float t = __fdiv_rn(q, p);
 		float u = __fsqrt_rn(fmaf(t, t, 1.f));
@@ -651,12 +667,18 @@ __device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
 			float z = S.sub[start];
 			float dk = S.diag[start], sk = S.sub[start], skm1 = 0.f;
 			const bool hasRow = tid < n;
-			float qk = hasRow ? MAT(tid, start) : 0.f;
+			// raw shared-window addresses: the bulge-chase loop below is the hot spot of the whole filter, and generic
+			// pointers make the compiler rebuild the shared base and reload `n` on every rotation
+			const uint32_t diagA = (uint32_t)__cvta_generic_to_shared(S.diag), subA = (uint32_t)__cvta_generic_to_shared(S.sub);
+			const uint32_t dWA = (uint32_t)__cvta_generic_to_shared(S.dW), sWA = (uint32_t)__cvta_generic_to_shared(S.sW);
+			const uint32_t colStep = 4u * (uint32_t)n;
+			uint32_t qA = (uint32_t)__cvta_generic_to_shared(M) + 4u * (uint32_t)(hasRow ? tid : 0) + colStep * (uint32_t)start; // &Q(tid, k)
+			float qk = hasRow ? ldsF(qA) : 0.f;
 			for(int k = start; k < end; ++k)
 			{
 				float c, s;
 				makeGivens(x, z, c, s);
-				const float dk1 = S.diag[k + 1];
+				const float dk1 = ldsF(diagA + 4u * (uint32_t)(k + 1));
 				const float sdk = fmaf(s, dk, c * sk);
 				const float dkp1 = fmaf(s, sk, c * dk1);
 				const float ndk = fmaf(c, fmaf(c, dk, -s * sk), -s * fmaf(c, sk, -s * dk1));
@@ -664,28 +686,29 @@ __device__ void eigFunction(const EigSmem& S, int n, int mode, float eps)
 				const float nsk = fmaf(c, sdk, -s * dkp1);
 				if(tid == 0)
 				{
-					S.dW[k] = ndk;
-					if(k > start) S.sW[k - 1] = fmaf(c, skm1, -s * z);
+					stsF(dWA + 4u * (uint32_t)k, ndk);
+					if(k > start) stsF(sWA + 4u * (uint32_t)(k - 1), fmaf(c, skm1, -s * z));
 				}
 				x = nsk;
 				float nsk1 = 0.f;
 				if(k < end - 1)
 				{
-					const float sk1 = S.sub[k + 1];
+					const float sk1 = ldsF(subA + 4u * (uint32_t)(k + 1));
 					z = -s * sk1;
 					nsk1 = c * sk1;
 				}
 				if(hasRow)
 				{
-					const float y = MAT(tid, k + 1);
-					MAT(tid, k) = fmaf(c, qk, -s * y);
+					const float y = ldsF(qA + colStep);
+					stsF(qA, fmaf(c, qk, -s * y));
 					qk = fmaf(s, qk, c * y);
 				}
+				qA += colStep;
 				dk = ndk1;
 				skm1 = nsk;
 				sk = nsk1;
 			}
-			if(hasRow) MAT(tid, end) = qk;
+			if(hasRow) stsF(qA, qk);
 			if(tid == 0)
 			{
 				S.dW[end] = dk;
