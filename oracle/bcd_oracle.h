@@ -47,6 +47,9 @@ void bcdo_merge(float* hi, int W, int H, const float* low_out);
 int  bcdo_denoise_multiscale(const float* color, const float* ns, const float* hist, const float* cov,
 		int W, int H, int B, const bcdo_params* p, int nscales, float* out);
 
+/* row f1: SpikeRemovalFilter (in place); src_index optional */
+void bcdo_spike_removal(float* color, float* ns, float* hist, float* cov, int W, int H, int B, float factor, int* src_index);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,21 @@ def port_denoise(color, nsamples, hist, cov, tau=1.0, w=1, b=6, eps=1e-8, m=1.0,
     if want_stats:
         return out, {k: getattr(st, k) for k, _ in _Stats._fields_}
     return out
+
+
+def ref_spike_removal(color, nsamples, hist, cov, factor=2.0):
+    """Reference SpikeRemovalFilter::filter (in place in the reference) -> filtered copies."""
+    H, W, _ = color.shape
+    c, n, h, v = [np.ascontiguousarray(a, np.float32).copy() for a in (color, nsamples, hist, cov)]
+    ref_lib().bcdref_spike_removal(c, n, h, v, W, H, h.shape[2], factor)
+    return dict(color=c, nsamples=n, hist=h, cov=v)
+
+
+def port_spike_removal(color, nsamples, hist, cov, factor=2.0):
+    H, W, _ = color.shape
+    c, n, h, v = [np.ascontiguousarray(a, np.float32).copy() for a in (color, nsamples, hist, cov)]
+    src = np.zeros((H, W), np.int32)
+    L = port_lib()
+    L.bcdo_spike_removal.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _i32p]
+    L.bcdo_spike_removal(c, n, h, v, W, H, h.shape[2], factor, src)
+    return dict(color=c, nsamples=n, hist=h, cov=v), src
