@@ -21,6 +21,7 @@ SYMBOLS = [
     "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_set_streams", "bcd_b200_upload",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
+    "bcd_b200_spike_removal", "bcd_b200_spike_removal_host", "bcd_b200_download_inputs",
     # row-tile API (multi-GPU), wrapped by bcd_b200/tiles.py
     "bcd_b200_tile_plan", "bcd_b200_tile_begin", "bcd_b200_tile_select", "bcd_b200_tile_mark", "bcd_b200_tile_filter",
     "bcd_b200_tile_finalize", "bcd_b200_tile_merge", "bcd_b200_tile_xfer_bytes", "bcd_b200_tile_export",
@@ -85,6 +86,10 @@ def lib():
         L.bcd_b200_mask_words.argtypes = [C.c_int]
         L.bcd_b200_debug_read_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_debug_read_active.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_spike_removal.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.bcd_b200_download_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bcd_b200_spike_removal_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                  C.c_float, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -184,6 +189,18 @@ class Handle:
         p = C.c_void_p()
         _check(lib().bcd_b200_result_device_ptr(self._h, C.byref(p)))
         return p.value
+
+    def spike_removal(self, factor=2.0, int_abs=True):
+        """SpikeRemovalFilter on the resident (uploaded) inputs; they stay resident for the next run."""
+        _check(lib().bcd_b200_spike_removal(self._h, float(factor), int(bool(int_abs))))
+
+    def download_inputs(self):
+        H, W, B = self.shape
+        out = dict(color=np.empty((H, W, 3), np.float32), nsamples=np.empty((H, W, 1), np.float32),
+                   hist=np.empty((H, W, B), np.float32), cov=np.empty((H, W, 6), np.float32))
+        _check(lib().bcd_b200_download_inputs(self._h, out["color"].ctypes.data, out["nsamples"].ctypes.data,
+                                              out["hist"].ctypes.data, out["cov"].ctypes.data))
+        return out
 
     def stats(self):
         s = Stats()

@@ -72,6 +72,7 @@ struct LevelBufs
 	int W = 0, H = 0;
 	const float *color = nullptr, *ns = nullptr, *hist = nullptr, *cov = nullptr; // inputs of this level
 	DevBuf ownColor, ownNs, ownHist, ownCov;                                         // storage when owned
+	DevBuf altColor, altNs, altHist, altCov;                                         // second set (spike prefilter output)
 	DevBuf out;                                                                      // W*H*3
 	// per-level state of the hot path (kept per level so that the stages of different levels can overlap)
 	DevBuf smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr;
@@ -557,7 +558,7 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	cudaStreamSynchronize(h->aux);
 	for(auto& L : h->levels)
 	{
-		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
+		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.altColor, &L.altNs, &L.altHist, &L.altCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
 				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr};
 		for(DevBuf* b : lb) b->release();
 		if(L.hostCtr) cudaFreeHost(L.hostCtr);
@@ -934,6 +935,66 @@ int bcd_b200_tile_download(bcd_b200_handle* h, float* out_rows)
 	CU(cudaMemcpyAsync(out_rows, (char*)h->levels[0].out.p + (size_t)own0 * rowBytes, rowBytes * (own1 - own0), cudaMemcpyDeviceToHost, h->stream));
 	CU(cudaStreamSynchronize(h->stream));
 	return 0;
+}
+
+int bcd_b200_spike_removal(bcd_b200_handle* h, float threshold_std_factor, int int_abs)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "bcd_b200_spike_removal called before upload");
+	LevelBufs& L = h->levels[0];
+	if(L.color != L.ownColor.as<float>() && L.color != L.altColor.as<float>())
+		return fail(BCD_B200_ERR_STATE, "bcd_b200_spike_removal needs uploaded inputs (bound device inputs are never modified)");
+	if(h->W < 3 || h->H < 3)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "spike removal needs at least a 3x3 image");
+	CU(cudaSetDevice(h->device));
+	const size_t np = (size_t)h->W * h->H;
+	const bool fromOwn = L.color == L.ownColor.as<float>();
+	DevBuf& oc = fromOwn ? L.altColor : L.ownColor;
+	DevBuf& on = fromOwn ? L.altNs : L.ownNs;
+	DevBuf& oh = fromOwn ? L.altHist : L.ownHist;
+	DevBuf& ov = fromOwn ? L.altCov : L.ownCov;
+	CU(oc.reserve(np * 3 * sizeof(float)));
+	CU(on.reserve(np * sizeof(float)));
+	CU(oh.reserve(np * h->B * sizeof(float)));
+	CU(ov.reserve(np * 6 * sizeof(float)));
+	CU(L.fullList.reserve(np * 4)); // scratch: source pixel of every output pixel
+	CU(launchSpikeFilter(L.color, L.ns, L.hist, L.cov, h->W, h->H, h->B, threshold_std_factor, int_abs ? 1 : 0,
+			L.fullList.as<int>(), oc.as<float>(), on.as<float>(), oh.as<float>(), ov.as<float>(), h->stream, &h->launches));
+	CU(cudaStreamSynchronize(h->stream));
+	L.color = oc.as<float>(); L.ns = on.as<float>(); L.hist = oh.as<float>(); L.cov = ov.as<float>();
+	h->ran = false;
+	return 0;
+}
+
+int bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples, float* hist, float* cov)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "no resident inputs");
+	CU(cudaSetDevice(h->device));
+	const LevelBufs& L = h->levels[0];
+	const size_t np = (size_t)h->W * h->H;
+	if(color) CU(cudaMemcpyAsync(color, L.color, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+	if(nsamples) CU(cudaMemcpyAsync(nsamples, L.ns, np * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+	if(hist) CU(cudaMemcpyAsync(hist, L.hist, np * h->B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+	if(cov) CU(cudaMemcpyAsync(cov, L.cov, np * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+	CU(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+int bcd_b200_spike_removal_host(float* color, float* nsamples, float* hist, float* cov, int32_t width, int32_t height,
+		int32_t hist_depth, float threshold_std_factor, int int_abs, int device)
+{
+	bcd_b200_images in = {color, nsamples, hist, cov, width, height, hist_depth};
+	int rc = checkImages(&in);
+	if(rc) return rc;
+	bcd_b200_handle* h = nullptr;
+	rc = bcd_b200_create(&h, device);
+	if(rc) return rc;
+	rc = bcd_b200_upload(h, &in);
+	if(!rc) rc = bcd_b200_spike_removal(h, threshold_std_factor, int_abs);
+	if(!rc) rc = bcd_b200_download_inputs(h, color, nsamples, hist, cov);
+	bcd_b200_destroy(h);
+	return rc;
 }
 
 int bcd_b200_denoise(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, int device,

@@ -127,6 +127,104 @@ cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStrea
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+//  SpikeRemovalFilter::filter — src/core/SpikeRemovalFilter.cpp:18-75 with :77-92 (average and
+// standard deviation of the 3x3 neighbourhood, sequential sums) and :94-116 (L1 median of the 9 colours).
+// k_spike_source decides, per pixel, which pixel it is copied from (itself, or the median neighbour of its clamped
+// 3x3 window when it is an outlier); k_spike_gather then copies colour, nSamples, histogram and covariance.
+// intAbs = 1 reproduces the overload the reference's unqualified abs() resolves to under GCC/glibc (::abs(int), i.e.
+// the float is truncated first — what the compiled oracle does); 0 is the float overload (MSVC, the intent).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float absMode(float v, int intAbs)
+{
+	if(intAbs)
+	{
+		const int t = (int)v; // C conversion: truncation toward zero (cvt.rzi)
+		return (float)(t < 0 ? -t : t);
+	}
+	return fabsf(v);
+}
+
+__global__ void k_spike_source(const float* __restrict__ color, int W, int H, float factor, int intAbs, int* __restrict__ src)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y * blockDim.y + threadIdx.y;
+	if(x >= W || y >= H)
+		return;
+	const int cl = y < 1 ? 1 : (y > H - 2 ? H - 2 : y);
+	const int cc = x < 1 ? 1 : (x > W - 2 ? W - 2 : x);
+	float v[3][9];
+	for(int k = 0; k < 9; ++k)
+	{
+		const float* p = color + ((size_t)(cl - 1 + k / 3) * W + (cc - 1 + k % 3)) * 3;
+		v[0][k] = p[0]; v[1][k] = p[1]; v[2][k] = p[2];
+	}
+	const float* me = color + ((size_t)y * W + x) * 3;
+	bool spike = false;
+	for(int c = 0; c < 3; ++c)
+	{
+		float total = 0.f;
+		for(int k = 0; k < 9; ++k) total = total + v[c][k];
+		const float avg = total / 9;
+		total = 0.f;
+		for(int k = 0; k < 9; ++k) total = total + (v[c][k] - avg) * (v[c][k] - avg);
+		const float sd = sqrtf(total / 8);
+		spike = spike || absMode(me[c] - avg, intAbs) > factor * sd;
+	}
+	int source = y * W + x;
+	if(spike)
+	{
+		int median = 0;
+		float best = -1.f;
+		for(int cand = 0; cand < 9; ++cand)
+		{
+			float tot = 0.f;
+			for(int k = 0; k < 9; ++k)
+			{
+				if(intAbs)
+				{
+					const int a0 = (int)(v[0][k] - v[0][cand]), a1 = (int)(v[1][k] - v[1][cand]), a2 = (int)(v[2][k] - v[2][cand]);
+					tot = tot + (float)((a0 < 0 ? -a0 : a0) + (a1 < 0 ? -a1 : a1) + (a2 < 0 ? -a2 : a2));
+				}
+				else
+					tot = tot + (fabsf(v[0][k] - v[0][cand]) + fabsf(v[1][k] - v[1][cand]) + fabsf(v[2][k] - v[2][cand]));
+			}
+			if(best < 0 || tot < best)
+			{
+				best = tot;
+				median = cand;
+			}
+		}
+		source = (cl - 1 + median / 3) * W + (cc - 1 + median % 3);
+	}
+	src[(size_t)y * W + x] = source;
+}
+
+__global__ void k_spike_gather(const float* __restrict__ in, const int* __restrict__ src, size_t npix, int D, float* __restrict__ out)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= npix * D)
+		return;
+	const size_t p = i / D;
+	const int z = (int)(i - p * D);
+	out[i] = in[(size_t)src[p] * D + z];
+}
+
+cudaError_t launchSpikeFilter(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
+		float factor, int intAbs, int* src, float* colorOut, float* nsOut, float* histOut, float* covOut, cudaStream_t st, int* launches)
+{
+	dim3 block(32, 8), grid(divUp(W, 32), divUp(H, 8));
+	k_spike_source<<<grid, block, 0, st>>>(color, W, H, factor, intAbs, src);
+	const size_t npix = (size_t)W * H;
+	auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
+	k_spike_gather<<<blocks(npix * 3), 256, 0, st>>>(color, src, npix, 3, colorOut);
+	k_spike_gather<<<blocks(npix), 256, 0, st>>>(ns, src, npix, 1, nsOut);
+	k_spike_gather<<<blocks(npix * B), 256, 0, st>>>(hist, src, npix, B, histOut);
+	k_spike_gather<<<blocks(npix * 6), 256, 0, st>>>(cov, src, npix, 6, covOut);
+	*launches += 5;
+	return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // pyramid
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int n) { return v <= 0 ? 0 : (v >= n ? n - 1 : v); }

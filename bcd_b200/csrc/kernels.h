@@ -52,6 +52,9 @@ cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uin
 cudaError_t launchAddStrip(float4* acc, const float4* strip, size_t n, cudaStream_t st, int* launches);
 // K4 finalAggregation
 cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches);
+// (row f1) SpikeRemovalFilter: out-of-place; src = W*H ints of scratch
+cudaError_t launchSpikeFilter(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
+		float factor, int intAbs, int* src, float* colorOut, float* nsOut, float* histOut, float* covOut, cudaStream_t st, int* launches);
 // K5 pyramid down, K6 merge
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
 		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches);

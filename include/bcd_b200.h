@@ -120,6 +120,20 @@ int  bcd_b200_result_device_ptr(bcd_b200_handle* h, const float** out_dev);
 int  bcd_b200_get_stats(bcd_b200_handle* h, bcd_b200_stats* s);
 int  bcd_b200_get_timings(bcd_b200_handle* h, bcd_b200_timings* t);
 
+/* ----  spike-removal prefilter, the step immediately before the path in bcd_cli / the GUI -------------
+ * Replaces SpikeRemovalFilter::filter (reference src/core/SpikeRemovalFilter.cpp:18-75): a pixel whose colour is
+ * further than factor * stddev from the mean of its clamped 3x3 neighbourhood is replaced — colour, nSamples,
+ * histogram and covariance — by the L1-median neighbour. Runs on the handle's resident inputs (they must have been
+ * uploaded, not bound) and leaves the filtered images resident as the inputs of the next bcd_b200_run.
+ * int_abs: 1 = the overload the reference's unqualified abs() resolves to under GCC/glibc (::abs(int): what the
+ * compiled oracle does), 0 = the float overload (MSVC builds of the reference, and the evident intent). */
+int  bcd_b200_spike_removal(bcd_b200_handle* h, float threshold_std_factor, int int_abs);
+/* host-side convenience: filters the four host images in place (upload, filter, download) */
+int  bcd_b200_spike_removal_host(float* color, float* nsamples, float* hist, float* cov, int32_t width, int32_t height,
+                                 int32_t hist_depth, float threshold_std_factor, int int_abs, int device);
+/* device -> host copy of the resident level-0 inputs (e.g. after bcd_b200_spike_removal) */
+int  bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples, float* hist, float* cov);
+
 /* ---- row-tile API (multi-GPU: one handle per GPU, one process per GPU) ---------------------------------------------
  * The frame is cut into horizontal bands. Tile t of n produces the output rows [own_row0, own_row1) and keeps the
  * input rows [sub_row0, sub_row1) resident (its band plus (b+w)*2^(s-1) halo rows, so that every pyramid level has

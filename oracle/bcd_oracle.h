@@ -48,7 +48,8 @@ int  bcdo_denoise_multiscale(const float* color, const float* ns, const float* h
 		int W, int H, int B, const bcdo_params* p, int nscales, float* out);
 
 /* row f1: SpikeRemovalFilter (in place); src_index optional */
-void bcdo_spike_removal(float* color, float* ns, float* hist, float* cov, int W, int H, int B, float factor, int* src_index);
+void bcdo_spike_removal(float* color, float* ns, float* hist, float* cov, int W, int H, int B, float factor, int int_abs,
+		int* src_index);
 
 #ifdef __cplusplus
 }

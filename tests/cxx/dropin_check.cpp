@@ -8,6 +8,7 @@
 #include "DeepImage.h"
 #include "SamplesAccumulator.h"
 #include "CovarianceMatrix.h"
+#include "SpikeRemovalFilter.h"
 
 #include <cmath>
 #include <cstdio>
@@ -82,6 +83,16 @@ int main(int argc, char** argv)
 		bad.m_pHistograms = &empty;
 		d.setInputs(bad);
 		CHECK(!d.denoise());
+	}
+	// --- row f1: the prefilter bcd_cli runs before denoising (src/cli/main.cpp:428-434), in place on the four images
+	if(gpu)
+	{
+		SamplesStatisticsImages spiky(stats);
+		spiky.m_meanImage.set(10, 10, 0, 40.f); // a firefly
+		const float before = spiky.m_meanImage.get(10, 10, 0);
+		SpikeRemovalFilter::filter(spiky.m_meanImage, spiky.m_nbOfSamplesImage, spiky.m_histoImage, spiky.m_covarImage, 2.f);
+		CHECK(before == 40.f && spiky.m_meanImage.get(10, 10, 0) < 2.f);
+		CHECK(spiky.m_meanImage.get(20, 5, 1) == stats.m_meanImage.get(20, 5, 1));
 	}
 	// --- the real thing through the abstract interface
 	DenoiserParameters params;

@@ -55,6 +55,16 @@ def main():
     out = dict(c)
     out["ref_s1_m0_w2b3"] = O.ref_denoise(**c, cores=8, m=0.0, scales=1, w=2, b=5)
     np.savez_compressed(os.path.join(HERE, "testraw_crop_c.npz"), **out)
+    # D (row f1): SpikeRemovalFilter of the compiled reference on the seeded synthetic frame G(96,64,spp=32) — the input is
+    # regenerated at test time by bcd_b200.host.synth (deterministic); only the reference's outputs are stored
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from bcd_b200 import host
+    g = host.synth(96, 64, spp=32)
+    r = O.ref_spike_removal(**g, factor=2.0)
+    changed = (r["color"] != g["color"]).any(-1)
+    np.savez_compressed(os.path.join(HERE, "spike_synth_96x64.npz"), color=r["color"], nsamples=r["nsamples"], cov=r["cov"],
+                        hist_channel_sums=r["hist"].astype(np.float64).sum(axis=(0, 1)), changed=changed,
+                        ref_denoised_after_spike=O.ref_denoise(**r, cores=1, m=1.0, scales=2))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -197,11 +197,11 @@ def ref_spike_removal(color, nsamples, hist, cov, factor=2.0):
     return dict(color=c, nsamples=n, hist=h, cov=v)
 
 
-def port_spike_removal(color, nsamples, hist, cov, factor=2.0):
+def port_spike_removal(color, nsamples, hist, cov, factor=2.0, int_abs=True):
     H, W, _ = color.shape
     c, n, h, v = [np.ascontiguousarray(a, np.float32).copy() for a in (color, nsamples, hist, cov)]
     src = np.zeros((H, W), np.int32)
     L = port_lib()
-    L.bcdo_spike_removal.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _i32p]
-    L.bcdo_spike_removal(c, n, h, v, W, H, h.shape[2], factor, src)
+    L.bcdo_spike_removal.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _i32p]
+    L.bcdo_spike_removal(c, n, h, v, W, H, h.shape[2], factor, int(int_abs), src)
     return dict(color=c, nsamples=n, hist=h, cov=v), src

@@ -165,3 +165,33 @@ def test_fractional_skip_probability_is_deterministic(capi, crop_b):
     sm0 = h.stats()
     h.close()
     assert sm1["active"] <= s1["active"] <= sm0["active"]
+
+
+def test_spike_removal_prefilter_bit_exact(capi):
+    """Row f1 on the GPU: bit-exact against the stored reference output (GCC-build semantics) and against the
+    restatement in float-abs mode; the filtered inputs stay resident and feed the denoiser."""
+    import os
+    from conftest import GOLDEN
+    from bcd_b200 import host
+    gold = dict(np.load(os.path.join(GOLDEN, "spike_synth_96x64.npz")))
+    g = host.synth(96, 64, spp=32)
+    h = capi.Handle(0)
+    h.upload(**g)
+    h.spike_removal(2.0, int_abs=True)
+    f = h.download_inputs()
+    assert np.array_equal(f["color"].view(np.uint32), gold["color"].view(np.uint32))
+    assert np.array_equal(f["cov"].view(np.uint32), gold["cov"].view(np.uint32))
+    assert np.array_equal(f["nsamples"], gold["nsamples"])
+    port, _ = O.port_spike_removal(**g, factor=2.0, int_abs=True)
+    assert np.array_equal(f["hist"].view(np.uint32), port["hist"].view(np.uint32))
+    h.run(m=1.0, scales=2)
+    out = h.download()
+    assert O.rel_linf(out, gold["ref_denoised_after_spike"]) <= TOL
+    # float-abs mode, starting again from the raw inputs
+    h.upload(**g)
+    h.spike_removal(2.0, int_abs=False)
+    ff = h.download_inputs()
+    h.close()
+    portf, _ = O.port_spike_removal(**g, factor=2.0, int_abs=False)
+    for k in ff:
+        assert np.array_equal(ff[k].view(np.uint32), portf[k].view(np.uint32)), k

@@ -79,3 +79,26 @@ def test_degenerate_inputs_produce_nan_like_the_reference():
     assert np.isnan(out).all()
     if O.have_ref():
         assert np.isnan(O.ref_denoise(**z, cores=1, m=0.0)).all()
+
+
+def test_spike_removal_restatement_matches_reference_golden():
+    """Row f1: the reference's unqualified abs() binds to ::abs(int) under GCC/glibc (the compiled oracle); the
+    restatement's int_abs mode must reproduce the stored reference output bit for bit."""
+    import os
+    from conftest import GOLDEN
+    from bcd_b200 import host
+    gold = dict(np.load(os.path.join(GOLDEN, "spike_synth_96x64.npz")))
+    g = host.synth(96, 64, spp=32)
+    p, src = O.port_spike_removal(**g, factor=2.0, int_abs=True)
+    assert np.array_equal(p["color"].view(np.uint32), gold["color"].view(np.uint32))
+    assert np.array_equal(p["cov"].view(np.uint32), gold["cov"].view(np.uint32))
+    assert np.array_equal(p["nsamples"], gold["nsamples"])
+    assert np.allclose(p["hist"].astype(np.float64).sum(axis=(0, 1)), gold["hist_channel_sums"], rtol=0, atol=0)
+    assert gold["changed"].sum() > 0 and np.array_equal(src != np.arange(96 * 64).reshape(64, 96), gold["changed"])
+    # the float-abs reading replaces many more pixels (MSVC builds of the reference behave like this)
+    pf, srcf = O.port_spike_removal(**g, factor=2.0, int_abs=False)
+    assert (srcf != np.arange(96 * 64).reshape(64, 96)).sum() > gold["changed"].sum()
+    if O.have_ref():
+        r = O.ref_spike_removal(**g, factor=2.0)
+        for k in r:
+            assert np.array_equal(r[k].view(np.uint32), p[k].view(np.uint32)), k
