@@ -7,7 +7,7 @@ CXX = g++
 ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -O3 -lineinfo --fmad=false -std=c++17 -ccbin $(CXX) -Xcompiler -fPIC -Xptxas -v
 CSRC = bcd_b200/csrc
-KOBJ = $(CSRC)/k_distance.o $(CSRC)/k_misc.o $(CSRC)/k_marking.o $(CSRC)/k_filter.o $(CSRC)/bcd_b200_capi.o
+KOBJ = $(CSRC)/k_distance.o $(CSRC)/k_misc.o $(CSRC)/k_marking.o $(CSRC)/k_filter.o $(CSRC)/k_eig_sub.o $(CSRC)/bcd_b200_capi.o
 HOSTSRC = $(wildcard bcd_b200/host/*.cpp)
 
 all: bcd_b200/libbcd_b200.so bcd_b200/libbcdcore_b200.so oracle

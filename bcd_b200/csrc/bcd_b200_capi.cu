@@ -524,6 +524,9 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		g_forceDensePair = e && e[0] == '1';
 		e = getenv("BCD_B200_GENERIC_MARKING");
 		g_forceGenericMarking = e && e[0] == '1';
+		e = getenv("BCD_B200_EIG_GROUP");
+		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
+			g_eigGroup = atoi(e);
 	}
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));

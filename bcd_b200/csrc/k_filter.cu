@@ -908,6 +908,8 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 
 	auto launchEig = [&](int doClamp) -> cudaError_t {
 		const int eg = count;
+		if(eigNT == 32 && g.d <= 32 && (g_eigGroup == 16 || g_eigGroup == 8))
+			return launchEigChainSub(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp, g_eigGroup, st);
 		if(eigNT == 32)
 		{
 			cudaFuncSetAttribute(k_eig_chain<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);

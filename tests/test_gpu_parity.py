@@ -136,6 +136,23 @@ def test_dense_pair_kernel_path(capi, crop_a, monkeypatch):
     assert int(np.unpackbits((masks ^ crop_a["port_masks"]).view(np.uint8)).sum()) == 0
 
 
+@pytest.mark.parametrize("group", [8, 16, 32])
+def test_eig_chain_layouts_agree_with_reference(capi, crop_a, crop_b, group, monkeypatch):
+    """K3e: 4 / 2 / 1 matrices per warp (k_eig_sub.cu, k_filter.cu) — each within tolerance of the reference golden,
+    also on the odd-sized crop whose full list is not a multiple of the matrices per warp."""
+    monkeypatch.setenv("BCD_B200_EIG_GROUP", str(group))
+    try:
+        h, out = _run(capi, inputs_of(crop_a), m=1.0, scales=1)
+        h.close()
+        assert O.rel_linf(out, crop_a["ref_s1_m1"]) <= TOL
+        h, out = _run(capi, inputs_of(crop_b), m=0.0, scales=2)
+        h.close()
+        assert O.rel_linf(out, crop_b["ref_s2_m0"]) <= TOL
+    finally:
+        monkeypatch.setenv("BCD_B200_EIG_GROUP", "16")
+        capi.Handle(0).close()  # reset the process-wide hook to the default
+
+
 @pytest.mark.parametrize("b", [10, 3])
 def test_other_search_radii_bit_exact(capi, crop_b, b):
     inp = inputs_of(crop_b)
