@@ -19,6 +19,7 @@ STAGE_NAMES = ["prepass", "pair", "select", "marking", "fallback", "filter_stats
 SYMBOLS = [
     "bcd_b200_default_params", "bcd_b200_last_error", "bcd_b200_abi_version", "bcd_b200_device_count",
     "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_set_streams", "bcd_b200_upload",
+    "bcd_b200_upload_async",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
     "bcd_b200_spike_removal", "bcd_b200_spike_removal_host", "bcd_b200_download_inputs",
@@ -77,6 +78,7 @@ def lib():
         L.bcd_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.bcd_b200_set_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_upload.argtypes = [C.c_void_p, C.POINTER(Images)]
+        L.bcd_b200_upload_async.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_bind_device.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
         L.bcd_b200_download.argtypes = [C.c_void_p, C.c_void_p]
@@ -157,11 +159,18 @@ class Handle:
         _check(lib().bcd_b200_upload(self._h, C.byref(img)))
         self.shape = (img.height, img.width, img.hist_depth)
 
-    def upload_ptrs(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B):
-        """Host pointers (e.g. pinned torch tensors' data_ptr())."""
+    def upload_ptrs(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B, streamed=False):
+        """Host pointers (e.g. pinned torch tensors' data_ptr()). streamed=True: bcd_b200_upload_async — the copies
+        overlap the next run(); the caller keeps the host buffers alive and unmodified until that run returned."""
         img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B)
-        _check(lib().bcd_b200_upload(self._h, C.byref(img)))
+        _check((lib().bcd_b200_upload_async if streamed else lib().bcd_b200_upload)(self._h, C.byref(img)))
         self.shape = (H, W, B)
+
+    def upload_async(self, color, nsamples, hist, cov):
+        img, keep = _host_images(color, nsamples, hist, cov)
+        self._pending_host = keep  # the arrays must outlive the streamed copy
+        _check(lib().bcd_b200_upload_async(self._h, C.byref(img)))
+        self.shape = (img.height, img.width, img.hist_depth)
 
     def bind_device(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B):
         """Borrow DEVICE pointers (e.g. torch CUDA tensors' data_ptr()) as the level-0 inputs."""

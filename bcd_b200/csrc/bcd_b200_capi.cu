@@ -96,6 +96,19 @@ struct bcd_b200_handle
 	// marking (K2) runs on a second, high-priority stream so that the latency-bound raster-order chain of level k
 	// overlaps the selection of level k-1 and the filters of the coarser levels on the main stream
 	cudaStream_t ownAux = nullptr, aux = nullptr;
+	std::vector<cudaStream_t> ownAuxLevel; // levels >= 1 get their own marking stream (the chains of different levels are independent)
+	// streamed upload (bcd_b200_upload_async): the histogram arrives in row bands on a copy stream, one event per band;
+	// the level-0 pair-term kernel (K1a) is launched band by band behind those events, so the PCIe transfer of the
+	// (dominant) histogram overlaps the dominant kernel
+	struct Upload
+	{
+		cudaStream_t copy = nullptr;
+		bool pending = false;
+		int bands = 0;
+		int rowEnd[16];
+		cudaEvent_t ev[16] = {};
+		cudaEvent_t evAll = nullptr, evOrder = nullptr;
+	} up;
 	int filterChunk = 0;
 	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
 	bool ran = false;
@@ -179,8 +192,10 @@ void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1)
 	own1 = h->ownRow1 >= h->imageH ? L.H : (h->ownRow1 - h->subRow0) >> k;
 }
 
-// stage 1 (main stream): prepass + distance/selection (K0, K1a-c); clears the accumulators and bit-rows of the level
-int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+// stage 1 (main stream): prepass + distance/selection (K0, K1a-c); clears the accumulators and bit-rows of the level.
+// Split in four pieces because the level-0 pieces that only need histogram + sample counts (clear, pair, patch select)
+// run under a streamed upload, before the other inputs have arrived.
+int levelClear(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
@@ -190,15 +205,67 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	const size_t npix = (size_t)g.W * g.H;
 	const int Wp = markingRowWords(g.W);
 	STAGE(h, BCD_B200_STAGE_PREPASS, {
-		CU(launchPixelCov(L.cov, L.ns, npix, L.pixcov.as<float>(), st, &h->launches));
 		CU(cudaMemsetAsync(L.acc.p, 0, npix * sizeof(float4), st));
 		CU(cudaMemsetAsync(L.active.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
 		CU(cudaMemsetAsync(L.asBits.p, 0, (size_t)g.H * Wp * sizeof(uint32_t), st));
 		CU(cudaMemsetAsync(L.ctr.p, 0, sizeof(DeviceCounters), st));
 	});
+	return 0;
+}
+
+int levelPixelCov(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	STAGE(h, BCD_B200_STAGE_PREPASS, {
+		CU(launchPixelCov(L.cov, L.ns, (size_t)g.W * g.H, L.pixcov.as<float>(), h->stream, &h->launches));
+	});
+	return 0;
+}
+
+// K1a. With a streamed upload pending (level 0 of a whole-frame run) the kernel is launched once per upload band:
+// band [r0, r1) reads histogram rows < min(H, r1 + b) (band heights are multiples of the tile height).
+int levelPair(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	cudaStream_t st = h->stream;
+	if(h->up.pending && (k != 0 || h->tiled || h->up.bands <= 1))
+	{
+		int rcu = finishUpload(h);
+		if(rcu) return rcu;
+	}
+	if(k == 0 && h->up.pending)
+	{
+		STAGE(h, BCD_B200_STAGE_PAIR, {
+			int r0 = 0;
+			for(int i = 0; i < h->up.bands; ++i)
+			{
+				const int r1 = h->up.rowEnd[i];
+				const int need = std::min(g.H, r1 + g.b);
+				int j = i;
+				while(h->up.rowEnd[j] < need) ++j;
+				CU(cudaStreamWaitEvent(st, h->up.ev[j], 0));
+				LevelGeom gb = g;
+				gb.yLo = r0;
+				gb.yHi = r1;
+				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+				r0 = r1;
+			}
+		});
+		return 0;
+	}
 	STAGE(h, BCD_B200_STAGE_PAIR, {
 		CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
 	});
+	return 0;
+}
+
+int levelPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	cudaStream_t st = h->stream;
 	STAGE(h, BCD_B200_STAGE_SELECT, {
 		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
 		const bool fastLayout = markingUsesFastLayout(g.b);
@@ -211,12 +278,41 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
+// a pending streamed upload becomes an ordinary dependency of the main stream
+int finishUpload(bcd_b200_handle* h)
+{
+	if(h->up.pending)
+	{
+		CU(cudaStreamWaitEvent(h->stream, h->up.evAll, 0));
+		h->up.pending = false;
+	}
+	return 0;
+}
+
+int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	int rc = finishUpload(h);
+	if(!rc) rc = levelClear(h, k, p);
+	if(!rc) rc = levelPixelCov(h, k, p);
+	if(!rc) rc = levelPair(h, k, p);
+	if(!rc) rc = levelPatchSelect(h, k, p);
+	return rc;
+}
+
+// marking stream of level k: the caller's aux stream when one was set, else one high-priority stream per level
+cudaStream_t auxOf(bcd_b200_handle* h, int k)
+{
+	if(h->aux != h->ownAux || k == 0 || k > (int)h->ownAuxLevel.size())
+		return h->aux;
+	return h->ownAuxLevel[k - 1];
+}
+
 // stage 2a (aux stream): marking strategy (K2) over the owned rows + work lists; asynchronous
 int levelMarkEnqueue(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
-	cudaStream_t st = h->aux;
+	cudaStream_t st = auxOf(h, k);
 	const int Wp = markingRowWords(g.W);
 	CU(cudaStreamWaitEvent(st, L.evSel, 0));
 	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
@@ -414,6 +510,14 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	const size_t xBytes = (size_t)g.Ns * g.d * 4;
 	if(xBytes + (size_t)g.d * g.d * 4 + 8 * 1024 > 190 * 1024)
 		CU(h->fX.reserve(xBytes * 148 * 2));
+	while((int)h->ownAuxLevel.size() < nl - 1)
+	{
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);
+		cudaStream_t a = nullptr;
+		CU(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, hi));
+		h->ownAuxLevel.push_back(a);
+	}
 	for(int i = 0; i < 6; ++i)
 		if(!h->fev[i]) CU(cudaEventCreate(&h->fev[i]));
 	for(int i = 0; i < 2; ++i)
@@ -557,8 +661,14 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 {
 	if(!h) return;
 	cudaSetDevice(h->device);
+	if(h->up.copy) cudaStreamSynchronize(h->up.copy);
 	cudaStreamSynchronize(h->stream);
 	cudaStreamSynchronize(h->aux);
+	for(cudaStream_t a : h->ownAuxLevel) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+	for(int i = 0; i < 16; ++i) if(h->up.ev[i]) cudaEventDestroy(h->up.ev[i]);
+	if(h->up.evAll) cudaEventDestroy(h->up.evAll);
+	if(h->up.evOrder) cudaEventDestroy(h->up.evOrder);
+	if(h->up.copy) cudaStreamDestroy(h->up.copy);
 	for(auto& L : h->levels)
 	{
 		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.altColor, &L.altNs, &L.altHist, &L.altCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
@@ -593,7 +703,7 @@ int bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream
 	return 0;
 }
 
-int bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in)
+int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
 	int rc = checkImages(in);
@@ -601,16 +711,43 @@ int bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in)
 	CU(cudaSetDevice(h->device));
 	if(h->levels.empty()) h->levels.resize(1);
 	LevelBufs& L = h->levels[0];
+	bcd_b200_handle::Upload& up = h->up;
+	if(!up.copy)
+	{
+		CU(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&up.evAll, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&up.evOrder, cudaEventDisableTiming));
+		for(int i = 0; i < 16; ++i)
+			CU(cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming));
+	}
 	const size_t np = (size_t)in->width * in->height;
 	CU(L.ownColor.reserve(np * 3 * sizeof(float)));
 	CU(L.ownNs.reserve(np * sizeof(float)));
 	CU(L.ownHist.reserve(np * in->hist_depth * sizeof(float)));
 	CU(L.ownCov.reserve(np * 6 * sizeof(float)));
-	CU(cudaMemcpyAsync(L.ownColor.p, in->color, np * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-	CU(cudaMemcpyAsync(L.ownNs.p, in->nsamples, np * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-	CU(cudaMemcpyAsync(L.ownHist.p, in->hist, np * in->hist_depth * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-	CU(cudaMemcpyAsync(L.ownCov.p, in->cov, np * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-	CU(cudaStreamSynchronize(h->stream));
+	// the copies may not overtake work of the main stream that still reads the resident inputs
+	CU(cudaEventRecord(up.evOrder, h->stream));
+	CU(cudaStreamWaitEvent(up.copy, up.evOrder, 0));
+	// order: what the first kernels need first — sample counts, then the histogram in row bands, then covariance + colour
+	const int H = in->height;
+	up.bands = H >= 64 ? 8 : 1;
+	const int bandRows = (divUp(H, up.bands) + 7) / 8 * 8;
+	up.bands = divUp(H, bandRows);
+	CU(cudaMemcpyAsync(L.ownNs.p, in->nsamples, np * sizeof(float), cudaMemcpyHostToDevice, up.copy));
+	const size_t rowFloats = (size_t)in->width * in->hist_depth;
+	for(int i = 0, r0 = 0; i < up.bands; ++i)
+	{
+		const int r1 = std::min(H, r0 + bandRows);
+		CU(cudaMemcpyAsync(L.ownHist.as<float>() + (size_t)r0 * rowFloats, in->hist + (size_t)r0 * rowFloats,
+				(size_t)(r1 - r0) * rowFloats * sizeof(float), cudaMemcpyHostToDevice, up.copy));
+		CU(cudaEventRecord(up.ev[i], up.copy));
+		up.rowEnd[i] = r1;
+		r0 = r1;
+	}
+	CU(cudaMemcpyAsync(L.ownCov.p, in->cov, np * 6 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
+	CU(cudaMemcpyAsync(L.ownColor.p, in->color, np * 3 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
+	CU(cudaEventRecord(up.evAll, up.copy));
+	up.pending = true;
 	L.color = L.ownColor.as<float>();
 	L.ns = L.ownNs.as<float>();
 	L.hist = L.ownHist.as<float>();
@@ -621,12 +758,26 @@ int bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in)
 	return 0;
 }
 
+int bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in)
+{
+	int rc = bcd_b200_upload_async(h, in);
+	if(rc) return rc;
+	CU(cudaEventSynchronize(h->up.evAll));
+	h->up.pending = false;
+	return 0;
+}
+
 int bcd_b200_bind_device(bcd_b200_handle* h, const bcd_b200_images* in)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
 	int rc = checkImages(in);
 	if(rc) return rc;
 	if(h->levels.empty()) h->levels.resize(1);
+	if(h->up.pending)
+	{
+		CU(cudaEventSynchronize(h->up.evAll));
+		h->up.pending = false;
+	}
 	LevelBufs& L = h->levels[0];
 	L.color = in->color; L.ns = in->nsamples; L.hist = in->hist; L.cov = in->cov;
 	h->W = in->width; h->H = in->height; h->B = in->hist_depth;
@@ -652,20 +803,27 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	const int s = p->nb_scales;
 	CU(cudaEventRecord(h->evTotal[0], st));
 	if(progress) progress(0.f, user);
-	// pyramid build (MultiscaleDenoiser.cpp:41-48)
 	h->tiled = false;
 	h->runParams = *p;
+	// Level 0 selection first: its clear / pair-term / patch-select kernels need only the histogram and the sample
+	// counts, so under a streamed upload they start as soon as the first bands have landed. Then the rest of the
+	// inputs is awaited, the pyramid is built (MultiscaleDenoiser.cpp:41-48) and the coarser levels are selected.
+	if((rc = levelClear(h, 0, *p))) return rc;
+	if((rc = levelPair(h, 0, *p))) return rc;
+	if((rc = levelPatchSelect(h, 0, *p))) return rc;
+	if((rc = finishUpload(h))) return rc;
+	if((rc = levelPixelCov(h, 0, *p))) return rc;
 	rc = buildPyramid(h, s);
 	if(rc) return rc;
-	// Coarsest to finest (MultiscaleDenoiser.cpp:79-134). The selection of every level is enqueued first on the main
-	// stream; the marking chain of level k runs on the aux stream as soon as its selection is done, i.e. under the
-	// selection of level k-1 and under the filters of the coarser levels; filters and merges follow on the main stream.
-	for(int k = s - 1; k >= 0; --k)
+	for(int k = s - 1; k >= 1; --k)
 	{
 		rc = levelSelect(h, k, *p);
 		if(rc) return rc;
 	}
-	for(int k = s - 1; k >= 0; --k)
+	// The marking chains run on their own high-priority streams (level 0 — the longest — first, under the selection of
+	// the coarser levels); filters and merges follow on the main stream coarsest to finest (MultiscaleDenoiser.cpp:79-134).
+	if((rc = levelMarkEnqueue(h, 0, *p))) return rc;
+	for(int k = s - 1; k >= 1; --k)
 	{
 		rc = levelMarkEnqueue(h, k, *p);
 		if(rc) return rc;
@@ -809,6 +967,7 @@ int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	h->runParams = *p;
 	h->ran = false;
 	CU(cudaEventRecord(h->evTotal[0], h->stream));
+	if((rc = finishUpload(h))) return rc;
 	return buildPyramid(h, p->nb_scales);
 }
 
@@ -885,7 +1044,7 @@ int bcd_b200_tile_export(bcd_b200_handle* h, int level, int what, int side, void
 	const int row = s.exportRow[side];
 	if(row < 0 || row + s.rows > h->levels[level].H)
 		return fail(BCD_B200_ERR_STATE, "export strip rows [%d,%d) outside the resident band (no neighbour on that side?)", row, row + s.rows);
-	cudaStream_t xs = what == BCD_B200_XFER_AS_ROWS ? h->aux : h->stream; // the marking chain lives on the aux stream
+	cudaStream_t xs = what == BCD_B200_XFER_AS_ROWS ? auxOf(h, level) : h->stream; // the marking chain lives on the aux stream
 	CU(cudaMemcpyAsync(dev_buf, s.base + (size_t)row * s.rowBytes, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, xs));
 	return 0;
 }
@@ -907,8 +1066,8 @@ int bcd_b200_tile_import(bcd_b200_handle* h, int level, int what, int side, cons
 	else if(what == BCD_B200_XFER_AS_ROWS)
 	{
 		// the bit-rows are cleared by the selection stage on the main stream: order the copy after it
-		CU(cudaStreamWaitEvent(h->aux, h->levels[level].evSel, 0));
-		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->aux));
+		CU(cudaStreamWaitEvent(auxOf(h, level), h->levels[level].evSel, 0));
+		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, auxOf(h, level)));
 	}
 	else
 		CU(cudaMemcpyAsync(dst, dev_buf, s.rowBytes * s.rows, cudaMemcpyDeviceToDevice, h->stream));
@@ -950,6 +1109,7 @@ int bcd_b200_spike_removal(bcd_b200_handle* h, float threshold_std_factor, int i
 	if(h->W < 3 || h->H < 3)
 		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "spike removal needs at least a 3x3 image");
 	CU(cudaSetDevice(h->device));
+	{ int rcu = finishUpload(h); if(rcu) return rcu; }
 	const size_t np = (size_t)h->W * h->H;
 	const bool fromOwn = L.color == L.ownColor.as<float>();
 	DevBuf& oc = fromOwn ? L.altColor : L.ownColor;
@@ -974,6 +1134,7 @@ int bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples, 
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
 	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "no resident inputs");
 	CU(cudaSetDevice(h->device));
+	{ int rcu = finishUpload(h); if(rcu) return rcu; }
 	const LevelBufs& L = h->levels[0];
 	const size_t np = (size_t)h->W * h->H;
 	if(color) CU(cudaMemcpyAsync(color, L.color, np * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1012,7 +1173,7 @@ int bcd_b200_denoise(const bcd_b200_images* in, const bcd_b200_params* p, float*
 	bcd_b200_handle* h = nullptr;
 	rc = bcd_b200_create(&h, device);
 	if(rc) return rc;
-	rc = bcd_b200_upload(h, in);
+	rc = bcd_b200_upload_async(h, in); // the host buffers outlive the call, so the transfer can stream under the run
 	if(!rc) rc = bcd_b200_run(h, p, progress, user);
 	if(!rc) rc = bcd_b200_download(h, out_rgb);
 	bcd_b200_destroy(h);

@@ -105,10 +105,17 @@ void bcd_b200_destroy(bcd_b200_handle* h);
 /* optional: run on a caller-owned stream (cudaStream_t passed as void*); NULL restores the handle's own stream */
 int  bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream);
 /* main + auxiliary stream: the marking stage (and its AS_ROWS strips in row-tile mode) runs on the auxiliary stream so
- * that it overlaps the selection of the next finer level; NULL keeps the handle's own (high-priority) stream */
+ * that it overlaps the selection / filters on the main stream; NULL keeps the handle's own high-priority streams (one
+ * per pyramid level) */
 int  bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream);
 /* host -> device copy of the four input images (pinned or pageable host memory) */
 int  bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in);
+/* streamed variant: returns as soon as the copies are enqueued (sample counts, then the histogram in row bands, then
+ * covariance and colour) on the handle's copy stream. The next bcd_b200_run launches the level-0 pair-term kernel band by
+ * band behind the arriving histogram rows, so the transfer overlaps the dominant kernel. The host buffers must stay
+ * valid and unmodified until that run (or any other call that consumes the inputs) has returned; use pinned memory for a
+ * truly asynchronous copy. bcd_b200_denoise uses this path. */
+int  bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in);
 /* same, but the pointers in `in` are DEVICE pointers that the handle borrows until the next upload/bind/destroy */
 int  bcd_b200_bind_device(bcd_b200_handle* h, const bcd_b200_images* in);
 /* whole hot path on the resident inputs; synchronous with respect to the host on return */
