@@ -223,6 +223,17 @@ int levelPixelCov(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
+// a pending streamed upload becomes an ordinary dependency of the main stream
+int finishUpload(bcd_b200_handle* h)
+{
+	if(h->up.pending)
+	{
+		CU(cudaStreamWaitEvent(h->stream, h->up.evAll, 0));
+		h->up.pending = false;
+	}
+	return 0;
+}
+
 // K1a. With a streamed upload pending (level 0 of a whole-frame run) the kernel is launched once per upload band:
 // band [r0, r1) reads histogram rows < min(H, r1 + b) (band heights are multiples of the tile height).
 int levelPair(bcd_b200_handle* h, int k, const bcd_b200_params& p)
@@ -275,17 +286,6 @@ int levelPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches));
 	});
 	CU(cudaEventRecord(L.evSel, st));
-	return 0;
-}
-
-// a pending streamed upload becomes an ordinary dependency of the main stream
-int finishUpload(bcd_b200_handle* h)
-{
-	if(h->up.pending)
-	{
-		CU(cudaStreamWaitEvent(h->stream, h->up.evAll, 0));
-		h->up.pending = false;
-	}
 	return 0;
 }
 
