@@ -234,57 +234,74 @@ int finishUpload(bcd_b200_handle* h)
 	return 0;
 }
 
-// K1a. With a streamed upload pending (level 0 of a whole-frame run) the kernel is launched once per upload band:
-// band [r0, r1) reads histogram rows < min(H, r1 + b) (band heights are multiples of the tile height).
-int levelPair(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+// K1b + K1c on the rows [r0, r1) of the level (the whole selection region when r0 < 0)
+int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1)
 {
 	LevelBufs& L = h->levels[k];
-	const LevelGeom g = levelGeom(h, k, p);
+	LevelGeom g = levelGeom(h, k, p);
 	cudaStream_t st = h->stream;
-	if(h->up.pending && (k != 0 || h->tiled || h->up.bands <= 1))
-	{
-		int rcu = finishUpload(h);
-		if(rcu) return rcu;
-	}
-	if(k == 0 && h->up.pending)
-	{
-		STAGE(h, BCD_B200_STAGE_PAIR, {
-			int r0 = 0;
-			for(int i = 0; i < h->up.bands; ++i)
-			{
-				const int r1 = h->up.rowEnd[i];
-				const int need = std::min(g.H, r1 + g.b);
-				int j = i;
-				while(h->up.rowEnd[j] < need) ++j;
-				CU(cudaStreamWaitEvent(st, h->up.ev[j], 0));
-				LevelGeom gb = g;
-				gb.yLo = r0;
-				gb.yHi = r1;
-				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
-				r0 = r1;
-			}
-		});
-		return 0;
-	}
-	STAGE(h, BCD_B200_STAGE_PAIR, {
-		CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+	const bool fastLayout = markingUsesFastLayout(g.b);
+	LevelGeom gb = g;
+	if(r0 >= 0) { gb.yLo = r0; gb.yHi = r1; }
+	STAGE(h, BCD_B200_STAGE_SELECT, {
+		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), gb, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
+		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, L.smask.as<uint32_t>(), L.counts.as<int>(),
+				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches, gb.yLo, gb.yHi));
 	});
 	return 0;
 }
 
-int levelPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	const int preWords = markingUsesFastLayout(g.b) ? fastMarkWords(g.b) : g.Pw;
+	CU(cudaMemsetAsync(L.pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, h->stream));
+	return 0;
+}
+
+// K1a (+ K1b/K1c). With a streamed upload pending (level 0 of a whole-frame run) the kernels are launched once per
+// upload band: the pair terms of band [r0, r1) read histogram rows < min(H, r1 + b) (band heights are multiples of the
+// tile height), and the patch selection of a band follows as soon as the pair terms of the next band (its w halo rows)
+// are there — so only the last band's kernels run after the transfer.
+int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
 	cudaStream_t st = h->stream;
-	STAGE(h, BCD_B200_STAGE_SELECT, {
-		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), g, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
-		const bool fastLayout = markingUsesFastLayout(g.b);
-		const int preWords = fastLayout ? fastMarkWords(g.b) : g.Pw;
-		CU(cudaMemsetAsync(L.pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, st));
-		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, L.smask.as<uint32_t>(), L.counts.as<int>(),
-				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches));
-	});
+	int rc;
+	if(h->up.pending && (k != 0 || h->tiled || h->up.bands <= 1 || h->up.rowEnd[0] <= g.w + g.b))
+		if((rc = finishUpload(h))) return rc;
+	if((rc = clearPre(h, k, p))) return rc;
+	if(k == 0 && h->up.pending)
+	{
+		int r0 = 0;
+		for(int i = 0; i < h->up.bands; ++i)
+		{
+			const int r1 = h->up.rowEnd[i];
+			const int need = std::min(g.H, r1 + g.b);
+			int j = i;
+			while(h->up.rowEnd[j] < need) ++j;
+			CU(cudaStreamWaitEvent(st, h->up.ev[j], 0));
+			LevelGeom gb = g;
+			gb.yLo = r0;
+			gb.yHi = r1;
+			STAGE(h, BCD_B200_STAGE_PAIR, {
+				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+			});
+			if(i > 0 && (rc = patchSelectRows(h, k, p, i > 1 ? h->up.rowEnd[i - 2] : 0, h->up.rowEnd[i - 1]))) return rc;
+			r0 = r1;
+		}
+		const int nb = h->up.bands;
+		if((rc = patchSelectRows(h, k, p, nb > 1 ? h->up.rowEnd[nb - 2] : 0, h->up.rowEnd[nb - 1]))) return rc;
+	}
+	else
+	{
+		STAGE(h, BCD_B200_STAGE_PAIR, {
+			CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+		});
+		if((rc = patchSelectRows(h, k, p, -1, -1))) return rc;
+	}
 	CU(cudaEventRecord(L.evSel, st));
 	return 0;
 }
@@ -294,8 +311,7 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	int rc = finishUpload(h);
 	if(!rc) rc = levelClear(h, k, p);
 	if(!rc) rc = levelPixelCov(h, k, p);
-	if(!rc) rc = levelPair(h, k, p);
-	if(!rc) rc = levelPatchSelect(h, k, p);
+	if(!rc) rc = levelPairAndPatchSelect(h, k, p);
 	return rc;
 }
 
@@ -809,8 +825,7 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	// counts, so under a streamed upload they start as soon as the first bands have landed. Then the rest of the
 	// inputs is awaited, the pyramid is built (MultiscaleDenoiser.cpp:41-48) and the coarser levels are selected.
 	if((rc = levelClear(h, 0, *p))) return rc;
-	if((rc = levelPair(h, 0, *p))) return rc;
-	if((rc = levelPatchSelect(h, 0, *p))) return rc;
+	if((rc = levelPairAndPatchSelect(h, 0, *p))) return rc;
 	if((rc = finishUpload(h))) return rc;
 	if((rc = levelPixelCov(h, 0, *p))) return rc;
 	rc = buildPyramid(h, s);

@@ -21,7 +21,7 @@ cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom&
 cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,
 		uint32_t* mplus, cudaStream_t st, int* launches);
 cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre, int prePitch, bool fastLayout,
-		cudaStream_t st, int* launches);
+		cudaStream_t st, int* launches, int rowLo = -1, int rowHi = -1); // rows [rowLo, rowHi) only (default: [g.yLo, g.yHi))
 // K2  marking strategy in raster order over the owned rows. asBits / actBits: H x Wp bit-rows (common.cuh), zeroed by
 // the caller (asBits rows above rowBeg may instead hold the upper row tile's hand-off); progress: >= ceil(rows/32).
 extern bool g_forceGenericMarking;

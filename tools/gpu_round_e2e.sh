@@ -1,9 +1,9 @@
 #!/bin/bash
-# streamed upload + per-level marking streams: tests, smoke, bench (resident / e2e streamed / e2e serial), 4K bench
+# streamed upload + per-level marking streams: tests, smoke, bench (resident / e2e streamed / e2e serial) + pipe-rate ubench
 set -x
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tee gpurun_out/smoke.log
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e.json 2> gpurun_out/bench_e2e.err
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_e2e_b.json 2> gpurun_out/bench_e2e_b.err
+timeout 60 tools/ubench/pipe_rates 2>&1 | tee gpurun_out/pipe_rates.txt
 ls -la gpurun_out
