@@ -399,6 +399,13 @@ int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 			if(e != cudaSuccess)
 				return fail(e == cudaErrorInvalidConfiguration ? BCD_B200_ERR_UNSUPPORTED : BCD_B200_ERR_CUDA,
 						"filter chunk failed: %s", cudaGetErrorString(e));
+			if(getenv("BCD_B200_TRACE"))
+			{
+				float t0 = 0.f, dt = 0.f;
+				cudaEventElapsedTime(&t0, h->evTotal[0], h->fev[0]);
+				cudaEventElapsedTime(&dt, h->fev[0], h->fev[5]);
+				fprintf(stderr, "[bcd_b200 trace] filter L%d    start %8.3f  dur %7.3f (%d matrices)\n", k, t0, dt, count);
+			}
 		}
 		h->timings.stage_ms[BCD_B200_STAGE_FILTER_STATS] += ms[0];
 		h->timings.stage_ms[BCD_B200_STAGE_FILTER_EIG] += ms[1];
@@ -451,6 +458,20 @@ int collectTimings(bcd_b200_handle* h)
 		h->timings.stage_ms[h->eventStage[i / 2]] += ms;
 	}
 	CU(cudaEventElapsedTime(&h->timings.total_ms, h->evTotal[0], h->evTotal[1]));
+	if(getenv("BCD_B200_TRACE")) // stage timeline (ms since the start of the run) on stderr: which stages overlap
+	{
+		static const char* names[] = {"prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
+				"finalize", "pyramid"};
+		for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
+		{
+			float t0 = 0.f, dt = 0.f;
+			cudaEventElapsedTime(&t0, h->evTotal[0], h->events[i]);
+			cudaEventElapsedTime(&dt, h->events[i], h->events[i + 1]);
+			const int sgi = h->eventStage[i / 2];
+			fprintf(stderr, "[bcd_b200 trace] %-12s start %8.3f  dur %7.3f\n", sgi >= 0 && sgi < 10 ? names[sgi] : "?", t0, dt);
+		}
+		fprintf(stderr, "[bcd_b200 trace] total %8.3f\n", h->timings.total_ms);
+	}
 	h->stats.kernel_launches = h->launches;
 	return 0;
 }

@@ -256,7 +256,7 @@ def main():
 
     ms_res, stages, launches, clocks = timed(step_resident, True)
     stats = h.stats()
-    ms_e2e, _, _, clocks_e2e = timed(step_e2e, False)
+    ms_e2e, stages_e2e, _, clocks_e2e = timed(step_e2e, False)
     ms_e2e_serial, _, _, _ = timed(step_e2e_serial, False)
     result_ok = bool(np.isfinite(out_pin.numpy()[2:-2, 2:-2]).all())
 
@@ -297,6 +297,7 @@ def main():
                     "ms_per_step_serial_upload": ms_e2e_serial / a.steps},
             "gpu_launches": launches, "roofline": roofline, "roofline_fp32": roofline_fp32,
             "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()},
+            "stage_ms_per_step_e2e": {k: v / a.steps for k, v in stages_e2e.items()},
             "work_counters": stats, "input_generation_s": gen_s, "output_finite": result_ok}
     if not a.no_cpu_baseline:
         cb = cpu_reference_sample({k: v.numpy() for k, v in pin.items()}, a.cpu_crop, a.scales, a.m, a.w, a.b)
