@@ -234,6 +234,10 @@ int finishUpload(bcd_b200_handle* h)
 	return 0;
 }
 
+// rows of look-ahead between an upload chunk and the kernel band that consumes it (>= the largest search radius, 15;
+// a multiple of the pair kernels' tile heights)
+constexpr int UPLOAD_HALO = 16;
+
 // K1b + K1c on the rows [r0, r1) of the level (the whole selection region when r0 < 0)
 int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1)
 {
@@ -270,30 +274,30 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	const LevelGeom g = levelGeom(h, k, p);
 	cudaStream_t st = h->stream;
 	int rc;
-	if(h->up.pending && (k != 0 || h->tiled || h->up.bands <= 1 || h->up.rowEnd[0] <= g.w + g.b))
+	if(h->up.pending && (h->tiled || h->up.bands <= 1))
 		if((rc = finishUpload(h))) return rc;
 	if((rc = clearPre(h, k, p))) return rc;
 	if(k == 0 && h->up.pending)
 	{
-		int r0 = 0;
-		for(int i = 0; i < h->up.bands; ++i)
+		// chunk i of the upload ends UPLOAD_HALO rows below band i of the kernels, so band i waits for chunk i only
+		int r0 = 0, prev0 = 0, prev1 = 0;
+		const int nb = h->up.bands;
+		for(int i = 0; i < nb; ++i)
 		{
-			const int r1 = h->up.rowEnd[i];
-			const int need = std::min(g.H, r1 + g.b);
-			int j = i;
-			while(h->up.rowEnd[j] < need) ++j;
-			CU(cudaStreamWaitEvent(st, h->up.ev[j], 0));
+			const int r1 = i == nb - 1 ? g.H : h->up.rowEnd[i] - UPLOAD_HALO;
+			CU(cudaStreamWaitEvent(st, h->up.ev[i], 0));
 			LevelGeom gb = g;
 			gb.yLo = r0;
 			gb.yHi = r1;
 			STAGE(h, BCD_B200_STAGE_PAIR, {
 				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
 			});
-			if(i > 0 && (rc = patchSelectRows(h, k, p, i > 1 ? h->up.rowEnd[i - 2] : 0, h->up.rowEnd[i - 1]))) return rc;
+			if(i > 0 && (rc = patchSelectRows(h, k, p, prev0, prev1))) return rc;
+			prev0 = r0;
+			prev1 = r1;
 			r0 = r1;
 		}
-		const int nb = h->up.bands;
-		if((rc = patchSelectRows(h, k, p, nb > 1 ? h->up.rowEnd[nb - 2] : 0, h->up.rowEnd[nb - 1]))) return rc;
+		if((rc = patchSelectRows(h, k, p, prev0, prev1))) return rc;
 	}
 	else
 	{
@@ -434,18 +438,26 @@ int levelMerge(bcd_b200_handle* h, int k)
 	return 0;
 }
 
+// level k (>= 1) of the input pyramid from level k-1 (MultiscaleDenoiser.cpp:41-48); parts: 1 = histogram + sample counts
+// (all the selection stage needs), 2 = colour + covariance (needed by the filters only)
+int pyramidLevel(bcd_b200_handle* h, int k, int parts)
+{
+	const LevelBufs& Lp = h->levels[k - 1];
+	LevelBufs& L = h->levels[k];
+	STAGE(h, BCD_B200_STAGE_PYRAMID, {
+		CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
+				L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches, parts));
+	});
+	return 0;
+}
+
 int buildPyramid(bcd_b200_handle* h, int s)
 {
-	if(s > 1)
-		STAGE(h, BCD_B200_STAGE_PYRAMID, {
-			for(int k = 1; k < s; ++k)
-			{
-				const LevelBufs& Lp = h->levels[k - 1];
-				LevelBufs& L = h->levels[k];
-				CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
-						L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches));
-			}
-		});
+	for(int k = 1; k < s; ++k)
+	{
+		int rc = pyramidLevel(h, k, 3);
+		if(rc) return rc;
+	}
 	return 0;
 }
 
@@ -766,19 +778,34 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 	CU(cudaEventRecord(up.evOrder, h->stream));
 	CU(cudaStreamWaitEvent(up.copy, up.evOrder, 0));
 	// order: what the first kernels need first — sample counts, then the histogram in row bands, then covariance + colour
+	// Chunk heights shrink geometrically (x0.8, about the ratio of the pair kernel's time to the transfer time of the
+	// same rows): each band's kernels then end when the next, smaller chunk lands, and only a short band is left to do
+	// after the last byte of the histogram has arrived. Chunk ends are multiples of 8 rows, every chunk >= 24 rows.
 	const int H = in->height;
-	up.bands = H >= 64 ? 8 : 1;
-	const int bandRows = (divUp(H, up.bands) + 7) / 8 * 8;
-	up.bands = divUp(H, bandRows);
+	{
+		int nb = std::max(1, std::min(8, H / 24));
+		double wsum = 0.0, wi = 1.0;
+		for(int i = 0; i < nb; ++i, wi *= 0.8) wsum += wi;
+		int r = 0, n = 0;
+		wi = 1.0;
+		for(int i = 0; i < nb && r < H; ++i, wi *= 0.8)
+		{
+			int rows = std::max(24, (int)(H * wi / wsum + 4.0) / 8 * 8);
+			int r1 = r + rows;
+			if(i == nb - 1 || H - r1 < 24) r1 = H;
+			up.rowEnd[n++] = r1;
+			r = r1;
+		}
+		up.bands = n;
+	}
 	CU(cudaMemcpyAsync(L.ownNs.p, in->nsamples, np * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 	const size_t rowFloats = (size_t)in->width * in->hist_depth;
 	for(int i = 0, r0 = 0; i < up.bands; ++i)
 	{
-		const int r1 = std::min(H, r0 + bandRows);
+		const int r1 = up.rowEnd[i];
 		CU(cudaMemcpyAsync(L.ownHist.as<float>() + (size_t)r0 * rowFloats, in->hist + (size_t)r0 * rowFloats,
 				(size_t)(r1 - r0) * rowFloats * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 		CU(cudaEventRecord(up.ev[i], up.copy));
-		up.rowEnd[i] = r1;
 		r0 = r1;
 	}
 	CU(cudaMemcpyAsync(L.ownCov.p, in->cov, np * 6 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
@@ -842,45 +869,40 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	if(progress) progress(0.f, user);
 	h->tiled = false;
 	h->runParams = *p;
-	// Level 0 selection first: its clear / pair-term / patch-select kernels need only the histogram and the sample
-	// counts, so under a streamed upload they start as soon as the first bands have landed. Then the rest of the
-	// inputs is awaited, the pyramid is built (MultiscaleDenoiser.cpp:41-48) and the coarser levels are selected.
-	if((rc = levelClear(h, 0, *p))) return rc;
-	if((rc = levelPairAndPatchSelect(h, 0, *p))) return rc;
+	// Phase 1 — everything that needs only histograms and sample counts, finest level first: under a streamed upload
+	// the level-0 kernels start as soon as the first row bands have landed, and the coarser levels' selection runs while
+	// covariance and colour are still in flight. Each level's marking chain (K2) follows on its own high-priority stream.
+	for(int k = 0; k < s; ++k)
+	{
+		if(k > 0 && (rc = pyramidLevel(h, k, 1))) return rc;
+		if((rc = levelClear(h, k, *p))) return rc;
+		if((rc = levelPairAndPatchSelect(h, k, *p))) return rc;
+		if((rc = levelMarkEnqueue(h, k, *p))) return rc;
+	}
+	// Phase 2 — colour + covariance: rest of the pyramid (MultiscaleDenoiser.cpp:41-48), per-pixel covariances, filters.
+	// Level 0 is filtered first (its marking finished under the coarser selections; theirs finish under this filter),
+	// then the coarser levels; the merges run coarsest to finest at the end (MultiscaleDenoiser.cpp:79-134).
 	if((rc = finishUpload(h))) return rc;
-	if((rc = levelPixelCov(h, 0, *p))) return rc;
-	rc = buildPyramid(h, s);
-	if(rc) return rc;
-	for(int k = s - 1; k >= 1; --k)
+	for(int k = 1; k < s; ++k)
+		if((rc = pyramidLevel(h, k, 2))) return rc;
+	for(int k = 0; k < s; ++k)
+		if((rc = levelPixelCov(h, k, *p))) return rc;
+	const float total = float(((1 << (2 * s)) - 1) / 3); // progress weights like MultiscaleDenoiser.cpp:85,103-112
+	float doneWeight = 0.f;
+	for(int i = 0; i < s; ++i)
 	{
-		rc = levelSelect(h, k, *p);
-		if(rc) return rc;
-	}
-	// The marking chains run on their own high-priority streams (level 0 — the longest — first, under the selection of
-	// the coarser levels); filters and merges follow on the main stream coarsest to finest (MultiscaleDenoiser.cpp:79-134).
-	if((rc = levelMarkEnqueue(h, 0, *p))) return rc;
-	for(int k = s - 1; k >= 1; --k)
-	{
-		rc = levelMarkEnqueue(h, k, *p);
-		if(rc) return rc;
-	}
-	const float total = float(((1 << (2 * s)) - 1) / 3); // progress mapped like MultiscaleDenoiser.cpp:85,103-112
-	for(int k = s - 1; k >= 0; --k)
-	{
+		const int k = i == 0 ? 0 : s - i;
 		if((rc = levelMarkWait(h, k))) return rc;
 		if((rc = levelFilter(h, k, *p))) return rc;
 		if((rc = levelFinalize(h, k, *p))) return rc;
-		if(k < s - 1)
-		{
-			rc = levelMerge(h, k);
-			if(rc) return rc;
-		}
+		doneWeight += float(1 << (2 * (s - 1 - k)));
 		if(progress)
-		{
-			const int sdone = s - 1 - k;
-			progress(float(((1 << (2 * (sdone + 1))) - 1) / 3) / total, user);
-		}
+			progress(std::min(1.f, doneWeight / total), user);
 	}
+	for(int k = s - 2; k >= 0; --k)
+		if((rc = levelMerge(h, k))) return rc;
+	if(progress)
+		progress(1.f, user);
 	CU(cudaEventRecord(h->evTotal[1], st));
 	CU(cudaStreamSynchronize(st));
 	rc = collectTimings(h);

@@ -269,17 +269,24 @@ __global__ void k_downscale_cov(const float* __restrict__ cov, const float* __re
 }
 
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
-		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches)
+		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts)
 {
 	const size_t npd = (size_t)(W / 2) * (H / 2);
 	if(npd == 0)
 		return cudaSuccess;
 	auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-	k_downscale<<<blocks(npd * 3), 256, 0, st>>>(color, W, H, 3, 1, colorD);
-	k_downscale<<<blocks(npd), 256, 0, st>>>(ns, W, H, 1, 0, nsD);
-	k_downscale<<<blocks(npd * B), 256, 0, st>>>(hist, W, H, B, 0, histD);
-	k_downscale_cov<<<blocks(npd * 6), 256, 0, st>>>(cov, ns, W, H, covD);
-	*launches += 4;
+	if(parts & 1) // what the selection stage of the coarser level reads
+	{
+		k_downscale<<<blocks(npd), 256, 0, st>>>(ns, W, H, 1, 0, nsD);
+		k_downscale<<<blocks(npd * B), 256, 0, st>>>(hist, W, H, B, 0, histD);
+		*launches += 2;
+	}
+	if(parts & 2) // what its filters read
+	{
+		k_downscale<<<blocks(npd * 3), 256, 0, st>>>(color, W, H, 3, 1, colorD);
+		k_downscale_cov<<<blocks(npd * 6), 256, 0, st>>>(cov, ns, W, H, covD);
+		*launches += 2;
+	}
 	return cudaGetLastError();
 }
 
