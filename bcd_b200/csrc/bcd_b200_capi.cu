@@ -108,6 +108,10 @@ struct bcd_b200_handle
 		int rowEnd[16];
 		cudaEvent_t ev[16] = {};
 		cudaEvent_t evAll = nullptr, evOrder = nullptr;
+		// banded level-0 selection: K1b/K1c of band i-1 run on `sel` next to K1a of band i+1 on the main stream
+		cudaStream_t sel = nullptr;
+		cudaEvent_t evPair[16] = {};
+		cudaEvent_t evSelDone = nullptr;
 	} up;
 	int filterChunk = 0;
 	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
@@ -239,15 +243,14 @@ int finishUpload(bcd_b200_handle* h)
 constexpr int UPLOAD_HALO = 16;
 
 // K1b + K1c on the rows [r0, r1) of the level (the whole selection region when r0 < 0)
-int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1)
+int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st)
 {
 	LevelBufs& L = h->levels[k];
 	LevelGeom g = levelGeom(h, k, p);
-	cudaStream_t st = h->stream;
 	const bool fastLayout = markingUsesFastLayout(g.b);
 	LevelGeom gb = g;
 	if(r0 >= 0) { gb.yLo = r0; gb.yHi = r1; }
-	STAGE(h, BCD_B200_STAGE_SELECT, {
+	STAGE_ON(h, st, BCD_B200_STAGE_SELECT, {
 		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), gb, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
 		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, L.smask.as<uint32_t>(), L.counts.as<int>(),
 				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches, gb.yLo, gb.yHi));
@@ -279,32 +282,42 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	if((rc = clearPre(h, k, p))) return rc;
 	if(k == 0 && h->up.pending)
 	{
-		// chunk i of the upload ends UPLOAD_HALO rows below band i of the kernels, so band i waits for chunk i only
+		// chunk i of the upload ends UPLOAD_HALO rows below band i of the kernels, so band i waits for chunk i only; the
+		// patch selection of band i-1 (needs the pair terms of band i for its w halo rows) runs on a second stream, so
+		// the tails of the small band kernels overlap instead of adding up
+		bcd_b200_handle::Upload& up = h->up;
+		cudaStream_t sel = up.sel;
+		CU(cudaEventRecord(up.evOrder, st)); // `pre` cleared, previous users of the scratch done
+		CU(cudaStreamWaitEvent(sel, up.evOrder, 0));
 		int r0 = 0, prev0 = 0, prev1 = 0;
-		const int nb = h->up.bands;
+		const int nb = up.bands;
 		for(int i = 0; i < nb; ++i)
 		{
-			const int r1 = i == nb - 1 ? g.H : h->up.rowEnd[i] - UPLOAD_HALO;
-			CU(cudaStreamWaitEvent(st, h->up.ev[i], 0));
+			const int r1 = i == nb - 1 ? g.H : up.rowEnd[i] - UPLOAD_HALO;
+			CU(cudaStreamWaitEvent(st, up.ev[i], 0));
 			LevelGeom gb = g;
 			gb.yLo = r0;
 			gb.yHi = r1;
 			STAGE(h, BCD_B200_STAGE_PAIR, {
 				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
 			});
-			if(i > 0 && (rc = patchSelectRows(h, k, p, prev0, prev1))) return rc;
+			CU(cudaEventRecord(up.evPair[i], st));
+			CU(cudaStreamWaitEvent(sel, up.evPair[i], 0));
+			if(i > 0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
 			prev0 = r0;
 			prev1 = r1;
 			r0 = r1;
 		}
-		if((rc = patchSelectRows(h, k, p, prev0, prev1))) return rc;
+		if((rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+		CU(cudaEventRecord(up.evSelDone, sel));
+		CU(cudaStreamWaitEvent(st, up.evSelDone, 0));
 	}
 	else
 	{
 		STAGE(h, BCD_B200_STAGE_PAIR, {
 			CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
 		});
-		if((rc = patchSelectRows(h, k, p, -1, -1))) return rc;
+		if((rc = patchSelectRows(h, k, p, -1, -1, st))) return rc;
 	}
 	CU(cudaEventRecord(L.evSel, st));
 	return 0;
@@ -715,6 +728,9 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	cudaStreamSynchronize(h->aux);
 	for(cudaStream_t a : h->ownAuxLevel) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
 	for(int i = 0; i < 16; ++i) if(h->up.ev[i]) cudaEventDestroy(h->up.ev[i]);
+	for(int i = 0; i < 16; ++i) if(h->up.evPair[i]) cudaEventDestroy(h->up.evPair[i]);
+	if(h->up.evSelDone) cudaEventDestroy(h->up.evSelDone);
+	if(h->up.sel) { cudaStreamSynchronize(h->up.sel); cudaStreamDestroy(h->up.sel); }
 	if(h->up.evAll) cudaEventDestroy(h->up.evAll);
 	if(h->up.evOrder) cudaEventDestroy(h->up.evOrder);
 	if(h->up.copy) cudaStreamDestroy(h->up.copy);
@@ -766,8 +782,13 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 		CU(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
 		CU(cudaEventCreateWithFlags(&up.evAll, cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&up.evOrder, cudaEventDisableTiming));
+		CU(cudaStreamCreateWithFlags(&up.sel, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&up.evSelDone, cudaEventDisableTiming));
 		for(int i = 0; i < 16; ++i)
+		{
 			CU(cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&up.evPair[i], cudaEventDisableTiming));
+		}
 	}
 	const size_t np = (size_t)in->width * in->height;
 	CU(L.ownColor.reserve(np * 3 * sizeof(float)));
@@ -778,21 +799,28 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 	CU(cudaEventRecord(up.evOrder, h->stream));
 	CU(cudaStreamWaitEvent(up.copy, up.evOrder, 0));
 	// order: what the first kernels need first — sample counts, then the histogram in row bands, then covariance + colour
-	// Chunk heights shrink geometrically (x0.8, about the ratio of the pair kernel's time to the transfer time of the
-	// same rows): each band's kernels then end when the next, smaller chunk lands, and only a short band is left to do
-	// after the last byte of the histogram has arrived. Chunk ends are multiples of 8 rows, every chunk >= 24 rows.
+	// Chunk heights: a small first chunk (the kernels start early), then heights that shrink geometrically (x0.85 —
+	// the kernels of a band take about 0.8x the transfer time of its rows, so each band is done when the next, smaller
+	// chunk lands) down to a short last band, the only one left to do after the last byte of the histogram has arrived.
+	// Chunk ends are multiples of 8 rows, every chunk >= 24 rows.
 	const int H = in->height;
 	{
-		int nb = std::max(1, std::min(8, H / 24));
-		double wsum = 0.0, wi = 1.0;
-		for(int i = 0; i < nb; ++i, wi *= 0.8) wsum += wi;
+		const int nb = std::max(1, std::min(8, H / 24));
 		int r = 0, n = 0;
-		wi = 1.0;
-		for(int i = 0; i < nb && r < H; ++i, wi *= 0.8)
+		if(nb >= 4)
 		{
-			int rows = std::max(24, (int)(H * wi / wsum + 4.0) / 8 * 8);
+			r = std::max(24, std::min(64, H / 16 / 8 * 8));
+			up.rowEnd[n++] = r;
+		}
+		const int rest = nb - n, Hr = H - r;
+		double wsum = 0.0, wi = 1.0;
+		for(int i = 0; i < rest; ++i, wi *= 0.85) wsum += wi;
+		wi = 1.0;
+		for(int i = 0; i < rest && r < H; ++i, wi *= 0.85)
+		{
+			const int rows = std::max(24, (int)(Hr * wi / wsum + 4.0) / 8 * 8);
 			int r1 = r + rows;
-			if(i == nb - 1 || H - r1 < 24) r1 = H;
+			if(i == rest - 1 || H - r1 < 24) r1 = H;
 			up.rowEnd[n++] = r1;
 			r = r1;
 		}
