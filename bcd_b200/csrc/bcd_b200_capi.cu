@@ -782,7 +782,13 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 		CU(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
 		CU(cudaEventCreateWithFlags(&up.evAll, cudaEventDisableTiming));
 		CU(cudaEventCreateWithFlags(&up.evOrder, cudaEventDisableTiming));
-		CU(cudaStreamCreateWithFlags(&up.sel, cudaStreamNonBlocking));
+		{
+			// high priority: the short selection kernels of band i-1 take the SMs the pair kernel of band i+1 frees, so
+			// the selection never lags more than one band behind
+			int lo = 0, hi = 0;
+			cudaDeviceGetStreamPriorityRange(&lo, &hi);
+			CU(cudaStreamCreateWithPriority(&up.sel, cudaStreamNonBlocking, hi));
+		}
 		CU(cudaEventCreateWithFlags(&up.evSelDone, cudaEventDisableTiming));
 		for(int i = 0; i < 16; ++i)
 		{
