@@ -805,24 +805,24 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 	CU(cudaEventRecord(up.evOrder, h->stream));
 	CU(cudaStreamWaitEvent(up.copy, up.evOrder, 0));
 	// order: what the first kernels need first — sample counts, then the histogram in row bands, then covariance + colour
-	// Chunk heights: a small first chunk (the kernels start early), then heights that shrink geometrically (x0.85 —
-	// the kernels of a band take about 0.8x the transfer time of its rows, so each band is done when the next, smaller
-	// chunk lands) down to a short last band, the only one left to do after the last byte of the histogram has arrived.
-	// Chunk ends are multiples of 8 rows, every chunk >= 24 rows.
+	// Chunk heights: up to 12 chunks, a small first one (the kernels start early), then heights that shrink slowly
+	// (x0.95: on a B200 behind PCIe 5 the banded kernels of a chunk take about as long as its transfer, so the pipeline
+	// is balanced and what counts is an early start and a short last band). Chunk ends are multiples of 8 rows, every
+	// chunk >= 24 rows.
 	const int H = in->height;
 	{
-		const int nb = std::max(1, std::min(8, H / 24));
+		const int nb = std::max(1, std::min(12, H / 24));
 		int r = 0, n = 0;
 		if(nb >= 4)
 		{
-			r = std::max(24, std::min(64, H / 16 / 8 * 8));
+			r = std::max(24, std::min(48, H / 16 / 8 * 8));
 			up.rowEnd[n++] = r;
 		}
 		const int rest = nb - n, Hr = H - r;
 		double wsum = 0.0, wi = 1.0;
-		for(int i = 0; i < rest; ++i, wi *= 0.85) wsum += wi;
+		for(int i = 0; i < rest; ++i, wi *= 0.95) wsum += wi;
 		wi = 1.0;
-		for(int i = 0; i < rest && r < H; ++i, wi *= 0.85)
+		for(int i = 0; i < rest && r < H; ++i, wi *= 0.95)
 		{
 			const int rows = std::max(24, (int)(Hr * wi / wsum + 4.0) / 8 * 8);
 			int r1 = r + rows;
