@@ -24,6 +24,7 @@ SYMBOLS = [
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
     "bcd_b200_spike_removal", "bcd_b200_spike_removal_host", "bcd_b200_download_inputs",
     # row-tile API (multi-GPU), wrapped by bcd_b200/tiles.py
+    "bcd_b200_set_level_aux_stream", "bcd_b200_tile_mark_enqueue", "bcd_b200_tile_mark_wait",
     "bcd_b200_tile_plan", "bcd_b200_tile_begin", "bcd_b200_tile_select", "bcd_b200_tile_mark", "bcd_b200_tile_filter",
     "bcd_b200_tile_finalize", "bcd_b200_tile_merge", "bcd_b200_tile_xfer_bytes", "bcd_b200_tile_export",
     "bcd_b200_tile_import", "bcd_b200_tile_end", "bcd_b200_tile_download",

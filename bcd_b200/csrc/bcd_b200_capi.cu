@@ -97,6 +97,7 @@ struct bcd_b200_handle
 	// overlaps the selection of level k-1 and the filters of the coarser levels on the main stream
 	cudaStream_t ownAux = nullptr, aux = nullptr;
 	std::vector<cudaStream_t> ownAuxLevel; // levels >= 1 get their own marking stream (the chains of different levels are independent)
+	std::vector<cudaStream_t> userAuxLevel; // caller-owned marking stream per level (bcd_b200_set_level_aux_stream), or null
 	// streamed upload (bcd_b200_upload_async): the histogram arrives in row bands on a copy stream, one event per band;
 	// the level-0 pair-term kernel (K1a) is launched band by band behind those events, so the PCIe transfer of the
 	// (dominant) histogram overlaps the dominant kernel
@@ -335,6 +336,8 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // marking stream of level k: the caller's aux stream when one was set, else one high-priority stream per level
 cudaStream_t auxOf(bcd_b200_handle* h, int k)
 {
+	if(k < (int)h->userAuxLevel.size() && h->userAuxLevel[k])
+		return h->userAuxLevel[k];
 	if(h->aux != h->ownAux || k == 0 || k > (int)h->ownAuxLevel.size())
 		return h->aux;
 	return h->ownAuxLevel[k - 1];
@@ -768,6 +771,15 @@ int bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream
 	return 0;
 }
 
+int bcd_b200_set_level_aux_stream(bcd_b200_handle* h, int level, void* aux_stream)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(level < 0 || level >= 16) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "level %d out of range", level);
+	if((int)h->userAuxLevel.size() <= level) h->userAuxLevel.resize(level + 1, nullptr);
+	h->userAuxLevel[level] = reinterpret_cast<cudaStream_t>(aux_stream);
+	return 0;
+}
+
 int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
@@ -1070,6 +1082,8 @@ int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 
 int bcd_b200_tile_select(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelSelect(h, level, h->runParams); }
 int bcd_b200_tile_mark(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMark(h, level, h->runParams); }
+int bcd_b200_tile_mark_enqueue(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMarkEnqueue(h, level, h->runParams); }
+int bcd_b200_tile_mark_wait(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMarkWait(h, level); }
 int bcd_b200_tile_filter(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFilter(h, level, h->runParams); }
 int bcd_b200_tile_finalize(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFinalize(h, level, h->runParams); }
 int bcd_b200_tile_merge(bcd_b200_handle* h, int level)

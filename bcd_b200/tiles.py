@@ -4,12 +4,16 @@ horizontal bands, no collective — only neighbour send/recv of small strips bet
 The stage functions and the strips are the row-tile API of the C ABI (include/bcd_b200.h, `bcd_b200_tile_*`); this
 module only sequences them and moves the strips:
 
-    per level, coarsest first:
+    per level, finest first (its marking chain is the longest, so it starts first):
         select                                       (independent on every rank: the dominant cost)
-        [m > 0]  AS rows: recv from rank-1 -> mark -> send to rank+1      (the raster-order marking is a chain)
-        filter                                       (independent)
+        [m > 0]  on the level's own stream — AS rows: recv from rank-1 -> mark (enqueue) -> send to rank+1
+                 (the raster-order marking is a chain through the ranks; the chains of the levels run side by side
+                 and under the selection of the other levels)
+    per level, level 0 first, then coarsest .. 1:
+        wait for the level's work counters; filter   (independent)
         accumulator halo: isend/irecv with both neighbours, add           ((b+w) rows x W x 16 B each way)
-        finalize; output rows: isend/irecv (2 rows); [level < s-1] merge; output rows again
+        finalize; output rows: isend/irecv (2 rows)
+    per level s-2 .. 0: merge; output rows again
 
 `LoopbackExchange` runs all tiles inside one process (tiles processed stage by stage, strips handed over directly);
 it is what the single-GPU parity test uses to check that tiles reproduce the full-frame result.
@@ -35,7 +39,8 @@ def _lib():
     if not getattr(L, "_tiles_ready", False):
         L.bcd_b200_tile_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(capi.Params), C.POINTER(Tile)]
         L.bcd_b200_tile_begin.argtypes = [C.c_void_p, C.POINTER(capi.Params), C.POINTER(Tile)]
-        for n in ("select", "mark", "filter", "finalize", "merge"):
+        L.bcd_b200_set_level_aux_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        for n in ("select", "mark", "mark_enqueue", "mark_wait", "filter", "finalize", "merge"):
             getattr(L, "bcd_b200_tile_" + n).argtypes = [C.c_void_p, C.c_int]
         L.bcd_b200_tile_xfer_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.bcd_b200_tile_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -44,6 +49,12 @@ def _lib():
         L.bcd_b200_tile_download.argtypes = [C.c_void_p, C.c_void_p]
         L._tiles_ready = True
     return L
+
+
+def make_aux_streams(torch_device, levels):
+    """One high-priority torch stream per pyramid level for the marking chains."""
+    import torch
+    return [torch.cuda.Stream(device=torch_device, priority=-1) for _ in range(levels)]
 
 
 def plan(W, H, index, count, params):
@@ -58,14 +69,23 @@ class TileWorker:
 
     def __init__(self, handle, params, tile, torch_device, main_stream=None, aux_stream=None):
         """main_stream / aux_stream: torch.cuda.Stream objects shared with the exchange (NCCL orders its transfers
-        against the current torch stream, so the strips of the marking chain must be moved under `aux_stream`)."""
+        against the current torch stream, so the strips of the marking chain of level k must be moved under
+        `aux_streams[k]`). aux_stream: one stream (all levels share it), a list with one stream per level, or None
+        (one high-priority stream per level is created)."""
         import torch
         self.torch = torch
         self.h, self.params, self.tile, self.device = handle, params, tile, torch_device
         self.has = {UP: tile.tile_index > 0, DOWN: tile.tile_index < tile.tile_count - 1}
         self.main_stream = main_stream if main_stream is not None else torch.cuda.Stream(device=torch_device)
-        self.aux_stream = aux_stream if aux_stream is not None else torch.cuda.Stream(device=torch_device, priority=-1)
+        if aux_stream is None:
+            aux_stream = make_aux_streams(torch_device, params.nb_scales)
+        elif not isinstance(aux_stream, (list, tuple)):
+            aux_stream = [aux_stream] * params.nb_scales
+        self.aux_streams = list(aux_stream)
+        self.aux_stream = self.aux_streams[0]
         handle.set_streams(self.main_stream.cuda_stream, self.aux_stream.cuda_stream)
+        for k, st in enumerate(self.aux_streams):
+            capi._check(_lib().bcd_b200_set_level_aux_stream(handle._h, k, C.c_void_p(st.cuda_stream)))
 
     def begin(self):
         capi._check(_lib().bcd_b200_tile_begin(self.h._h, C.byref(self.params), C.byref(self.tile)))
@@ -127,6 +147,12 @@ class DistExchange:
         self.dist.send(buf, dst=self.rank + 1)
 
 
+def level_order(s):
+    """Order in which the levels are filtered: level 0 first (its marking chain was started first and its filter is the
+    longest, so the chains of the coarser levels finish under it), then coarsest .. 1."""
+    return [0] + list(range(s - 1, 0, -1))
+
+
 def run_tile(worker, ex):
     """Drives one tile through all levels with a DistExchange (every rank calls this)."""
     import torch
@@ -134,23 +160,24 @@ def run_tile(worker, ex):
     s = p.nb_scales
     with torch.cuda.stream(worker.main_stream):
         worker.begin()
-        for k in range(s - 1, -1, -1):  # every selection first: the marking chain below overlaps it
+        for k in range(s):  # selection + this rank's link of the marking chain, finest level first
             worker.stage("select", k)
-        for k in range(s - 1, -1, -1):
-            with torch.cuda.stream(worker.aux_stream):
+            with torch.cuda.stream(worker.aux_streams[k]):
                 if p.skip_prob > 0 and worker.has[UP]:
                     buf = torch.empty(worker.strip_bytes(k, AS_ROWS), dtype=torch.uint8, device=worker.device)
                     worker.import_(k, AS_ROWS, UP, ex.recv_from_up(buf))
-                worker.stage("mark", k)  # blocks the host until this rank's part of the chain is done
+                worker.stage("mark_enqueue", k)
                 if p.skip_prob > 0 and worker.has[DOWN]:
                     ex.send_down(worker.export(k, AS_ROWS, DOWN))
+        for k in level_order(s):
+            worker.stage("mark_wait", k)  # host: this rank's work counters of the level
             worker.stage("filter", k)
             _swap_and_import(worker, ex, k, ACC_HALO)
             worker.stage("finalize", k)
             _swap_and_import(worker, ex, k, OUT_ROWS)
-            if k < s - 1:
-                worker.stage("merge", k)
-                _swap_and_import(worker, ex, k, OUT_ROWS)
+        for k in range(s - 2, -1, -1):
+            worker.stage("merge", k)
+            _swap_and_import(worker, ex, k, OUT_ROWS)
         worker.end()
 
 
@@ -179,24 +206,26 @@ def run_tiles_loopback(workers):
 
     for w in workers:
         w.begin()
-    for k in range(s - 1, -1, -1):
+    for k in range(s):
         for w in workers:
             w.stage("select", k)
-    for k in range(s - 1, -1, -1):
         for i, w in enumerate(workers):  # the marking chain, top to bottom
-            if p.skip_prob > 0 and i > 0:
-                w.import_(k, AS_ROWS, UP, workers[i - 1].export(k, AS_ROWS, DOWN))
-            w.stage("mark", k)
+            with w.torch.cuda.stream(w.aux_streams[k]):
+                if p.skip_prob > 0 and i > 0:
+                    w.import_(k, AS_ROWS, UP, workers[i - 1].export(k, AS_ROWS, DOWN))
+                w.stage("mark_enqueue", k)
+    for k in level_order(s):
         for w in workers:
+            w.stage("mark_wait", k)
             w.stage("filter", k)
         swap_all(k, ACC_HALO)
         for w in workers:
             w.stage("finalize", k)
         swap_all(k, OUT_ROWS)
-        if k < s - 1:
-            for w in workers:
-                w.stage("merge", k)
-            swap_all(k, OUT_ROWS)
+    for k in range(s - 2, -1, -1):
+        for w in workers:
+            w.stage("merge", k)
+        swap_all(k, OUT_ROWS)
     for w in workers:
         w.end()
     assert n == workers[0].tile.tile_count
@@ -243,10 +272,9 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
     # an explicit (non-default) stream shared by torch/NCCL and the handle: the legacy default stream has handle 0,
     # which bcd_b200_set_stream reads as "use the handle's own stream" and would leave the strips unordered
     stream = torch.cuda.Stream(device=dev)
-    aux = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(stream)
     h = capi.Handle(local_rank)
-    worker = TileWorker(h, params, t, dev, stream, aux)
+    worker = TileWorker(h, params, t, dev, stream, None)  # one marking stream per level
     ex = DistExchange(dist, rank, world)
 
     def step_resident():

@@ -108,6 +108,9 @@ int  bcd_b200_set_stream(bcd_b200_handle* h, void* cuda_stream);
  * that it overlaps the selection / filters on the main stream; NULL keeps the handle's own high-priority streams (one
  * per pyramid level) */
 int  bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream);
+/* caller-owned marking stream of one pyramid level (NULL: back to the default). Row-tile drivers give every level its
+ * own stream so that the marking chains of the levels — each a dependency through all ranks — run side by side */
+int  bcd_b200_set_level_aux_stream(bcd_b200_handle* h, int level, void* aux_stream);
 /* host -> device copy of the four input images (pinned or pageable host memory) */
 int  bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in);
 /* streamed variant: returns as soon as the copies are enqueued (sample counts, then the histogram in row bands, then
@@ -150,15 +153,20 @@ int  bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples,
  * this with torch.distributed send/recv):
  *
  *   tile_begin                      pyramid build (local)
- *   for level = s-1 .. 0:
+ *   for level = 0 .. s-1:           (finest first: its marking chain is the longest)
  *     tile_select(level)            K0 + K1 on the band (+ halo rows)
- *     [m > 0] import AS_ROWS from the upper neighbour -> tile_mark(level) -> export AS_ROWS to the lower neighbour
+ *     [m > 0] on the level's marking stream: import AS_ROWS from the upper neighbour -> tile_mark_enqueue(level) ->
+ *             export AS_ROWS to the lower neighbour (the raster-order marking is a chain through the ranks)
+ *   for level = 0, s-1, .., 1:
+ *     tile_mark_wait(level)         host: work counters of the level
  *     tile_filter(level)            fallback + two-step filter into the local accumulator
  *     export ACC_HALO (up, down) -> neighbours -> import (adds)      the only data-path exchange: (b+w) rows x W x 16 B
  *     tile_finalize(level)
  *     export OUT_ROWS (up, down) -> neighbours -> import             2 rows of the level's output
- *     [level < s-1] tile_merge(level), then OUT_ROWS again (the merged rows feed the next finer level)
+ *   for level = s-2 .. 0:
+ *     tile_merge(level), then OUT_ROWS again (the merged rows feed the next finer level)
  *   tile_download                   owned rows of level 0
+ * (any order that respects select -> mark -> filter -> finalize per level and finalize(k), merge(k+1) -> merge(k) works)
  *
  * No collective is needed: replaces nothing in the reference (it has no multi-GPU path). */
 typedef struct bcd_b200_tile {
@@ -176,7 +184,12 @@ int  bcd_b200_tile_plan(int image_width, int image_height, int tile_index, int t
                         bcd_b200_tile* out);
 int  bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t);
 int  bcd_b200_tile_select(bcd_b200_handle* h, int level);
-int  bcd_b200_tile_mark(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_mark(bcd_b200_handle* h, int level);          /* = tile_mark_enqueue + tile_mark_wait */
+/* asynchronous halves of tile_mark: enqueue K2 + list builder + counter read-back on the level's marking stream;
+ * wait for the counters on the host (needed before tile_filter). Between the two the caller may already export the
+ * AS_ROWS strip for the lower neighbour (stream-ordered) and go on with other levels. */
+int  bcd_b200_tile_mark_enqueue(bcd_b200_handle* h, int level);
+int  bcd_b200_tile_mark_wait(bcd_b200_handle* h, int level);
 int  bcd_b200_tile_filter(bcd_b200_handle* h, int level);
 int  bcd_b200_tile_finalize(bcd_b200_handle* h, int level);
 int  bcd_b200_tile_merge(bcd_b200_handle* h, int level);

@@ -21,7 +21,8 @@ def _full(capi, inp, **kw):
 def _tiled(capi, tiles, inp, count, **kw):
     import torch
     params = capi.make_params(**kw)
-    stream, aux = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)  # all tiles exchange strips on shared streams
+    # all tiles exchange strips on shared streams: one main stream, one marking stream per level
+    stream, aux = torch.cuda.Stream(), tiles.make_aux_streams(torch.device("cuda", 0), params.nb_scales)
     with torch.cuda.stream(stream):
         workers = [tiles.make_worker(inp, params, i, count, main_stream=stream, aux_stream=aux) for i in range(count)]
         tiles.run_tiles_loopback(workers)

@@ -28,7 +28,7 @@ def main():
         rows = t.sub_row1 - t.sub_row0
         sub = host.synth(W, H, spp=24, row0=t.sub_row0, rows=rows)
         h = capi.Handle(lr)
-        worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr), stream, aux)
+        worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr), stream, None)  # one marking stream per level
         h.upload(**sub)
         tiles.run_tile(worker, tiles.DistExchange(dist, rank, world))
         mine = torch.from_numpy(worker.download()).cuda()
