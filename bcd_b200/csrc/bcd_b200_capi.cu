@@ -105,6 +105,7 @@ struct bcd_b200_handle
 	{
 		cudaStream_t copy = nullptr;
 		bool pending = false;
+		bool histOrdered = false; // the main stream has waited for every histogram chunk of the pending upload
 		int bands = 0;
 		int rowEnd[16];
 		cudaEvent_t ev[16] = {};
@@ -127,6 +128,10 @@ struct bcd_b200_handle
 	int launches = 0;
 	// row-tile mode (multi-GPU): the resident inputs are rows [subRow0, subRow1) of an imageH-row frame and this
 	// handle produces the output rows [ownRow0, ownRow1) (frame coordinates)
+	// row-tile mode builds the pyramid lazily: histogram part of level k before its selection, colour part before its
+	// filter (highest level built so far), so that a streamed upload overlaps the level-0 selection here too
+	int pyrHistDone = 0, pyrColorDone = 0;
+	bool pixcovDone[16] = {};
 	bool tiled = false;
 	int imageH = 0, subRow0 = 0, subRow1 = 0, ownRow0 = 0, ownRow1 = 0;
 	bcd_b200_params runParams;
@@ -278,7 +283,7 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	const LevelGeom g = levelGeom(h, k, p);
 	cudaStream_t st = h->stream;
 	int rc;
-	if(h->up.pending && (h->tiled || h->up.bands <= 1))
+	if(h->up.pending && h->up.bands <= 1)
 		if((rc = finishUpload(h))) return rc;
 	if((rc = clearPre(h, k, p))) return rc;
 	if(k == 0 && h->up.pending)
@@ -290,12 +295,15 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		cudaStream_t sel = up.sel;
 		CU(cudaEventRecord(up.evOrder, st)); // `pre` cleared, previous users of the scratch done
 		CU(cudaStreamWaitEvent(sel, up.evOrder, 0));
-		int r0 = 0, prev0 = 0, prev1 = 0;
+		int r0 = g.yLo, prev0 = 0, prev1 = 0;
 		const int nb = up.bands;
 		for(int i = 0; i < nb; ++i)
 		{
-			const int r1 = i == nb - 1 ? g.H : up.rowEnd[i] - UPLOAD_HALO;
+			// band = rows of chunk i minus the look-ahead, clipped to the rows the selection runs on (row tiles)
+			const int r1 = std::min(g.yHi, i == nb - 1 ? g.H : up.rowEnd[i] - UPLOAD_HALO);
 			CU(cudaStreamWaitEvent(st, up.ev[i], 0));
+			if(r1 <= r0)
+				continue;
 			LevelGeom gb = g;
 			gb.yLo = r0;
 			gb.yHi = r1;
@@ -304,14 +312,15 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 			});
 			CU(cudaEventRecord(up.evPair[i], st));
 			CU(cudaStreamWaitEvent(sel, up.evPair[i], 0));
-			if(i > 0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+			if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
 			prev0 = r0;
 			prev1 = r1;
 			r0 = r1;
 		}
-		if((rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+		if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
 		CU(cudaEventRecord(up.evSelDone, sel));
 		CU(cudaStreamWaitEvent(st, up.evSelDone, 0));
+		up.histOrdered = true;
 	}
 	else
 	{
@@ -324,11 +333,41 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
+// level k (>= 1) of the input pyramid from level k-1 (MultiscaleDenoiser.cpp:41-48); parts: 1 = histogram + sample counts
+// (all the selection stage needs), 2 = colour + covariance (needed by the filters only)
+int pyramidLevel(bcd_b200_handle* h, int k, int parts)
+{
+	const LevelBufs& Lp = h->levels[k - 1];
+	LevelBufs& L = h->levels[k];
+	STAGE(h, BCD_B200_STAGE_PYRAMID, {
+		CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
+				L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches, parts));
+	});
+	return 0;
+}
+
+int buildPyramid(bcd_b200_handle* h, int s)
+{
+	for(int k = 1; k < s; ++k)
+	{
+		int rc = pyramidLevel(h, k, 3);
+		if(rc) return rc;
+	}
+	return 0;
+}
+
+// row-tile entry: selection of level k, with the histogram part of the pyramid built on demand
 int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
-	int rc = finishUpload(h);
+	int rc = 0;
+	if(k > 0 && h->up.pending && !h->up.histOrdered) // the level-0 bands have not been through yet
+		rc = finishUpload(h);
+	for(int l = h->pyrHistDone + 1; l <= k && !rc; ++l)
+	{
+		rc = pyramidLevel(h, l, 1);
+		h->pyrHistDone = l;
+	}
 	if(!rc) rc = levelClear(h, k, p);
-	if(!rc) rc = levelPixelCov(h, k, p);
 	if(!rc) rc = levelPairAndPatchSelect(h, k, p);
 	return rc;
 }
@@ -434,6 +473,24 @@ int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
+// row-tile entry: filters of level k; colour / covariance part of the pyramid and the per-pixel covariances on demand
+int levelFilterTile(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	int rc = finishUpload(h);
+	for(int l = h->pyrColorDone + 1; l <= k && !rc; ++l)
+	{
+		rc = pyramidLevel(h, l, 2);
+		h->pyrColorDone = l;
+	}
+	if(!rc && !h->pixcovDone[k])
+	{
+		rc = levelPixelCov(h, k, p);
+		h->pixcovDone[k] = true;
+	}
+	if(!rc) rc = levelFilter(h, k, p);
+	return rc;
+}
+
 // stage 4 (main stream): out = sum / count
 int levelFinalize(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
@@ -451,29 +508,6 @@ int levelMerge(bcd_b200_handle* h, int k)
 		CU(launchMerge(h->levels[k].out.as<float>(), h->levels[k].W, h->levels[k].H, h->levels[k + 1].out.as<float>(),
 				h->tmpLow.as<float>(), h->stream, &h->launches));
 	});
-	return 0;
-}
-
-// level k (>= 1) of the input pyramid from level k-1 (MultiscaleDenoiser.cpp:41-48); parts: 1 = histogram + sample counts
-// (all the selection stage needs), 2 = colour + covariance (needed by the filters only)
-int pyramidLevel(bcd_b200_handle* h, int k, int parts)
-{
-	const LevelBufs& Lp = h->levels[k - 1];
-	LevelBufs& L = h->levels[k];
-	STAGE(h, BCD_B200_STAGE_PYRAMID, {
-		CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(),
-				L.ownNs.as<float>(), L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches, parts));
-	});
-	return 0;
-}
-
-int buildPyramid(bcd_b200_handle* h, int s)
-{
-	for(int k = 1; k < s; ++k)
-	{
-		int rc = pyramidLevel(h, k, 3);
-		if(rc) return rc;
-	}
 	return 0;
 }
 
@@ -858,6 +892,7 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 	CU(cudaMemcpyAsync(L.ownColor.p, in->color, np * 3 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 	CU(cudaEventRecord(up.evAll, up.copy));
 	up.pending = true;
+	up.histOrdered = false;
 	L.color = L.ownColor.as<float>();
 	L.ns = L.ownNs.as<float>();
 	L.hist = L.ownHist.as<float>();
@@ -1071,8 +1106,9 @@ int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	h->runParams = *p;
 	h->ran = false;
 	CU(cudaEventRecord(h->evTotal[0], h->stream));
-	if((rc = finishUpload(h))) return rc;
-	return buildPyramid(h, p->nb_scales);
+	h->pyrHistDone = h->pyrColorDone = 0; // the pyramid is built on demand by tile_select / tile_filter
+	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));
+	return 0;
 }
 
 #define TILE_GUARD(h, level) \
@@ -1084,7 +1120,7 @@ int bcd_b200_tile_select(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); 
 int bcd_b200_tile_mark(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMark(h, level, h->runParams); }
 int bcd_b200_tile_mark_enqueue(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMarkEnqueue(h, level, h->runParams); }
 int bcd_b200_tile_mark_wait(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelMarkWait(h, level); }
-int bcd_b200_tile_filter(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFilter(h, level, h->runParams); }
+int bcd_b200_tile_filter(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFilterTile(h, level, h->runParams); }
 int bcd_b200_tile_finalize(bcd_b200_handle* h, int level) { TILE_GUARD(h, level); return levelFinalize(h, level, h->runParams); }
 int bcd_b200_tile_merge(bcd_b200_handle* h, int level)
 {

@@ -139,12 +139,17 @@ class DistExchange:
                 r.wait()
         return recv
 
+    # The links of the marking chain go through batch_isend_irecv as well: with an eagerly initialised NCCL group
+    # torch treats *unbatched* send/recv as collectives and serialises them with every other op of the group, which
+    # would chain the levels' marking streams together. wait() orders the current stream (NCCL) / blocks (gloo).
     def recv_from_up(self, like):
-        self.dist.recv(like, src=self.rank - 1)
+        for r in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.irecv, like, self.rank - 1)]):
+            r.wait()
         return like
 
     def send_down(self, buf):
-        self.dist.send(buf, dst=self.rank + 1)
+        for r in self.dist.batch_isend_irecv([self.dist.P2POp(self.dist.isend, buf, self.rank + 1)]):
+            r.wait()
 
 
 def level_order(s):
@@ -231,7 +236,7 @@ def run_tiles_loopback(workers):
     assert n == workers[0].tile.tile_count
 
 
-def make_worker(inputs_full, params, index, count, device_index=0, main_stream=None, aux_stream=None):
+def make_worker(inputs_full, params, index, count, device_index=0, main_stream=None, aux_stream=None, streamed=False):
     """Uploads the rows of tile `index` of a full-frame dict(color,nsamples,hist,cov) and returns its TileWorker.
     Workers that exchange strips in one process must share their two streams (explicit torch.cuda.Stream objects)."""
     import torch
@@ -240,7 +245,10 @@ def make_worker(inputs_full, params, index, count, device_index=0, main_stream=N
     sub = {k: np.ascontiguousarray(v[t.sub_row0:t.sub_row1]) for k, v in inputs_full.items()}
     h = capi.Handle(device_index)
     worker = TileWorker(h, params, t, torch.device("cuda", device_index), main_stream, aux_stream)
-    h.upload(**sub)
+    if streamed:
+        h.upload_async(**sub)  # bcd_b200_upload_async: the tile's level-0 selection runs behind the arriving rows
+    else:
+        h.upload(**sub)
     return worker
 
 
@@ -281,7 +289,8 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         run_tile(worker, ex)
 
     def step_e2e():
-        h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd)
+        h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd,
+                      streamed=True)
         run_tile(worker, ex)
         worker.download(out_pin.data_ptr())
 

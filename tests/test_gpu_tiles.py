@@ -18,13 +18,13 @@ def _full(capi, inp, **kw):
     return out, st
 
 
-def _tiled(capi, tiles, inp, count, **kw):
+def _tiled(capi, tiles, inp, count, streamed=False, **kw):
     import torch
     params = capi.make_params(**kw)
     # all tiles exchange strips on shared streams: one main stream, one marking stream per level
     stream, aux = torch.cuda.Stream(), tiles.make_aux_streams(torch.device("cuda", 0), params.nb_scales)
     with torch.cuda.stream(stream):
-        workers = [tiles.make_worker(inp, params, i, count, main_stream=stream, aux_stream=aux) for i in range(count)]
+        workers = [tiles.make_worker(inp, params, i, count, main_stream=stream, aux_stream=aux, streamed=streamed) for i in range(count)]
         tiles.run_tiles_loopback(workers)
         out = np.concatenate([w.download() for w in workers], axis=0)
     st = {}
@@ -49,6 +49,19 @@ def test_tiles_equal_full_frame(count, kw):
     for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full"):
         assert st[k] == st_ref[k], (k, st[k], st_ref[k])
     assert O.rel_linf(out, ref) <= 2e-6  # only the order of the float atomics differs
+
+
+def test_tiles_with_streamed_upload_equal_full_frame():
+    """Row tiles fed by bcd_b200_upload_async: the banded level-0 selection is clipped to the tile's selection rows and
+    the pyramid is built on demand — same counters and image as the full-frame run."""
+    from bcd_b200 import capi, host, tiles
+    inp = host.synth(120, 208, spp=24)
+    kw = dict(m=1.0, scales=3)
+    ref, st_ref = _full(capi, inp, **kw)
+    out, st = _tiled(capi, tiles, inp, 3, streamed=True, **kw)
+    for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full"):
+        assert st[k] == st_ref[k], (k, st[k], st_ref[k])
+    assert O.rel_linf(out, ref) <= 2e-6
 
 
 def test_tiles_match_reference_golden(crop_a):
