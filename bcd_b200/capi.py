@@ -21,7 +21,7 @@ SYMBOLS = [
     "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_set_streams", "bcd_b200_upload",
     "bcd_b200_upload_async",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
-    "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active",
+    "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active", "bcd_b200_debug_read_pair_terms",
     "bcd_b200_spike_removal", "bcd_b200_spike_removal_host", "bcd_b200_download_inputs",
     # row-tile API (multi-GPU), wrapped by bcd_b200/tiles.py
     "bcd_b200_set_level_aux_stream", "bcd_b200_tile_mark_enqueue", "bcd_b200_tile_mark_wait",
@@ -89,6 +89,7 @@ def lib():
         L.bcd_b200_mask_words.argtypes = [C.c_int]
         L.bcd_b200_debug_read_selection.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_debug_read_active.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_debug_read_pair_terms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_spike_removal.argtypes = [C.c_void_p, C.c_float, C.c_int]
         L.bcd_b200_download_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_spike_removal_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -237,3 +238,11 @@ class Handle:
         active = np.zeros((H, W), np.uint8)
         _check(lib().bcd_b200_debug_read_active(self._h, active.ctypes.data))
         return active
+
+    def read_pair_terms(self, b=6):
+        """After a single-scale run: (sums (J,H,W) float32, counts (J,H,W) uint8) of the selection stage."""
+        H, W, _ = self.shape
+        J = ((2 * b + 1) ** 2 + 1) // 2
+        sums, counts = np.empty((J, H, W), np.float32), np.empty((J, H, W), np.uint8)
+        _check(lib().bcd_b200_debug_read_pair_terms(self._h, sums.ctypes.data, counts.ctypes.data))
+        return sums, counts

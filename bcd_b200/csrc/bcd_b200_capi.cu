@@ -1035,6 +1035,18 @@ int bcd_b200_debug_read_selection(bcd_b200_handle* h, uint32_t* masks, int32_t* 
 	return 0;
 }
 
+int bcd_b200_debug_read_pair_terms(bcd_b200_handle* h, float* sums, uint8_t* counts)
+{
+	if(!h || !sums || !counts) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null argument");
+	if(!h->ran || h->runParams.nb_scales != 1 || h->tiled)
+		return fail(BCD_B200_ERR_STATE, "pair terms are only kept after a single-scale whole-frame run");
+	CU(cudaSetDevice(h->device));
+	const size_t n = (size_t)h->g0.J * h->g0.W * h->g0.H;
+	CU(cudaMemcpy(sums, h->sP.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(counts, h->cP.p, n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 int bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active)
 {
 	if(!h || !active) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");

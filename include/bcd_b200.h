@@ -210,6 +210,10 @@ int  bcd_b200_tile_download(bcd_b200_handle* h, float* out_rows /* (own_row1-own
 int  bcd_b200_mask_words(int search_radius);
 int  bcd_b200_debug_read_selection(bcd_b200_handle* h, uint32_t* masks, int32_t* counts);
 int  bcd_b200_debug_read_active(bcd_b200_handle* h, uint8_t* active);
+/* after a single-scale run: the pair terms of the selection stage (DenoisingUnit.cpp:360-386) for every pixel and
+ * every offset delta_j at or after the window centre, planes [J][H][W], J = ((2b+1)^2+1)/2; entries whose partner
+ * pixel lies outside the image are undefined */
+int  bcd_b200_debug_read_pair_terms(bcd_b200_handle* h, float* sums, uint8_t* counts);
 
 #ifdef __cplusplus
 }

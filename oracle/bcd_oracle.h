@@ -25,6 +25,8 @@ void bcdo_pixel_cov(const float* cov, const float* ns, long long npix, float* pi
 float bcdo_pair_term(const float* hx, const float* hy, float nx, float ny, int B, int* cnt);
 float bcdo_patch_distance(const float* hist, const float* ns, int W, int H, int B, int w,
 		int pl, int pc, int ql, int qc);
+/* every pair term of a frame, planes [J][H][W] (see bcd_oracle.c) */
+void bcdo_pair_terms_all(const float* hist, const float* ns, int W, int H, int B, int b, float* sums, unsigned char* counts);
 /* A.4: masks[(l*W+c)*words + k]: bit index = (dy+b)*(2b+1) + (dx+b), words = ceil((2b+1)^2/32); counts[l*W+c] */
 int  bcdo_mask_words(int b);
 void bcdo_select_all(const float* hist, const float* ns, int W, int H, int B, int w, int b, float tau,

@@ -123,6 +123,7 @@ def port_lib():
         lib.bcdo_pixel_cov.argtypes = [_fp, _fp, C.c_longlong, _fp]
         lib.bcdo_select_all.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _u32p, _i32p]
         lib.bcdo_marking.argtypes = [_u32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        lib.bcdo_pair_terms_all.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _u8p]
         lib.bcdo_eigh.restype = C.c_int
         lib.bcdo_eigh.argtypes = [_fp, C.c_int, _fp, _fp, _fp]
         lib.bcdo_denoise.restype = C.c_int
@@ -152,6 +153,16 @@ def port_select(hist, nsamples, w=1, b=6, tau=1.0):
     counts = np.zeros((H, W), np.int32)
     port_lib().bcdo_select_all(_c(hist), _c(nsamples), W, H, B, w, b, tau, masks, counts)
     return masks, counts
+
+
+def port_pair_terms(hist, nsamples, b=6):
+    """-> sums (J,H,W) float32 (NaN where the offset leaves the image), counts (J,H,W) uint8 (255 there)."""
+    H, W, B = hist.shape
+    J = ((2 * b + 1) ** 2 + 1) // 2
+    sums = np.empty((J, H, W), np.float32)
+    counts = np.empty((J, H, W), np.uint8)
+    port_lib().bcdo_pair_terms_all(_c(hist), _c(nsamples), W, H, B, b, sums, counts)
+    return sums, counts
 
 
 def port_marking(masks, counts, w=1, b=6):

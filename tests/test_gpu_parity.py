@@ -48,6 +48,28 @@ def test_selection_bit_exact(capi, crop_a):
     assert st["strong"] == int((ref_counts >= 28).sum())
 
 
+@pytest.mark.parametrize("dense", [False, True])
+def test_pair_terms_bit_exact(capi, crop_a, crop_b, dense, monkeypatch):
+    """K1a alone: every pair term (sum bits and count) of every pixel and offset equals the restated reference term
+    (DenoisingUnit.cpp:360-386) — the selection bits downstream only see these through a threshold, which would hide a
+    last-bit difference such as a contracted multiply-add in the packed-arithmetic path."""
+    monkeypatch.setenv("BCD_B200_DENSE_PAIR", "1" if dense else "0")
+    try:
+        for crop, bsr in ((crop_a, 6), (crop_b, 4)):
+            inp = inputs_of(crop)
+            h, _ = _run(capi, inp, m=0.0, scales=1, b=bsr)
+            sums, counts = h.read_pair_terms(b=bsr)
+            h.close()
+            ref_s, ref_c = O.port_pair_terms(inp["hist"], inp["nsamples"], b=bsr)
+            valid = ref_c != 255
+            assert valid.sum() > 0.9 * valid.size
+            assert np.array_equal(counts[valid], ref_c[valid])
+            assert np.array_equal(sums[valid].view(np.uint32), ref_s[valid].view(np.uint32))
+    finally:
+        monkeypatch.setenv("BCD_B200_DENSE_PAIR", "0")
+        capi.Handle(0).close()  # reset the process-wide hook
+
+
 def test_marking_bit_exact(capi, crop_a):
     h, _ = _run(capi, inputs_of(crop_a), m=1.0)
     active = h.read_active()

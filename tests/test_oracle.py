@@ -102,3 +102,33 @@ def test_spike_removal_restatement_matches_reference_golden():
         r = O.ref_spike_removal(**g, factor=2.0)
         for k in r:
             assert np.array_equal(r[k].view(np.uint32), p[k].view(np.uint32)), k
+
+
+def test_pair_term_planes_reproduce_the_golden_selection(crop_a):
+    """bcdo_pair_terms_all (the layout of the GPU intermediate) is pinned by recomputing the selection from it: the
+    row-major chain sum of the 3x3 pair terms / count <= tau (DenoisingUnit.cpp:336-358) must give the committed masks."""
+    from conftest import inputs_of
+    inp = inputs_of(crop_a)
+    b, w, tau = 6, 1, np.float32(1.0)
+    sums, counts = O.port_pair_terms(inp["hist"], inp["nsamples"], b=b)
+    H, W = counts.shape[1:]
+    side = 2 * b + 1
+    masks = crop_a["port_masks"]
+    checked = 0
+    for j in (0, 1, 7, 13, 40, 84):
+        idx = b * side + b + j
+        dy, dx = idx // side - b, idx % side - b
+        ys = slice(w, H - w - dy)
+        x0, x1 = max(w, w - dx), min(W - w, W - w - dx)
+        acc = np.zeros((H - 2 * w - dy, x1 - x0), np.float32)
+        cnt = np.zeros(acc.shape, np.int32)
+        for oy in range(-w, w + 1):          # same order as the reference's patch iterator: row-major
+            for ox in range(-w, w + 1):
+                acc = acc + sums[j, w + oy:H - w - dy + oy, x0 + ox:x1 + ox]
+                cnt = cnt + counts[j, w + oy:H - w - dy + oy, x0 + ox:x1 + ox]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            sel = (acc / cnt.astype(np.float32)) <= tau
+        got = (masks[ys, x0:x1, idx >> 5] >> np.uint32(idx & 31)) & 1
+        assert np.array_equal(sel, got.astype(bool)), "offset %d" % j
+        checked += sel.size
+    assert checked > 50000
