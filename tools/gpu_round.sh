@@ -9,14 +9,14 @@ timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_m1.json 2> g
 timeout 300 python bench.py --m 0 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_m0.json 2> gpurun_out/bench_m0.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_m1.csv \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_pair_terms -s 2 -c 1 -f -o gpurun_out/prof_pair \
+ncu --set full --clock-control none --import-source on -k regex:k_pair_terms -s 0 -c 1 -f -o gpurun_out/prof_pair \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_pair.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_eig_chain -s 4 -c 1 -f -o gpurun_out/prof_eig \
+ncu --set full --clock-control none --import-source on -k regex:k_eig_chain -s 0 -c 1 -f -o gpurun_out/prof_eig \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_eig.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_patch_select -s 2 -c 1 -f -o gpurun_out/prof_sel \
+ncu --set full --clock-control none --import-source on -k regex:k_patch_select -s 0 -c 1 -f -o gpurun_out/prof_sel \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_sel.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_filter_apply -s 4 -c 1 -f -o gpurun_out/prof_apply \
+ncu --set full --clock-control none --import-source on -k regex:k_filter_apply -s 0 -c 1 -f -o gpurun_out/prof_apply \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_apply.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_marking -s 2 -c 1 -f -o gpurun_out/prof_mark \
+ncu --set full --clock-control none --import-source on -k regex:k_marking -s 0 -c 1 -f -o gpurun_out/prof_mark \
     timeout 200 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_mark.log 2>&1
 ls -la gpurun_out
