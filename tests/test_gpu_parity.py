@@ -55,7 +55,7 @@ def test_pair_terms_bit_exact(capi, crop_a, crop_b, dense, monkeypatch):
     last-bit difference such as a contracted multiply-add in the packed-arithmetic path."""
     monkeypatch.setenv("BCD_B200_DENSE_PAIR", "1" if dense else "0")
     try:
-        for crop, bsr in ((crop_a, 6), (crop_b, 4)):
+        for crop, bsr in ((crop_a, 6), (crop_b, 4), (crop_b, 14)):
             inp = inputs_of(crop)
             h, _ = _run(capi, inp, m=0.0, scales=1, b=bsr)
             sums, counts = h.read_pair_terms(b=bsr)
@@ -158,6 +158,25 @@ def test_dense_pair_kernel_path(capi, crop_a, monkeypatch):
     assert int(np.unpackbits((masks ^ crop_a["port_masks"]).view(np.uint8)).sum()) == 0
 
 
+def test_handle_reuse_across_frame_sizes_and_parameters(capi, crop_a, crop_b, crop_c):
+    """One handle, frames of different sizes / radii / scales back to back (buffers and streams persist and are
+    re-dimensioned): every result still matches its reference golden."""
+    h = capi.Handle(0)
+    try:
+        for crop, key, kw, streamed in ((crop_a, "ref_s3_m1", dict(m=1.0, scales=3), False),
+                                        (crop_b, "ref_s2_m0", dict(m=0.0, scales=2), True),
+                                        (crop_c, "ref_s1_m0_w2b3", dict(m=0.0, w=2, b=5), False),
+                                        (crop_b, "ref_s1_m0_b4", dict(m=0.0, scales=1, b=4), True),
+                                        (crop_a, "ref_s1_m1", dict(m=1.0, scales=1), True)):
+            inp = inputs_of(crop)
+            (h.upload_async if streamed else h.upload)(**inp)
+            h.run(**kw)
+            err = O.rel_linf(h.download(), crop[key])
+            assert err <= TOL, "%s: rel Linf %.3e" % (key, err)
+    finally:
+        h.close()
+
+
 def test_streamed_upload_matches_serial_upload(capi, crop_a):
     """bcd_b200_upload_async: level-0 pair terms launched band by band behind the arriving histogram rows — same
     selection bits and the same output as the serial upload, and within tolerance of the reference golden."""
@@ -197,7 +216,7 @@ def test_eig_chain_layouts_agree_with_reference(capi, crop_a, crop_b, group, mon
         capi.Handle(0).close()  # reset the process-wide hook to the default
 
 
-@pytest.mark.parametrize("b", [10, 3])
+@pytest.mark.parametrize("b", [10, 3, 14])
 def test_other_search_radii_bit_exact(capi, crop_b, b):
     inp = inputs_of(crop_b)
     h, out = _run(capi, inp, m=1.0, b=b)
