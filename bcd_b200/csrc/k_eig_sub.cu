@@ -9,6 +9,11 @@
 // and each lane rotates ceil(n/G) rows. Matrices in one warp run in lock-step: loops with data-dependent trip counts
 // (QR sweeps, deflation) iterate to the warp maximum with per-matrix predicates, so every __syncwarp() is reached by
 // all lanes.
+//
+// Shared memory holds ONE n x n buffer per matrix (3.9 KB at d = 27): V f(L) V^T is written straight to global memory
+// (the chain's own scratch, L2-resident) and read back with the noise blocks added; the Cholesky factor, the inverse
+// of the factor (strict upper triangle) and the factorised input share that buffer, and A^-1 goes straight to the
+// output. A matrix whose Cholesky path is rejected is re-read from global memory for the eigen path (rare).
 
 #include "common.cuh"
 #include "kernels.h"
@@ -95,16 +100,15 @@ __device__ __forceinline__ void makeGivens(float p, float q, float& c, float& s)
 
 struct SubSmem
 {
-	float *M, *O, *diag, *sub, *dW, *sW, *hco, *pv;
+	float *M, *diag, *sub, *dW, *sW, *hco, *pv, *rowAbs;
 };
 
 #define MAT(r, c) M[(r) + (c) * n]
-#define OUT(r, c) O[(r) + (c) * n]
 
-// O <- V f(L) V^T of the matrix whose lower triangle is in M (mode 0: f = max(0, l); mode 1: f = 1/max(eps, l)).
-// `commit` (per matrix): when false the matrix only keeps the warp in step and O is left untouched.
+// outG (global, n x n) <- V f(L) V^T of the matrix whose lower triangle is in M (mode 0: f = max(0, l); mode 1:
+// f = 1/max(eps, l)). `commit` (per matrix): when false the matrix only keeps the warp in step and nothing is written.
 template <int G>
-__device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, bool commit)
+__device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, bool commit, float* __restrict__ outG)
 {
 	constexpr int RMAX = (32 + G - 1) / G;
 	float* M = S.M;
@@ -354,27 +358,26 @@ __device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, boo
 			float a = 0.f;
 			for(int k = 0; k < n; ++k)
 				a += MAT(r, k) * (S.pv[k] * MAT(c, k));
-			S.O[r + c * n] = a;
-			S.O[c + r * n] = a;
+			outG[r + c * n] = a;
+			outG[c + r * n] = a;
 		}
 	__syncwarp();
 }
 
-// Cholesky fast path of the clamped inverse (see choleskyInverse in k_filter.cu). Returns true per matrix on success;
-// never breaks out early, so all matrices of the warp stay in step (a failed factorisation just computes garbage).
+// Cholesky fast path of the clamped inverse (see choleskyInverse in k_filter.cu), in place: L overwrites the lower
+// triangle of M, X = L^-1 goes to the strict upper triangle (X(i,j), i > j, at M(j,i); X(j,j) in pv[j]) and
+// A^-1 = X^T X is written to outG. Returns true per matrix when the factorisation exists and 1/||A^-1||_inf > 2 eps;
+// never breaks out early, so all matrices of the warp stay in step (a failed factorisation just computes garbage that
+// the caller replaces).
 template <int G>
-__device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps)
+__device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps, float* __restrict__ outG, bool valid)
 {
 	float* M = S.M;
-	float* O = S.O;
 	const int lid = threadIdx.x & (G - 1);
-	for(int e = lid; e < n * n; e += G)
-		O[e] = (e % n >= e / n) ? M[e] : 0.f;
-	__syncwarp();
 	bool ok = true;
 	for(int k = 0; k < n; ++k)
 	{
-		const float piv = OUT(k, k);
+		const float piv = MAT(k, k);
 		if(!(piv > 0.f) || !(piv < 3e38f)) ok = false;
 		const float pv = ok ? piv : 1.f;
 		float inv;
@@ -382,32 +385,35 @@ __device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps)
 		const float lkkInv = inv * fmaf(-0.5f * pv, inv * inv, 1.5f);
 		__syncwarp();
 		for(int r = k + lid; r < n; r += G)
-			OUT(r, k) = r == k ? pv * lkkInv : OUT(r, k) * lkkInv;
+			MAT(r, k) = r == k ? pv * lkkInv : MAT(r, k) * lkkInv;
 		__syncwarp();
 		for(int c = k + 1 + lid; c < n; c += G)
 		{
-			const float lck = OUT(c, k);
+			const float lck = MAT(c, k);
 			for(int r = c; r < n; ++r)
-				OUT(r, c) = fmaf(-OUT(r, k), lck, OUT(r, c));
+				MAT(r, c) = fmaf(-MAT(r, k), lck, MAT(r, c));
 		}
 		__syncwarp();
 	}
-	// X = L^-1 by forward substitution, one column per lane; X(i,j) (i > j) stored at M(j,i), X(j,j) in pv[j]
 	for(int j = lid; j < n; j += G)
-		S.pv[j] = __fdiv_rn(1.f, OUT(j, j));
+	{
+		S.pv[j] = __fdiv_rn(1.f, MAT(j, j));
+		S.rowAbs[j] = 0.f;
+	}
 	__syncwarp();
-	for(int j = lid; j < n; j += G)
+	for(int j = lid; j < n; j += G) // forward substitution, one column of X per lane
 	{
 		const float xjj = S.pv[j];
 		for(int i = j + 1; i < n; ++i)
 		{
-			float a = OUT(i, j) * xjj;
+			float a = MAT(i, j) * xjj;
 			for(int k = j + 1; k < i; ++k)
-				a = fmaf(OUT(i, k), MAT(j, k), a);
+				a = fmaf(MAT(i, k), MAT(j, k), a);
 			MAT(j, i) = -a * S.pv[i];
 		}
 	}
 	__syncwarp();
+	// A^-1(r,c) = sum_{k >= r} X(k,r) X(k,c)   (r >= c); the row sums of |A^-1| give its infinity norm
 	const int L = n * (n + 1) / 2;
 	for(int e = lid; e < L; e += G)
 	{
@@ -417,78 +423,81 @@ __device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps)
 		float a = S.pv[r] * (r == c ? S.pv[r] : MAT(c, r));
 		for(int k = r + 1; k < n; ++k)
 			a = fmaf(MAT(r, k), MAT(c, k), a);
-		OUT(r, c) = a;
-	}
-	__syncwarp();
-	for(int e = lid; e < n * n; e += G)
-	{
-		const int r = e % n, c = e / n;
-		if(r < c) O[e] = OUT(c, r);
+		if(valid)
+		{
+			outG[r + c * n] = a;
+			outG[c + r * n] = a;
+		}
+		atomicAdd(&S.rowAbs[r], fabsf(a));
+		if(r != c) atomicAdd(&S.rowAbs[c], fabsf(a));
 	}
 	__syncwarp();
 	float rowMax = 0.f;
 	for(int r = lid; r < n; r += G)
-	{
-		float a = 0.f;
-		for(int c = 0; c < n; ++c)
-			a += fabsf(OUT(r, c));
-		rowMax = fmaxf(rowMax, a);
-	}
+		rowMax = fmaxf(rowMax, S.rowAbs[r]);
 	const float norm = subMax<G>(rowMax);
 	return ok && norm < 0.5f / eps && norm == norm;
 }
 #undef MAT
-#undef OUT
 
+// A (in): the matrices; in a clamp launch A[slot] is overwritten with V max(0,L) V^T (its consumer, the apply kernel,
+// rewrites A anyway). MinvG (out): the clamped inverses.
 template <int G>
-__global__ void __launch_bounds__(32)
-k_eig_chain_sub(const float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
+__global__ void __launch_bounds__(32, G == 16 ? 24 : 14)
+k_eig_chain_sub(float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
 		int n, int np, float eps, int doClamp)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	constexpr int NM = 32 / G; // matrices per warp
 	const int sub = threadIdx.x / G, lid = threadIdx.x & (G - 1);
-	const int perMat = 2 * n * n + 6 * n + np * 6;
+	const int perMat = n * n + 7 * n + np * 6;
 	float* f = reinterpret_cast<float*>(smemRaw) + (size_t)sub * perMat;
 	SubSmem S;
 	S.M = f; f += n * n;
-	S.O = f; f += n * n;
 	S.diag = f; f += n;
 	S.sub = f; f += n;
 	S.dW = f; f += n;
 	S.sW = f; f += n;
 	S.hco = f; f += n;
 	S.pv = f; f += n;
+	S.rowAbs = f; f += n;
 	float* noise = f;
 	for(int base = blockIdx.x * NM; base < count; base += gridDim.x * NM)
 	{
 		const int slot = base + sub;
 		const bool valid = slot < count;
+		float* Aslot = A + (size_t)(valid ? slot : 0) * n * n;
+		float* outSlot = MinvG + (size_t)(valid ? slot : 0) * n * n;
 		__syncwarp();
 		for(int e = lid; e < n * n; e += G)
-			S.M[e] = valid ? A[(size_t)slot * n * n + e] : ((e % n == e / n) ? 1.f : 0.f); // identity keeps idle lanes harmless
+			S.M[e] = valid ? Aslot[e] : ((e % n == e / n) ? 1.f : 0.f); // identity keeps idle lanes harmless
 		for(int e = lid; e < np * 6; e += G)
 			noise[e] = valid ? noiseG[(size_t)slot * np * 6 + e] : 0.f;
 		__syncwarp();
-		if(doClamp)
+		// M <- (global matrix) + Sigma_n on the 3x3 diagonal blocks (DenoisingUnit.cpp:538-556)
+		auto reloadWithNoise = [&](bool addNoise)
 		{
-			eigFunctionSub<G>(S, n, 0, 0.f, true);
-			for(int e = lid; e < n * n; e += G) // M <- O + Sigma_n on the 3x3 diagonal blocks (:538-556)
+			for(int e = lid; e < n * n; e += G)
 			{
 				const int r = e % n, c = e / n;
-				float v = S.O[e];
-				if(r / 3 == c / 3)
+				float v = valid ? Aslot[e] : (r == c ? 1.f : 0.f);
+				if(addNoise && r / 3 == c / 3)
 					v = __fadd_rn(v, noise[(r / 3) * 6 + symIndex(r % 3, c % 3)]);
 				S.M[e] = v;
 			}
 			__syncwarp();
+		};
+		if(doClamp)
+		{
+			eigFunctionSub<G>(S, n, 0, 0.f, valid, Aslot); // A[slot] <- V max(0,L) V^T
+			reloadWithNoise(true);
 		}
-		const bool okChol = choleskyInverseSub<G>(S, n, eps);
-		if(!__all_sync(FULL, okChol))
-			eigFunctionSub<G>(S, n, 1, eps, !okChol); // rare: only the failed matrices commit their result
-		if(valid)
-			for(int e = lid; e < n * n; e += G)
-				MinvG[(size_t)slot * n * n + e] = S.O[e];
+		const bool okChol = choleskyInverseSub<G>(S, n, eps, outSlot, valid);
+		if(!__all_sync(FULL, okChol)) // rare: the failed matrices of the warp take the reference's eigen path
+		{
+			reloadWithNoise(doClamp != 0);
+			eigFunctionSub<G>(S, n, 1, eps, valid && !okChol, outSlot);
+		}
 	}
 }
 
@@ -496,11 +505,11 @@ k_eig_chain_sub(const float* __restrict__ A, float* __restrict__ MinvG, const fl
 
 int g_eigGroup = 16; // lanes per matrix for d <= 32 (BCD_B200_EIG_GROUP = 32 selects the one-warp-per-matrix kernel)
 
-cudaError_t launchEigChainSub(const float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
+cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
 		int group, cudaStream_t st)
 {
 	const int nm = 32 / group;
-	const size_t smem = (size_t)nm * (2 * n * n + 6 * n + np * 6) * 4;
+	const size_t smem = (size_t)nm * (n * n + 7 * n + np * 6) * 4;
 	const int grid = (count + nm - 1) / nm;
 	cudaError_t err;
 	if(group == 16)

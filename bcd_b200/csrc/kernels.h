@@ -28,7 +28,7 @@ extern bool g_forceGenericMarking;
 // K3e for d <= 32: lanes per matrix (16 or 8: several matrices per warp, k_eig_sub.cu; 32: one warp per matrix). Test hook
 // BCD_B200_EIG_GROUP.
 extern int g_eigGroup;
-cudaError_t launchEigChainSub(const float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
+cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
 		int group, cudaStream_t st);
 bool markingUsesFastLayout(int b); // k_symmetrize must then write the `pre2` layout
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
