@@ -19,7 +19,7 @@ STAGE_NAMES = ["prepass", "pair", "select", "marking", "fallback", "filter_stats
 SYMBOLS = [
     "bcd_b200_default_params", "bcd_b200_last_error", "bcd_b200_abi_version", "bcd_b200_device_count",
     "bcd_b200_denoise", "bcd_b200_create", "bcd_b200_destroy", "bcd_b200_set_stream", "bcd_b200_set_streams", "bcd_b200_upload",
-    "bcd_b200_upload_async",
+    "bcd_b200_upload_async", "bcd_b200_host_register", "bcd_b200_host_unregister",
     "bcd_b200_bind_device", "bcd_b200_run", "bcd_b200_download", "bcd_b200_result_device_ptr", "bcd_b200_get_stats",
     "bcd_b200_get_timings", "bcd_b200_mask_words", "bcd_b200_debug_read_selection", "bcd_b200_debug_read_active", "bcd_b200_debug_read_pair_terms",
     "bcd_b200_spike_removal", "bcd_b200_spike_removal_host", "bcd_b200_download_inputs",
@@ -80,6 +80,8 @@ def lib():
         L.bcd_b200_set_streams.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_upload.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_upload_async.argtypes = [C.c_void_p, C.POINTER(Images)]
+        L.bcd_b200_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.bcd_b200_host_unregister.argtypes = [C.c_void_p]
         L.bcd_b200_bind_device.argtypes = [C.c_void_p, C.POINTER(Images)]
         L.bcd_b200_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
         L.bcd_b200_download.argtypes = [C.c_void_p, C.c_void_p]

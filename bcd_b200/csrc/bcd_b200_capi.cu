@@ -805,6 +805,23 @@ int bcd_b200_set_streams(bcd_b200_handle* h, void* main_stream, void* aux_stream
 	return 0;
 }
 
+int bcd_b200_host_register(const void* ptr, size_t bytes)
+{
+	if(!ptr || !bytes) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null / empty host range");
+	cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+	if(e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(BCD_B200_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+	return 0;
+}
+
+int bcd_b200_host_unregister(const void* ptr)
+{
+	if(!ptr) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null host pointer");
+	cudaError_t e = cudaHostUnregister(const_cast<void*>(ptr));
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(BCD_B200_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e)); }
+	return 0;
+}
+
 int bcd_b200_set_level_aux_stream(bcd_b200_handle* h, int level, void* aux_stream)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");

@@ -119,6 +119,11 @@ int  bcd_b200_upload(bcd_b200_handle* h, const bcd_b200_images* in);
  * valid and unmodified until that run (or any other call that consumes the inputs) has returned; use pinned memory for a
  * truly asynchronous copy. bcd_b200_denoise uses this path. */
 int  bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in);
+/* page-lock / release a host range the caller owns (thin wrappers over cudaHostRegister / cudaHostUnregister for hosts
+ * that do not link the CUDA runtime themselves): registering the image buffers a renderer reuses frame after frame
+ * once is what makes the streamed upload asynchronous. Registering an already registered range is not an error. */
+int  bcd_b200_host_register(const void* ptr, size_t bytes);
+int  bcd_b200_host_unregister(const void* ptr);
 /* same, but the pointers in `in` are DEVICE pointers that the handle borrows until the next upload/bind/destroy */
 int  bcd_b200_bind_device(bcd_b200_handle* h, const bcd_b200_images* in);
 /* whole hot path on the resident inputs; synchronous with respect to the host on return */

@@ -177,6 +177,27 @@ def test_handle_reuse_across_frame_sizes_and_parameters(capi, crop_a, crop_b, cr
         h.close()
 
 
+def test_host_register_makes_caller_buffers_streamable(capi, crop_a):
+    """bcd_b200_host_register / _unregister: page-lock the caller's own arrays, stream them, release them."""
+    import ctypes as C
+    inp = {k: np.ascontiguousarray(v) for k, v in inputs_of(crop_a).items()}
+    L = capi.lib()
+    for v in inp.values():
+        assert L.bcd_b200_host_register(C.c_void_p(v.ctypes.data), v.nbytes) == 0
+        assert L.bcd_b200_host_register(C.c_void_p(v.ctypes.data), v.nbytes) == 0  # idempotent
+    try:
+        h = capi.Handle(0)
+        h.upload_async(**inp)
+        h.run(m=1.0, scales=1)
+        out = h.download()
+        h.close()
+    finally:
+        for v in inp.values():
+            assert L.bcd_b200_host_unregister(C.c_void_p(v.ctypes.data)) == 0
+    assert O.rel_linf(out, crop_a["ref_s1_m1"]) <= TOL
+    assert L.bcd_b200_host_register(None, 16) != 0
+
+
 def test_streamed_upload_matches_serial_upload(capi, crop_a):
     """bcd_b200_upload_async: level-0 pair terms launched band by band behind the arriving histogram rows — same
     selection bits and the same output as the serial upload, and within tolerance of the reference golden."""
