@@ -253,7 +253,10 @@ __device__ __forceinline__ FilterSmem carveFilterSmem(unsigned char* raw, const 
 // mean over i (sequential, :500-509), centring in place (:511-520) and the lower triangle of the empirical
 // covariance (:522-536; products summed in patch order, then scaled by 1/(n-1)). sgn*Sigma_n is added on the
 // 3x3 diagonal blocks (:538-576) and the symmetric result is written to Aout (column-major d x d).
-template <int NT>
+// DT = compile-time d (27) selects the register-tiled covariance: thread (group, tile) accumulates one 3 x 3 tile of
+// the lower triangle (45 tiles for d = 27) over its share of the patches — 6 shared loads feed 9 FMAs instead of 2 per
+// FMA — and the NT/45 groups are reduced through the (then dead) patch matrix X. DT = 0: one element per thread.
+template <int NT, int DT>
 __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, const float* noise, float sgn,
 		float* __restrict__ Aout, float* __restrict__ meanOut)
 {
@@ -280,6 +283,58 @@ __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, 
 	}
 	__syncthreads();
 	const float invn1 = __fdiv_rn(1.f, (float)(n - 1));
+	if constexpr(DT > 0)
+	{
+		constexpr int T = DT / 3, LT = T * (T + 1) / 2, NGC = NT / LT;
+		static_assert(DT % 3 == 0 && NGC >= 1 && (NGC - 1) * LT * 9 <= 28 * DT, "tile partials must fit the first 28 rows of X");
+		const int grp = tid / LT, tile = tid - grp * LT;
+		int C = 0, R = tile;
+		while(R >= T - C) { R -= T - C; ++C; }
+		R += C; // R >= C
+		float acc[9];
+#pragma unroll
+		for(int k = 0; k < 9; ++k) acc[k] = 0.f;
+		if(grp < NGC)
+		{
+			const int i0 = (n * grp) / NGC, i1 = (n * (grp + 1)) / NGC;
+			const float* xr = X + (size_t)i0 * DT + 3 * R;
+			const float* xc = X + (size_t)i0 * DT + 3 * C;
+			for(int i = i0; i < i1; ++i, xr += DT, xc += DT)
+			{
+				const float r0 = xr[0], r1 = xr[1], r2 = xr[2], c0 = xc[0], c1 = xc[1], c2 = xc[2];
+				acc[0] = fmaf(r0, c0, acc[0]); acc[1] = fmaf(r0, c1, acc[1]); acc[2] = fmaf(r0, c2, acc[2]);
+				acc[3] = fmaf(r1, c0, acc[3]); acc[4] = fmaf(r1, c1, acc[4]); acc[5] = fmaf(r1, c2, acc[5]);
+				acc[6] = fmaf(r2, c0, acc[6]); acc[7] = fmaf(r2, c1, acc[7]); acc[8] = fmaf(r2, c2, acc[8]);
+			}
+		}
+		if(NGC > 1)
+		{
+			__syncthreads(); // every thread is done reading X: its first rows become the reduction scratch
+			if(grp >= 1 && grp < NGC)
+#pragma unroll
+				for(int k = 0; k < 9; ++k) X[((grp - 1) * LT + tile) * 9 + k] = acc[k];
+			__syncthreads();
+		}
+		if(grp == 0)
+		{
+			for(int g2 = 1; g2 < NGC; ++g2)
+#pragma unroll
+				for(int k = 0; k < 9; ++k) acc[k] = __fadd_rn(acc[k], X[((g2 - 1) * LT + tile) * 9 + k]);
+#pragma unroll
+			for(int a = 0; a < 3; ++a)
+#pragma unroll
+				for(int b3 = 0; b3 < 3; ++b3)
+				{
+					const int r = 3 * R + a, c = 3 * C + b3;
+					float v = __fmul_rn(acc[a * 3 + b3], invn1);
+					if(R == C)
+						v = __fadd_rn(v, __fmul_rn(sgn, noise[R * 6 + symIndex(a, b3)]));
+					Aout[r + (size_t)c * DT] = v;
+					Aout[c + (size_t)r * DT] = v;
+				}
+		}
+		return;
+	}
 	const int L = d * (d + 1) / 2;
 	for(int e = tid; e < L; e += NT)
 	{
@@ -300,7 +355,7 @@ __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, 
 // ---------------------------------------------------------------------------------------------------------------
 // K3a: stats
 // ---------------------------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, int DT>
 __global__ void __launch_bounds__(NT)
 k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov, const uint32_t* __restrict__ smask,
 		LevelGeom g, const int* __restrict__ list, int first, int count,
@@ -329,7 +384,7 @@ k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov
 			noiseG[(size_t)slot * np * 6 + e] = a;
 		}
 		__syncthreads();
-		meanCenterCov<NT>(s.X, n, g, s.mean, s.noise, -1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
+		meanCenterCov<NT, DT>(s.X, n, g, s.mean, s.noise, -1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
 		__syncthreads();
 	}
 }
@@ -338,7 +393,9 @@ k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov
 // K3b / K3c: apply.  STEP 1: Y in place, then mu2 and A = cov(Y) + Sigma_n.  STEP 2: Z scattered to the accumulator.
 // Groups of GS threads handle one similar patch at a time: t = -(Minv (X_i - mean)); out = Sigma_n t + X_i.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NT, int GS, int STEP>
+// DT = compile-time d (27): lane r of a group keeps row r of Minv in registers for the whole pixel (the products
+// then need one broadcast LDS.128 of the 4 centred patches per 4 FMAs and no Minv traffic); DT = 0: Minv in shared memory.
+template <int NT, int GS, int STEP, int DT>
 __global__ void __launch_bounds__(NT)
 k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ smask, LevelGeom g,
 		const int* __restrict__ list, int first, int count,
@@ -360,8 +417,17 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 		const int py = p / g.W, px = p - py * g.W;
 		const int n = expandSimilarList<NT>(smask + (size_t)p * g.Nw, g, px, py, s.words, s.prefix, s.qbase);
 		gatherPatches<NT>(color, g, s.qbase, n, s.X);
-		for(int e = tid; e < d * d; e += NT)
-			s.Minv[e] = MinvG[(size_t)slot * d * d + e];
+		float mrow[DT > 0 ? DT : 1];
+		if(DT > 0)
+		{
+			// Minv is symmetric: row r = column r, contiguous in the column-major matrix
+			const float* src = MinvG + (size_t)slot * DT * DT + (size_t)(gl < DT ? gl : 0) * DT;
+#pragma unroll
+			for(int c = 0; c < DT; ++c) mrow[c] = __ldg(src + c);
+		}
+		else
+			for(int e = tid; e < d * d; e += NT)
+				s.Minv[e] = MinvG[(size_t)slot * d * d + e];
 		for(int e = tid; e < d; e += NT)
 			s.mean[e] = meanG[(size_t)slot * d + e];
 		for(int e = tid; e < np * 6; e += NT)
@@ -381,17 +447,33 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 				xcv4[c] = make_float4(__fsub_rn(X0[c], m), __fsub_rn(X1[c], m), __fsub_rn(X2[c], m), __fsub_rn(X3[c], m));
 			}
 			__syncthreads();
-			for(int r = gl; r < d; r += GS)
+			if(DT > 0)
 			{
-				float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-				for(int c = 0; c < d; ++c)
+				if(gl < DT)
 				{
-					const float m = s.Minv[r + c * d];
-					const float4 v = xcv4[c];
-					a0 = fmaf(m, v.x, a0); a1 = fmaf(m, v.y, a1); a2 = fmaf(m, v.z, a2); a3 = fmaf(m, v.w, a3);
+					float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+					for(int c = 0; c < DT; ++c)
+					{
+						const float m = mrow[c];
+						const float4 v = xcv4[c];
+						a0 = fmaf(m, v.x, a0); a1 = fmaf(m, v.y, a1); a2 = fmaf(m, v.z, a2); a3 = fmaf(m, v.w, a3);
+					}
+					tv4[gl] = make_float4(-a0, -a1, -a2, -a3);
 				}
-				tv4[r] = make_float4(-a0, -a1, -a2, -a3);
 			}
+			else
+				for(int r = gl; r < d; r += GS)
+				{
+					float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+					for(int c = 0; c < d; ++c)
+					{
+						const float m = s.Minv[r + c * d];
+						const float4 v = xcv4[c];
+						a0 = fmaf(m, v.x, a0); a1 = fmaf(m, v.y, a1); a2 = fmaf(m, v.z, a2); a3 = fmaf(m, v.w, a3);
+					}
+					tv4[r] = make_float4(-a0, -a1, -a2, -a3);
+				}
 			__syncthreads();
 			for(int jj = gl; jj < d; jj += GS)
 			{
@@ -440,7 +522,7 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 		__syncthreads();
 		if(STEP == 1)
 		{
-			meanCenterCov<NT>(s.X, n, g, s.mean, s.noise, 1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
+			meanCenterCov<NT, DT>(s.X, n, g, s.mean, s.noise, 1.f, A + (size_t)slot * d * d, meanG + (size_t)slot * d);
 			__syncthreads();
 		}
 	}
@@ -884,7 +966,7 @@ k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float*
 // ---------------------------------------------------------------------------------------------------------------
 // launcher of the chain for one chunk of the full list
 // ---------------------------------------------------------------------------------------------------------------
-template <int NT, int GS>
+template <int NT, int GS, int DT>
 static cudaError_t runFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const LevelGeom& g,
 		float minEig, const int* fullList, int first, int count, const FilterBuffers& fb, float4* acc,
 		cudaStream_t st, int* launches, float* stageMs, cudaEvent_t* ev, int eigNT)
@@ -899,9 +981,9 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 	const size_t smApply = filterSmemBytes(g, xInSmem, true, NT / GS);
 	const size_t smEig = ((size_t)2 * g.d * g.d + 6 * g.d + 32 + g.np * 6) * 4;
 	cudaError_t err;
-	auto kStats = k_filter_stats<NT>;
-	auto kA1 = k_filter_apply<NT, GS, 1>;
-	auto kA2 = k_filter_apply<NT, GS, 2>;
+	auto kStats = k_filter_stats<NT, DT>;
+	auto kA1 = k_filter_apply<NT, GS, 1, DT>;
+	auto kA2 = k_filter_apply<NT, GS, 2, DT>;
 	if((err = cudaFuncSetAttribute(kStats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smStats)) != cudaSuccess) return err;
 	if((err = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
 	if((err = cudaFuncSetAttribute(kA2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
@@ -966,12 +1048,14 @@ cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uin
 	(void)counts;
 	if(count <= 0)
 		return cudaSuccess;
+	if(g.d == 27) // the default patch radius: compile-time d
+		return runFilterChunk<128, 32, 27>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
 	if(g.d <= 32)
-		return runFilterChunk<128, 32>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
+		return runFilterChunk<128, 32, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
 	if(g.d <= 96)
-		return runFilterChunk<192, 96>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 96);
+		return runFilterChunk<192, 96, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 96);
 	if(g.d <= 160)
-		return runFilterChunk<160, 160>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 160);
+		return runFilterChunk<160, 160, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 160);
 	return cudaErrorInvalidValue;
 }
 
