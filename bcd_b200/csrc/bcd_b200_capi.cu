@@ -393,7 +393,8 @@ int levelMarkEnqueue(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
 			CU(launchMarking(L.pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, L.active.as<uint32_t>(),
-					L.asBits.as<uint32_t>(), Wp, L.progress.as<unsigned int>(), st, &h->launches));
+					L.asBits.as<uint32_t>(), Wp, L.progress.as<unsigned int>(), st, &h->launches,
+					&L.ctr.as<DeviceCounters>()->markTimeouts));
 		else
 			CU(launchAllActive(g, L.active.as<uint32_t>(), Wp, st, &h->launches));
 		CU(launchBuildLists(L.counts.as<int>(), L.active.as<uint32_t>(), Wp, g, L.fullList.as<int>(),
@@ -411,6 +412,8 @@ int levelMarkWait(bcd_b200_handle* h, int k)
 	CU(cudaEventSynchronize(L.evMark));
 	const DeviceCounters c = *L.hostCtr;
 	L.counters = c;
+	if(c.markTimeouts)
+		return fail(BCD_B200_ERR_CUDA, "marking kernel: %u bounded waits expired at level %d (hand-off between row bands lost)", c.markTimeouts, k);
 	h->stats.interior += (int64_t)c.interior;
 	h->stats.strong += (int64_t)c.strong;
 	h->stats.active += (int64_t)c.active;
@@ -582,7 +585,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 		CU(L.counts.reserve(np * 4));
 		CU(L.active.reserve(rowWords * 4));
 		CU(L.asBits.reserve(rowWords * 4));
-		CU(L.progress.reserve((size_t)(divUp(std::max(L.H, 1), 32) + 2) * 4));
+		CU(L.progress.reserve(markingScratchWords(L.W, L.H) * 4));
 		CU(L.fullList.reserve(np * 4));
 		CU(L.fallbackList.reserve(np * 4));
 		CU(L.acc.reserve(np * sizeof(float4)));
@@ -727,6 +730,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		g_forceDensePair = e && e[0] == '1';
 		e = getenv("BCD_B200_GENERIC_MARKING");
 		g_forceGenericMarking = e && e[0] == '1';
+		e = getenv("BCD_B200_MARKING");
+		g_markingKernel = (e && !strcmp(e, "v4")) ? 0 : 1;
 		e = getenv("BCD_B200_EIG_GROUP");
 		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
 			g_eigGroup = atoi(e);

@@ -68,6 +68,14 @@ __host__ __device__ inline int fastMarkWords(int b)
 	const int fw = 2 * b + 4, fpw = fw <= 16 ? 2 : 1, nf = (b + fpw - 1) / fpw;
 	return (nf + 1 + 3) & ~3;
 }
+// scratch of the marking stage (uint32 words): progress counters of the shared-memory wavefront kernel, or the time-out
+// counter + the band hand-off ring [bands][6 rows][ringPitch blocks of 4 columns] of the systolic kernel
+__host__ __device__ inline int markingRingPitch(int W) { return ((W + 3) / 4 + 7) & ~3; }
+inline size_t markingScratchWords(int W, int H)
+{
+	const size_t bands = (size_t)((H > 0 ? H : 1) + 31) / 32 + 2;
+	return 4 + bands * 6 * (size_t)markingRingPitch(W) + bands;
+}
 // `pre` rows are pitched to a multiple of 4 pixels so that 4-pixel groups are 16-byte aligned (cp.async 16)
 __host__ __device__ inline int prePitchOf(int W) { return (W + 3) & ~3; }
 __device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)

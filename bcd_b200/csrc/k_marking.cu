@@ -402,6 +402,235 @@ k_marking_fast(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, flo
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Systolic kernel (b = 6): the same wavefront (lane l = row r0 + l, 4 pixels per step, lane l at block t - 3 l), but the
+// AS bits never go through shared memory. The 16-column windows of the six rows above travel DOWN the warp as a
+// three-word packet, one shuffle per word and step:
+//     P_l(t)   = fields of rows l-1 .. l-6 at columns [C-6, C+9],  C = 4 (t - 3 l)          (what lane l consumes at step t)
+//     P_l+1(t+1) = { own row at [C-14, C+1] (bits 14..29 of the lane's 32-column history), rows l-1 .. l-5 of P_l(t-2) }
+// so a step costs 3 SHFL + 3 PRMT instead of 12 LDS + 6 SHF + 3 PRMT + STS + a warp barrier, and the compute warp does
+// nothing else: a second warp streams the per-pixel input (`pre2`, cp.async into a double-buffered tile, one named
+// barrier per 8 steps), a third one feeds lane 0 — from the AS bit-rows above the launch range (band 0: zeros, or the
+// upper row tile's hand-off) or from the previous band's hand-off ring. Bands (one CTA each, all co-resident) are
+// chained through that ring in global memory: the last six lanes of a band publish the four AS bits of every block
+// they finish as ONE 32-bit word carrying its own valid flag (bit 31), so no fence and no progress counter is needed;
+// the next band's feeder polls the words it needs (volatile loads) eight steps at a time.
+// Every wait is bounded: a feeder that times out raises `dead` and the band finishes with whatever it has (the parity
+// tests then fail; the GPU does not hang).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SYS_CHS = 8;                          // steps per tile chunk (32 pixels per row)
+constexpr int SYS_RS = SYS_CHS * 4 * 4 + 4;         // tile row stride in words (== 4 mod 32: LDS.128 conflict-free)
+constexpr int SYS_PR = 64;                          // packet ring entries (steps)
+constexpr int SYS_SPIN_LIMIT = 1 << 22;
+
+__device__ __forceinline__ void namedBarrier64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ldVolatileGlobal(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stVolatileGlobal(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+template <bool ALWAYS>
+__global__ void __launch_bounds__(96)
+k_marking_sys6(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
+		uint32_t* __restrict__ actBits, uint32_t* asBits, int Wp, uint32_t* ring, int ringPitch,
+		unsigned int* timeouts)
+{
+	constexpr int b = 6, PX = 4, SKS = 3, SKC = PX * SKS, PW2 = 4;
+	extern __shared__ __align__(16) uint32_t smem[];
+	uint32_t* tileS = smem;                                              // [2][32][SYS_RS]
+	uint4* pktS = reinterpret_cast<uint4*>(smem + 2 * 32 * SYS_RS);      // [SYS_PR]
+	volatile int* flags = reinterpret_cast<volatile int*>(pktS + SYS_PR); // [0] packets ready, [1] steps consumed, [2] dead
+	const int W = g.W, H = g.H, w = g.w;
+	const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+	const int band = blockIdx.x;
+	const int r0 = g.rowBeg + band * 32;
+	const int lastLane = min(31, g.rowEnd - 1 - r0);
+	const int nBlocks = (W + PX - 1) / PX;
+	const int tEnd = nBlocks + SKS * 31;
+	const int nChunks = (tEnd + SYS_CHS - 1) / SYS_CHS;
+	if(threadIdx.x < 3)
+		flags[threadIdx.x] = 0;
+	__syncthreads();
+
+	if(role == 1)
+	{
+		// ---- tile feeder: chunk q of row l covers pixels [32 q - 12 l, +32); one 16-byte unit (= one pixel) per lane
+		for(int q = 0; q < nChunks; ++q)
+		{
+			uint32_t* stage = tileS + (size_t)(q & 1) * 32 * SYS_RS;
+			for(int l = 0; l < 32; ++l)
+			{
+				const int rr = r0 + l;
+				const int px = SYS_CHS * PX * q - SKC * l + lane;
+				const bool inside = rr < g.rowEnd && px >= 0 && px < prePitch;
+				const uint32_t* src = inside ? pre2 + ((size_t)rr * prePitch + px) * PW2 : pre2;
+				__pipeline_memcpy_async(stage + (size_t)l * SYS_RS + lane * PW2, src, 16, inside ? 0 : 16);
+			}
+			__pipeline_commit();
+			__pipeline_wait_prior(0);
+			__threadfence_block();
+			namedBarrier64(); // chunk q has landed; the compute warp arrives here after finishing chunk q - 1
+		}
+		return;
+	}
+	if(role == 2)
+	{
+		// ---- lane-0 feeder: packets P_0(t), eight steps per batch
+		const uint32_t* prevRing = ring + (size_t)(band > 0 ? band - 1 : 0) * 6 * ringPitch;
+		for(int T = 0; T < tEnd; T += 8)
+		{
+			int spins = 0;
+			while(flags[1] < T + 8 - SYS_PR && !flags[2])
+				if(++spins > SYS_SPIN_LIMIT) { flags[2] = 1; atomicAdd(timeouts, 1u); }
+			const int t = T + lane;
+			if(lane < 8 && t < tEnd)
+			{
+				uint32_t f[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+				if(t < nBlocks + 2)
+				{
+					if(band == 0)
+					{
+						const int posLo = PX * t - b + MARK_PAD;
+						const int wi = posLo >> 5, sh = posLo & 31;
+#pragma unroll
+						for(int k = 1; k <= 6; ++k)
+						{
+							const int rr = r0 - k;
+							if(rr >= 0)
+								f[k - 1] = __funnelshift_r(asBits[(size_t)rr * Wp + wi], asBits[(size_t)rr * Wp + wi + 1], sh) & 0xffffu;
+						}
+					}
+					else
+					{
+						// blocks t-2 .. t+2 cover columns 4t-8 .. 4t+11; the field is bits 2..17 of the 20-bit concatenation
+						uint32_t v[6][5];
+						bool all = false;
+						int sp = 0;
+						while(!all)
+						{
+							all = true;
+#pragma unroll
+							for(int k = 0; k < 6; ++k)
+#pragma unroll
+								for(int j = 0; j < 5; ++j)
+								{
+									const int blk = t - 2 + j;
+									uint32_t x = 0x80000000u;
+									if(blk >= 0 && blk < nBlocks)
+										x = ldVolatileGlobal(prevRing + (size_t)k * ringPitch + blk);
+									v[k][j] = x;
+									all = all && (x & 0x80000000u) != 0u;
+								}
+							if(!all)
+							{
+								if(flags[2]) break;
+								if(++sp > SYS_SPIN_LIMIT / 64) { flags[2] = 1; atomicAdd(timeouts, 1u); break; }
+								__nanosleep(40);
+							}
+						}
+#pragma unroll
+						for(int k = 0; k < 6; ++k)
+						{
+							const uint32_t cat = (v[k][0] & 15u) | ((v[k][1] & 15u) << 4) | ((v[k][2] & 15u) << 8) | ((v[k][3] & 15u) << 12) | ((v[k][4] & 15u) << 16);
+							f[k] = (cat >> 2) & 0xffffu;
+						}
+					}
+				}
+				pktS[t & (SYS_PR - 1)] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), 0u);
+			}
+			__syncwarp();
+			__threadfence_block();
+			if(lane == 0)
+				flags[0] = T + 8;
+		}
+		return;
+	}
+
+	// ---- compute warp
+	const int r = r0 + lane;
+	const bool rowValid = r < g.rowEnd;
+	const bool rowCentre = rowValid && r >= w && r <= H - 1 - w;
+	const uint32_t thr = (uint32_t)(fminf(skipProb, 0.99999994f) * 4294967296.f);
+	const size_t rowBase = (size_t)(rowValid ? r : 0) * Wp;
+	const int ringRow = lastLane - lane; // 0..5 for the six hand-off rows of the band
+	uint32_t* myRing = ring + ((size_t)band * 6 + (ringRow >= 0 && ringRow < 6 ? ringRow : 0)) * ringPitch;
+	const bool emits = rowValid && ringRow >= 0 && ringRow < 6;
+	uint32_t hh = 0u;                 // AS bits of my row: bit 31 = the newest column
+	uint32_t o0 = 0u, o1 = 0u, o2 = 0u; // packet for the lane below
+	uint32_t d1a = 0u, d1b = 0u, d1c = 0u, d2a = 0u, d2b = 0u, d2c = 0u; // my packets of the last two steps
+	uint32_t curAS = 0u, curAct = 0u;
+
+	for(int t = 0; t < tEnd; ++t)
+	{
+		const int s = t % SYS_CHS, q = t / SYS_CHS;
+		if(s == 0)
+		{
+			namedBarrier64();
+			if(lane == 0)
+				flags[1] = t;
+			int spins = 0;
+			while(flags[0] < t + 8 && !flags[2])
+				if(++spins > SYS_SPIN_LIMIT) { flags[2] = 1; atomicAdd(timeouts, 1u); }
+			__threadfence_block();
+		}
+		const int C = PX * (t - SKS * lane);
+		const bool valid = rowValid && C >= 0 && C < W;
+		const uint4* src = reinterpret_cast<const uint4*>(tileS + (size_t)(q & 1) * 32 * SYS_RS + (size_t)lane * SYS_RS + s * PX * PW2);
+		uint4 pw[PX];
+#pragma unroll
+		for(int i = 0; i < PX; ++i)
+			pw[i] = src[i];
+		const uint4 first = pktS[t & (SYS_PR - 1)];
+		uint32_t i0 = __shfl_up_sync(0xffffffffu, o0, 1);
+		uint32_t i1 = __shfl_up_sync(0xffffffffu, o1, 1);
+		uint32_t i2 = __shfl_up_sync(0xffffffffu, o2, 1);
+		if(lane == 0) { i0 = first.x; i1 = first.y; i2 = first.z; }
+
+		uint32_t asNibble = 0u, actNibble = 0u;
+#pragma unroll
+		for(int i = 0; i < PX; ++i)
+		{
+			const uint32_t above = (i0 & pw[i].x) | (i1 & pw[i].y) | (i2 & pw[i].z);
+			const uint32_t hit = above | ((pw[i].w << 26) & hh); // same row: bits 0..5 of word 3 = columns c-6..c-1
+			const int c = C + i;
+			const bool centre = rowCentre && valid && c >= w && c <= W - 1 - w;
+			const bool skipIfMarked = ALWAYS || hash32((uint32_t)r, (uint32_t)c, seed) <= thr;
+			const bool act = centre && !(hit != 0u && skipIfMarked);
+			const bool as = act && ((pw[i].w >> 16) & 1u) != 0u;
+			hh = (hh >> 1) | (as ? 0x80000000u : 0u);
+			asNibble |= (as ? 1u : 0u) << i;
+			actNibble |= (act ? 1u : 0u) << i;
+		}
+		// packet for the lane below (consumed at its step t + 1, block C - 8): my row at [C-14, C+1] + my packet of step t - 2
+		o0 = __byte_perm(hh >> 14, d2a, 0x5410);
+		o1 = __byte_perm(d2a, d2b, 0x5432);
+		o2 = __byte_perm(d2b, d2c, 0x5432);
+		d2a = d1a; d2b = d1b; d2c = d1c;
+		d1a = i0; d1b = i1; d1c = i2;
+		if(valid)
+		{
+			const int pos = C + MARK_PAD; // multiple of 4: a block never straddles a word
+			curAS |= asNibble << (pos & 31);
+			curAct |= actNibble << (pos & 31);
+			if(emits)
+				stVolatileGlobal(myRing + (C >> 2), 0x80000000u | asNibble);
+			if((pos & 31) == 28 || C + PX >= W)
+			{
+				actBits[rowBase + (pos >> 5)] = curAct;
+				asBits[rowBase + (pos >> 5)] = curAS;
+				curAS = 0u;
+				curAct = 0u;
+			}
+		}
+	}
+}
+
 // m = 0: every interior pixel is processed (the mask is never consulted, DenoisingUnit.cpp:165-166)
 __global__ void k_all_active_bits(LevelGeom g, uint32_t* __restrict__ actBits, int Wp)
 {
@@ -429,17 +658,38 @@ cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaS
 }
 
 bool g_forceGenericMarking = false; // test hook (BCD_B200_GENERIC_MARKING=1)
+int g_markingKernel = 1;            // b = 6: 1 = systolic kernel (default), 0 = shared-memory wavefront (BCD_B200_MARKING=v4)
 
 bool markingUsesFastLayout(int b) { return (b == 6 || b == 10 || b == 14) && !g_forceGenericMarking; }
 
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
-		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches)
+		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
+		unsigned int* timeouts)
 {
 	const int rows = g.rowEnd - g.rowBeg;
 	if(rows <= 0)
 		return cudaSuccess;
 	const int bands = divUp(rows, 32);
 	cudaError_t err;
+	if(g.b == 6 && !g_forceGenericMarking && g_markingKernel == 1 && bands <= 4 * 148)
+	{
+		// scratch layout (markingScratchWords): [0] time-out counter, [4 ..) hand-off ring [bands][6][ringPitch]
+		const int ringPitch = markingRingPitch(g.W);
+		if((err = cudaMemsetAsync(progress, 0, sizeof(uint32_t) * (4 + (size_t)bands * 6 * ringPitch), st)) != cudaSuccess) return err;
+		*launches += 1;
+		const size_t smem = ((size_t)2 * 32 * SYS_RS + 4 * SYS_PR + 4) * 4;
+		if(skipProb >= 1.f)
+		{
+			if((err = cudaFuncSetAttribute(k_marking_sys6<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+			k_marking_sys6<true><<<bands, 96, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress + 4, ringPitch, timeouts ? timeouts : progress);
+		}
+		else
+		{
+			if((err = cudaFuncSetAttribute(k_marking_sys6<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+			k_marking_sys6<false><<<bands, 96, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress + 4, ringPitch, timeouts ? timeouts : progress);
+		}
+		return cudaGetLastError();
+	}
 	if((err = cudaMemsetAsync(progress, 0, sizeof(unsigned int) * bands, st)) != cudaSuccess) return err;
 	*launches += 1;
 	const size_t asWords = ((size_t)(32 + g.b) * Wp + 3) & ~(size_t)3;

@@ -10,6 +10,7 @@ struct DeviceCounters
 {
 	unsigned long long interior, strong, active, full, fallback, sum_n_full;
 	int nFull, nFallback; // list lengths of the current level
+	unsigned int markTimeouts, pad_; // bounded waits of the marking kernel that expired (must stay 0)
 };
 
 // K0  Denoiser::computePixelCovFromSampleCov
@@ -25,6 +26,7 @@ cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t
 // K2  marking strategy in raster order over the owned rows. asBits / actBits: H x Wp bit-rows (common.cuh), zeroed by
 // the caller (asBits rows above rowBeg may instead hold the upper row tile's hand-off); progress: >= ceil(rows/32).
 extern bool g_forceGenericMarking;
+extern int g_markingKernel; // b = 6: 1 = systolic kernel (default), 0 = shared-memory wavefront (test hook BCD_B200_MARKING=v4)
 // K3e for d <= 32: lanes per matrix (16 or 8: several matrices per warp, k_eig_sub.cu; 32: one warp per matrix). Test hook
 // BCD_B200_EIG_GROUP.
 extern int g_eigGroup;
@@ -32,7 +34,8 @@ cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int cou
 		int group, cudaStream_t st);
 bool markingUsesFastLayout(int b); // k_symmetrize must then write the `pre2` layout
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
-		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches);
+		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
+		unsigned int* timeouts = nullptr);
 cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
 // work lists
 cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,

@@ -301,7 +301,7 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
             fn()
         torch.cuda.synchronize()
         dist.barrier()
-        sampler = B.ClockSampler(local_rank)
+        sampler = B.ClockSampler(local_rank, B.gpu_uuid(local_rank))
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage_acc, launches = {}, 0

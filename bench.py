@@ -55,16 +55,87 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU, sampled DURING the timed region: NVML (pynvml) polled every 2 ms from a
+    thread — the timed region of the default run is only ~0.2 s, too short for `nvidia-smi -lms` to deliver a sample —
+    with the nvidia-smi loop of the profiling recipe as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    _nvml = None
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, uuid=None):
+        self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
+        self.samples, self.reasons, self.max_mhz, self.stop_flag, self.t, self.handle = [], set(), None, False, None, None
+
+    @classmethod
+    def _init_nvml(cls):
+        if cls._nvml is None:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                cls._nvml = pynvml
+            except Exception:
+                cls._nvml = False
+        return cls._nvml
+
+    def _open_nvml(self):
+        nv = self._init_nvml()
+        if not nv:
+            return False
+        try:
+            h = None
+            if self.uuid:
+                for u in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(u.encode() if isinstance(u, str) else u)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = self.index
+                if vis:
+                    ent = [v.strip() for v in vis.split(",") if v.strip()]
+                    if self.index < len(ent) and ent[self.index].isdigit():
+                        idx = int(ent[self.index])
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.handle = h
+            return True
+        except Exception:
+            return False
+
+    def _poll_nvml(self):
+        nv, h = self._nvml, self.handle
+        bits = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            v = getattr(nv, attr, None)
+            if v is None:
+                v = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if v is not None:
+                bits.append((name, v))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if get_reasons:
+                    r = get_reasons(h)
+                    for name, bit in bits:
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self._open_nvml():
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,6 +147,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.handle is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period, timed region only"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,7 +175,15 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
+
+
+def gpu_uuid(local_rank):
+    try:
+        import torch
+        return str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------ CPU reference
@@ -238,7 +323,7 @@ def main():
         for _ in range(a.warmup):
             fn()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank, gpu_uuid(local_rank))
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage_acc, launches = {}, 0

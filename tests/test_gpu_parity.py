@@ -250,6 +250,43 @@ def test_other_search_radii_bit_exact(capi, crop_b, b):
     assert O.rel_linf(out, O.port_denoise(**inp, m=1.0, b=b)) <= TOL
 
 
+@pytest.mark.parametrize("size", [(1003, 205), (260, 517), (64, 40)])
+def test_marking_on_large_frames_both_kernels(capi, size, monkeypatch):
+    """K2 alone at sizes with many row bands (the crops of the reference fixture have three): the GPU's own selection
+    masks go through the restated sequential process (DenoisingUnit.cpp:164-173,690 in raster order) on the CPU and the
+    active map must match bit for bit — for the systolic kernel (default at b = 6) and the shared-memory wavefront
+    (BCD_B200_MARKING=v4), widths that are not a multiple of 4 and heights that are not a multiple of 32."""
+    from bcd_b200 import host
+    W, H = size
+    inp = host.synth(W, H, spp=16)
+    got = {}
+    try:
+        for kern in ("sys", "v4"):
+            monkeypatch.setenv("BCD_B200_MARKING", kern)
+            h, out = _run(capi, inp, m=1.0)
+            masks, counts = h.read_selection()
+            active = h.read_active()
+            st = h.stats()
+            h.close()
+            ref = O.port_marking(masks, counts)
+            bad = np.argwhere(active != ref)
+            assert bad.shape[0] == 0, "%s: %d marking mismatches, first (row,col) %s" % (kern, bad.shape[0], bad[:8].tolist())
+            assert st["active"] == int(ref.sum()) and st["full"] == int((ref.astype(bool) & (counts >= 28)).sum())
+            got[kern] = (active, out)
+        assert np.array_equal(got["sys"][0], got["v4"][0])
+        # fractional m: both kernels use the same counter-based hash, so they must agree with each other
+        frac = {}
+        for kern in ("sys", "v4"):
+            monkeypatch.setenv("BCD_B200_MARKING", kern)
+            h, _ = _run(capi, inp, m=0.5)
+            frac[kern] = h.read_active()
+            h.close()
+        assert np.array_equal(frac["sys"], frac["v4"])
+    finally:
+        monkeypatch.setenv("BCD_B200_MARKING", "sys")
+        capi.Handle(0).close()  # reset the process-wide hook
+
+
 def test_fractional_skip_probability_is_deterministic(capi, crop_b):
     inp = inputs_of(crop_b)
     h, out1 = _run(capi, inp, m=0.5)
