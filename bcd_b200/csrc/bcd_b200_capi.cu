@@ -253,7 +253,7 @@ int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0,
 {
 	LevelBufs& L = h->levels[k];
 	LevelGeom g = levelGeom(h, k, p);
-	const bool fastLayout = markingUsesFastLayout(g.b);
+	const int fastLayout = markingPreLayout(g.b);
 	LevelGeom gb = g;
 	if(r0 >= 0) { gb.yLo = r0; gb.yHi = r1; }
 	STAGE_ON(h, st, BCD_B200_STAGE_SELECT, {
@@ -268,8 +268,10 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
-	const int preWords = markingUsesFastLayout(g.b) ? fastMarkWords(g.b) : g.Pw;
-	CU(cudaMemsetAsync(L.pre.p, 0, (size_t)g.H * prePitchOf(g.W) * preWords * 4, h->stream));
+	const int layout = markingPreLayout(g.b);
+	const size_t bytes = layout == 2 ? sysPreBytes(g.W, g.rowEnd - g.rowBeg)
+	                                 : (size_t)g.H * prePitchOf(g.W) * (layout == 1 ? fastMarkWords(g.b) : g.Pw) * 4;
+	CU(cudaMemsetAsync(L.pre.p, 0, bytes, h->stream));
 	return 0;
 }
 
@@ -581,11 +583,16 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 		const size_t np = std::max<size_t>((size_t)L.W * L.H, 1);
 		const size_t rowWords = (size_t)std::max(L.H, 1) * markingRowWords(L.W);
 		CU(L.smask.reserve(np * gk.Nw * 4));
-		CU(L.pre.reserve((size_t)std::max(L.H, 1) * prePitchOf(L.W) * std::max(gk.Pw, fastMarkWords(gk.b)) * 4 + 64));
+		CU(L.pre.reserve(markingPreBytes(L.W, L.H, gk.b, gk.Pw)));
 		CU(L.counts.reserve(np * 4));
 		CU(L.active.reserve(rowWords * 4));
 		CU(L.asBits.reserve(rowWords * 4));
-		CU(L.progress.reserve(markingScratchWords(L.W, L.H) * 4));
+		{
+			const void* before = L.progress.p;
+			CU(L.progress.reserve(markingScratchWords(L.W, L.H) * 4));
+			if(L.progress.p != before) // ring words carry epoch tags: start from a defined state
+				CU(cudaMemset(L.progress.p, 0, L.progress.cap));
+		}
 		CU(L.fullList.reserve(np * 4));
 		CU(L.fallbackList.reserve(np * 4));
 		CU(L.acc.reserve(np * sizeof(float4)));
@@ -732,6 +739,10 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		g_forceGenericMarking = e && e[0] == '1';
 		e = getenv("BCD_B200_MARKING");
 		g_markingKernel = (e && !strcmp(e, "v4")) ? 0 : 1;
+		e = getenv("BCD_B200_MARK_TRACE");
+		g_markingTrace = (e && e[0] == '1') ? 1 : 0;
+		e = getenv("BCD_B200_MARKING_NW");
+		g_markingBandsPerCta = (e && atoi(e) >= 1) ? atoi(e) : 4;
 		e = getenv("BCD_B200_EIG_GROUP");
 		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
 			g_eigGroup = atoi(e);

@@ -70,12 +70,22 @@ __host__ __device__ inline int fastMarkWords(int b)
 }
 // scratch of the marking stage (uint32 words): progress counters of the shared-memory wavefront kernel, or the time-out
 // counter + the band hand-off ring [bands][6 rows][ringPitch blocks of 4 columns] of the systolic kernel
-__host__ __device__ inline int markingRingPitch(int W) { return ((W + 3) / 4 + 7) & ~3; }
+// (a ring row has 96 slack words in front and 112 behind: the producers store unconditionally for every step)
+__host__ __device__ inline int markingRingPitch(int W) { return ((W + 3) / 4 + 96 + 112 + 3) & ~3; }
 inline size_t markingScratchWords(int W, int H)
 {
 	const size_t bands = (size_t)((H > 0 ? H : 1) + 31) / 32 + 2;
-	return 4 + bands * 6 * (size_t)markingRingPitch(W) + bands;
+	return 4 + (bands * 6 + 1) * (size_t)markingRingPitch(W) + bands; // + 1: the spare row of the systolic kernel
 }
+// Systolic marking kernel (b = 6): number of steps of a band (lane l handles block t - 3 l at step t; multiple of 8) and
+// its band-major `pre2` layout — [band][step t][pixel i of the block][lane] x 16 bytes, so that the 32 lanes (rows) of a
+// band read 512 contiguous bytes per load instead of 32 different rows
+__host__ __device__ inline int sysTEnd(int W) { return ((W + 3) / 4 + 3 * 31 + 8 + 7) & ~7; }
+__host__ __device__ inline size_t sysPreIndex(int band, int t, int i, int lane, int tEnd)
+{
+	return (((size_t)band * tEnd + t) * 4 + i) * 32 + lane; // in 16-byte units
+}
+inline size_t sysPreBytes(int W, int rows) { return (size_t)((rows > 0 ? rows : 1) + 31) / 32 * sysTEnd(W) * 128 * 16; }
 // `pre` rows are pitched to a multiple of 4 pixels so that 4-pixel groups are 16-byte aligned (cp.async 16)
 __host__ __device__ inline int prePitchOf(int W) { return (W + 3) & ~3; }
 __device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)

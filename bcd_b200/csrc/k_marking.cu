@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda_pipeline.h>
+#include <atomic>
+#include <cstdio>
 
 namespace bcdk
 {
@@ -404,26 +406,45 @@ k_marking_fast(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, flo
 
 // ---------------------------------------------------------------------------------------------------------------
 // Systolic kernel (b = 6): the same wavefront (lane l = row r0 + l, 4 pixels per step, lane l at block t - 3 l), but the
-// AS bits never go through shared memory. The 16-column windows of the six rows above travel DOWN the warp as a
-// three-word packet, one shuffle per word and step:
-//     P_l(t)   = fields of rows l-1 .. l-6 at columns [C-6, C+9],  C = 4 (t - 3 l)          (what lane l consumes at step t)
+// AS bits never go through shared memory inside a band. The 16-column windows of the six rows above travel DOWN the
+// warp as a three-word packet, one shuffle per word and step:
+//     P_l(t)     = fields of rows l-1 .. l-6 at columns [C-6, C+9],  C = 4 (t - 3 l)        (what lane l consumes at step t)
 //     P_l+1(t+1) = { own row at [C-14, C+1] (bits 14..29 of the lane's 32-column history), rows l-1 .. l-5 of P_l(t-2) }
-// so a step costs 3 SHFL + 3 PRMT instead of 12 LDS + 6 SHF + 3 PRMT + STS + a warp barrier, and the compute warp does
-// nothing else: a second warp streams the per-pixel input (`pre2`, cp.async into a double-buffered tile, one named
-// barrier per 8 steps), a third one feeds lane 0 — from the AS bit-rows above the launch range (band 0: zeros, or the
-// upper row tile's hand-off) or from the previous band's hand-off ring. Bands (one CTA each, all co-resident) are
-// chained through that ring in global memory: the last six lanes of a band publish the four AS bits of every block
-// they finish as ONE 32-bit word carrying its own valid flag (bit 31), so no fence and no progress counter is needed;
-// the next band's feeder polls the words it needs (volatile loads) eight steps at a time.
-// Every wait is bounded: a feeder that times out raises `dead` and the band finishes with whatever it has (the parity
-// tests then fail; the GPU does not hang).
+// so a step costs 3 SHFL + 3 PRMT instead of 12 LDS + 6 SHF + 3 PRMT + STS + a warp barrier. The per-pixel input
+// (`pre2`, 16 bytes per pixel; bit 17 of word 3 = "is a patch centre", bit 16 = strong) is read straight from global
+// memory / L2 eight steps ahead into registers (every lane streams its own row: 64 contiguous bytes per step).
+// A CTA holds NW consecutive bands, one warp each: lane 31 of a band hands its packets to lane 0 of the next band
+// through a tagged 16-byte slot per step in shared memory (tag = step + 1, written and read as one 128-bit access).
+// CTAs — and, over NVLink, the row tiles of neighbouring GPUs — are chained through a ring in global memory: the last
+// six lanes of a CTA's last band publish the four AS bits of every block they finish as ONE 32-bit word that carries
+// its own epoch tag (bits 8..31), so no fence, no progress counter and no clearing is needed; a feeder warp of the next
+// CTA polls the words (volatile loads) and turns them into lane-0 packets. The first band of a launch is fed from the AS
+// bit-rows above the launch range (zeros, or the strip received from the upper row tile) unless an inbox ring is given.
+// The kernel only resolves the sequential part, AS(p) = active(p) and strong(p): the AS bit-rows are written as whole
+// 32-bit words, all lanes at the same step (every 8 steps: no divergence), and k_active_from_as then derives
+// active(p) = centre(p) and no AS bit under the earlier part of S(p) for every pixel in parallel.
+// Every wait is bounded in time: on a time-out the CTA raises `dead`, counts it and finishes with whatever it has
+// (the run then fails with an error; the GPU does not hang).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SYS_CHS = 8;                          // steps per tile chunk (32 pixels per row)
-constexpr int SYS_RS = SYS_CHS * 4 * 4 + 4;         // tile row stride in words (== 4 mod 32: LDS.128 conflict-free)
-constexpr int SYS_PR = 64;                          // packet ring entries (steps)
-constexpr int SYS_SPIN_LIMIT = 1 << 22;
+constexpr int SYS_PF = 4;                           // steps of read-ahead (= the unroll of the step loop: the loop body must fit
+                                                    // the ~6 KB L0 instruction cache — a lone latency-bound warp cannot hide fetch misses)
+constexpr long long SYS_TIMEOUT_CYCLES = 1ll << 33; // ~4 s
 
-__device__ __forceinline__ void namedBarrier64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+struct SysArgs
+{
+	const uint32_t* pre2; int prePitch;
+	LevelGeom g; float skipProb; uint32_t seed;
+	uint32_t* actBits; uint32_t* asBits; int Wp;
+	uint32_t* ring; int ringPitch;   // hand-off ring of this launch: [CTAs][6 rows][ringPitch blocks]
+	const uint32_t* inRing;          // non-null: the first band is fed from this ring [6][ringPitch] (written by the upper row tile)
+	uint32_t* outRing;               // non-null: the last band of the launch publishes here [6][ringPitch] (the lower row tile's inbox)
+	uint32_t tag;                    // 0x80000000 | epoch << 8: valid marker of the words of `ring` written by this launch
+	uint32_t tagPeer;                // same for inRing / outRing (an epoch the neighbouring row tiles agree on)
+	unsigned int* timeouts;
+	int nBlocks, tEnd, bands;
+	int trace;                       // BCD_B200_MARK_TRACE=1: every band prints its timeline (cycles since its CTA started)
+};
+
 __device__ __forceinline__ uint32_t ldVolatileGlobal(const uint32_t* p)
 {
 	uint32_t v;
@@ -434,201 +455,350 @@ __device__ __forceinline__ void stVolatileGlobal(uint32_t* p, uint32_t v)
 {
 	asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-
-template <bool ALWAYS>
-__global__ void __launch_bounds__(96)
-k_marking_sys6(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
-		uint32_t* __restrict__ actBits, uint32_t* asBits, int Wp, uint32_t* ring, int ringPitch,
-		unsigned int* timeouts)
+__device__ __forceinline__ uint4 ldVolatileShared4(const uint4* p)
 {
-	constexpr int b = 6, PX = 4, SKS = 3, SKC = PX * SKS, PW2 = 4;
+	uint4 v;
+	asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+			: "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stVolatileShared4(uint4* p, uint4 v)
+{
+	asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"((uint32_t)__cvta_generic_to_shared(p)),
+			"r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+constexpr int SYS_PAD = 96;                         // slack entries in front of every ring row / packet row: the producers
+                                                    // store unconditionally, indices before the first block land here
+__host__ __device__ inline int sysPktStride(int tEnd) { return tEnd + SYS_PAD; }
+
+__device__ __forceinline__ uint4 ldVolatileSharedAddr4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stVolatileSharedAddr4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+	asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// cold path of the packet wait (the producer is normally far ahead): bounded spin until the packets of the steps
+// t .. t + SYS_PF - 1 (16 bytes apart from addr) carry their tags
+__device__ __noinline__ void sysWaitPackets(uint32_t addr, uint32_t t, volatile int* dead, long long tStart, unsigned int* timeouts)
+{
+	for(;;)
+	{
+		bool all = true;
+#pragma unroll
+		for(int s = 0; s < SYS_PF; ++s)
+			all = all && ldVolatileSharedAddr4(addr + 16u * s).w == t + (uint32_t)s + 1u;
+		if(all || *dead)
+			return;
+		if(clock64() - tStart > SYS_TIMEOUT_CYCLES) { *dead = 1; atomicAdd(timeouts, 1u); }
+		__nanosleep(20);
+	}
+}
+template <typename T> __device__ __forceinline__ T opaque(T v)
+{
+	asm volatile("" : "+r"(v)); // keeps a loop-invariant value in its register instead of recomputing it every step
+	return v;
+}
+
+template <int NW, bool ALWAYS>
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
+k_marking_sys6(const SysArgs a)
+{
+	constexpr int b = 6, PX = 4, SKS = 3;
 	extern __shared__ __align__(16) uint32_t smem[];
-	uint32_t* tileS = smem;                                              // [2][32][SYS_RS]
-	uint4* pktS = reinterpret_cast<uint4*>(smem + 2 * 32 * SYS_RS);      // [SYS_PR]
-	volatile int* flags = reinterpret_cast<volatile int*>(pktS + SYS_PR); // [0] packets ready, [1] steps consumed, [2] dead
-	const int W = g.W, H = g.H, w = g.w;
-	const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-	const int band = blockIdx.x;
-	const int r0 = g.rowBeg + band * 32;
-	const int lastLane = min(31, g.rowEnd - 1 - r0);
-	const int nBlocks = (W + PX - 1) / PX;
-	const int tEnd = nBlocks + SKS * 31;
-	const int nChunks = (tEnd + SYS_CHS - 1) / SYS_CHS;
-	if(threadIdx.x < 3)
-		flags[threadIdx.x] = 0;
+	const int tEnd = a.tEnd, nBlocks = a.nBlocks;
+	const int pktStride = sysPktStride(tEnd);
+	uint4* pktS = reinterpret_cast<uint4*>(smem);                         // [NW + 1][pktStride] lane-0 packets of the CTA's bands
+	volatile int* dead = reinterpret_cast<volatile int*>(pktS + (size_t)(NW + 1) * pktStride);
+	const LevelGeom& g = a.g;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int cta = blockIdx.x;
+	for(int e = threadIdx.x; e < (NW + 1) * pktStride; e += blockDim.x)
+		pktS[e] = make_uint4(0u, 0u, 0u, 0u);
+	if(threadIdx.x == 0)
+		*dead = 0;
 	__syncthreads();
 
-	if(role == 1)
+	if(warp == NW)
 	{
-		// ---- tile feeder: chunk q of row l covers pixels [32 q - 12 l, +32); one 16-byte unit (= one pixel) per lane
-		for(int q = 0; q < nChunks; ++q)
+		// ---- feeder of the CTA's first band: packets P_0(t) = fields of the six rows above at columns [4t-6, 4t+9]
+		const int band = cta * NW;
+		const int r0 = g.rowBeg + band * 32;
+		const uint32_t* src = band > 0 ? a.ring + (size_t)(cta - 1) * 6 * a.ringPitch : a.inRing;
+		const uint32_t tag = band > 0 ? a.tag : a.tagPeer;
+		uint4* dst = pktS + SYS_PAD;
+		const long long t0 = clock64();
+		for(int T = 0; T < tEnd; T += 32)
 		{
-			uint32_t* stage = tileS + (size_t)(q & 1) * 32 * SYS_RS;
-			for(int l = 0; l < 32; ++l)
-			{
-				const int rr = r0 + l;
-				const int px = SYS_CHS * PX * q - SKC * l + lane;
-				const bool inside = rr < g.rowEnd && px >= 0 && px < prePitch;
-				const uint32_t* src = inside ? pre2 + ((size_t)rr * prePitch + px) * PW2 : pre2;
-				__pipeline_memcpy_async(stage + (size_t)l * SYS_RS + lane * PW2, src, 16, inside ? 0 : 16);
-			}
-			__pipeline_commit();
-			__pipeline_wait_prior(0);
-			__threadfence_block();
-			namedBarrier64(); // chunk q has landed; the compute warp arrives here after finishing chunk q - 1
-		}
-		return;
-	}
-	if(role == 2)
-	{
-		// ---- lane-0 feeder: packets P_0(t), eight steps per batch
-		const uint32_t* prevRing = ring + (size_t)(band > 0 ? band - 1 : 0) * 6 * ringPitch;
-		for(int T = 0; T < tEnd; T += 8)
-		{
-			int spins = 0;
-			while(flags[1] < T + 8 - SYS_PR && !flags[2])
-				if(++spins > SYS_SPIN_LIMIT) { flags[2] = 1; atomicAdd(timeouts, 1u); }
 			const int t = T + lane;
-			if(lane < 8 && t < tEnd)
+			if(t >= tEnd)
+				break;
+			uint32_t f[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+			if(t < nBlocks + 2)
 			{
-				uint32_t f[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-				if(t < nBlocks + 2)
+				if(src == nullptr)
 				{
-					if(band == 0)
+					const int posLo = PX * t - b + MARK_PAD;
+					const int wi = posLo >> 5, sh = posLo & 31;
+#pragma unroll
+					for(int k = 1; k <= 6; ++k)
 					{
-						const int posLo = PX * t - b + MARK_PAD;
-						const int wi = posLo >> 5, sh = posLo & 31;
-#pragma unroll
-						for(int k = 1; k <= 6; ++k)
-						{
-							const int rr = r0 - k;
-							if(rr >= 0)
-								f[k - 1] = __funnelshift_r(asBits[(size_t)rr * Wp + wi], asBits[(size_t)rr * Wp + wi + 1], sh) & 0xffffu;
-						}
-					}
-					else
-					{
-						// blocks t-2 .. t+2 cover columns 4t-8 .. 4t+11; the field is bits 2..17 of the 20-bit concatenation
-						uint32_t v[6][5];
-						bool all = false;
-						int sp = 0;
-						while(!all)
-						{
-							all = true;
-#pragma unroll
-							for(int k = 0; k < 6; ++k)
-#pragma unroll
-								for(int j = 0; j < 5; ++j)
-								{
-									const int blk = t - 2 + j;
-									uint32_t x = 0x80000000u;
-									if(blk >= 0 && blk < nBlocks)
-										x = ldVolatileGlobal(prevRing + (size_t)k * ringPitch + blk);
-									v[k][j] = x;
-									all = all && (x & 0x80000000u) != 0u;
-								}
-							if(!all)
-							{
-								if(flags[2]) break;
-								if(++sp > SYS_SPIN_LIMIT / 64) { flags[2] = 1; atomicAdd(timeouts, 1u); break; }
-								__nanosleep(40);
-							}
-						}
-#pragma unroll
-						for(int k = 0; k < 6; ++k)
-						{
-							const uint32_t cat = (v[k][0] & 15u) | ((v[k][1] & 15u) << 4) | ((v[k][2] & 15u) << 8) | ((v[k][3] & 15u) << 12) | ((v[k][4] & 15u) << 16);
-							f[k] = (cat >> 2) & 0xffffu;
-						}
+						const int rr = r0 - k;
+						if(rr >= 0)
+							f[k - 1] = __funnelshift_r(a.asBits[(size_t)rr * a.Wp + wi], a.asBits[(size_t)rr * a.Wp + wi + 1], sh) & 0xffffu;
 					}
 				}
-				pktS[t & (SYS_PR - 1)] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), 0u);
+				else
+				{
+					// blocks t-2 .. t+2 cover columns 4t-8 .. 4t+11; a field is bits 2..17 of the 20-bit concatenation.
+					// Row 0 (the band's last row) is written last: wait for its newest word first, then verify all of them.
+					const uint32_t* s0 = src + SYS_PAD;
+					const int newest = min(t + 2, nBlocks - 1);
+					while((ldVolatileGlobal(s0 + newest) & 0xffffff00u) != tag && !*dead)
+					{
+						if(clock64() - t0 > SYS_TIMEOUT_CYCLES) { *dead = 1; atomicAdd(a.timeouts, 1u); }
+						__nanosleep(100);
+					}
+					uint32_t v[6][5];
+					bool all = false;
+					while(!all)
+					{
+						all = true;
+#pragma unroll
+						for(int k = 0; k < 6; ++k)
+#pragma unroll
+							for(int j = 0; j < 5; ++j)
+							{
+								const int blk = t - 2 + j;
+								uint32_t x = tag;
+								if(blk >= 0 && blk < nBlocks)
+									x = ldVolatileGlobal(s0 + (size_t)k * a.ringPitch + blk);
+								v[k][j] = x;
+								all = all && (x & 0xffffff00u) == tag;
+							}
+						if(!all)
+						{
+							if(*dead) break;
+							if(clock64() - t0 > SYS_TIMEOUT_CYCLES) { *dead = 1; atomicAdd(a.timeouts, 1u); break; }
+							__nanosleep(100);
+						}
+					}
+#pragma unroll
+					for(int k = 0; k < 6; ++k)
+					{
+						const uint32_t cat = (v[k][0] & 15u) | ((v[k][1] & 15u) << 4) | ((v[k][2] & 15u) << 8) | ((v[k][3] & 15u) << 12) | ((v[k][4] & 15u) << 16);
+						f[k] = (cat >> 2) & 0xffffu;
+					}
+				}
 			}
-			__syncwarp();
-			__threadfence_block();
-			if(lane == 0)
-				flags[0] = T + 8;
+			stVolatileShared4(dst + t, make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), (uint32_t)t + 1u));
 		}
 		return;
 	}
 
-	// ---- compute warp
+	// ---- compute warps: one band each
+	const int band = cta * NW + warp;
+	if(band >= a.bands)
+		return;
+	const int r0 = g.rowBeg + band * 32;
+	const int lastLane = min(31, g.rowEnd - 1 - r0);
 	const int r = r0 + lane;
 	const bool rowValid = r < g.rowEnd;
-	const bool rowCentre = rowValid && r >= w && r <= H - 1 - w;
-	const uint32_t thr = (uint32_t)(fminf(skipProb, 0.99999994f) * 4294967296.f);
-	const size_t rowBase = (size_t)(rowValid ? r : 0) * Wp;
-	const int ringRow = lastLane - lane; // 0..5 for the six hand-off rows of the band
-	uint32_t* myRing = ring + ((size_t)band * 6 + (ringRow >= 0 && ringRow < 6 ? ringRow : 0)) * ringPitch;
-	const bool emits = rowValid && ringRow >= 0 && ringRow < 6;
-	uint32_t hh = 0u;                 // AS bits of my row: bit 31 = the newest column
-	uint32_t o0 = 0u, o1 = 0u, o2 = 0u; // packet for the lane below
-	uint32_t d1a = 0u, d1b = 0u, d1c = 0u, d2a = 0u, d2b = 0u, d2c = 0u; // my packets of the last two steps
-	uint32_t curAS = 0u, curAct = 0u;
-
-	for(int t = 0; t < tEnd; ++t)
+	const uint32_t thr = (uint32_t)(fminf(a.skipProb, 0.99999994f) * 4294967296.f);
+	const size_t rowBase = (size_t)(rowValid ? r : 0) * a.Wp;
+	const uint32_t pktBase = (uint32_t)__cvta_generic_to_shared(pktS);
+	// my lane-0 packets: entry t at inAddr + 16 t
+	uint32_t inAddr = opaque(pktBase + 16u * (uint32_t)(warp * pktStride + SYS_PAD));
+	// lane 31 hands its packets to the next band of the CTA ("lane 32" is 96 steps behind: its step t - 95 consumes my
+	// packet of step t); every other lane — and the CTA's last band — stores into the spare row NW, which nobody reads
+	const bool handsOn = lane == 31 && warp + 1 < NW && band + 1 < a.bands;
+	uint32_t outAddr = opaque(pktBase + 16u * (uint32_t)((handsOn ? warp + 1 : NW) * pktStride + SYS_PAD - 95));
+	// hand-off ring: the CTA's last band feeds the next CTA; the launch's last band feeds the lower row tile (if any).
+	// In such a band every lane stores every step: the six hand-off rows into the ring, the others into the spare row.
+	const int ringRow = lastLane - lane;
+	uint32_t* ringBase = nullptr;
+	uint32_t myTag = a.tag;
+	if(band == a.bands - 1)
 	{
-		const int s = t % SYS_CHS, q = t / SYS_CHS;
-		if(s == 0)
-		{
-			namedBarrier64();
-			if(lane == 0)
-				flags[1] = t;
-			int spins = 0;
-			while(flags[0] < t + 8 && !flags[2])
-				if(++spins > SYS_SPIN_LIMIT) { flags[2] = 1; atomicAdd(timeouts, 1u); }
-			__threadfence_block();
-		}
-		const int C = PX * (t - SKS * lane);
-		const bool valid = rowValid && C >= 0 && C < W;
-		const uint4* src = reinterpret_cast<const uint4*>(tileS + (size_t)(q & 1) * 32 * SYS_RS + (size_t)lane * SYS_RS + s * PX * PW2);
-		uint4 pw[PX];
-#pragma unroll
-		for(int i = 0; i < PX; ++i)
-			pw[i] = src[i];
-		const uint4 first = pktS[t & (SYS_PR - 1)];
-		uint32_t i0 = __shfl_up_sync(0xffffffffu, o0, 1);
-		uint32_t i1 = __shfl_up_sync(0xffffffffu, o1, 1);
-		uint32_t i2 = __shfl_up_sync(0xffffffffu, o2, 1);
-		if(lane == 0) { i0 = first.x; i1 = first.y; i2 = first.z; }
+		ringBase = a.outRing;
+		myTag = a.tagPeer;
+	}
+	else if(warp == NW - 1)
+		ringBase = a.ring + (size_t)cta * 6 * a.ringPitch;
+	const bool warpEmits = ringBase != nullptr; // warp-uniform
+	uint32_t* ringPtr = a.ring + (size_t)gridDim.x * 6 * a.ringPitch; // spare row
+	if(warpEmits && rowValid && ringRow >= 0 && ringRow < 6)
+		ringPtr = ringBase + (size_t)ringRow * a.ringPitch;
+	ringPtr += SYS_PAD - SKS * lane; // + t = + SYS_PAD + block index
+	// per-lane constant of the word stores: after a step t with (t+1) % 8 == 0 the lane has completed n = 4(t+1) - 12 lane
+	// columns; the newest complete 32-bit word starts 32 - (n mod 32) bits into the 64-bit history (n mod 32 == 0: 32)
+	const int mW = (-12 * lane) & 31;
+	const int shW = mW ? 32 - mW : 32;
+	const bool isLane0 = opaque(lane) == 0;
 
-		uint32_t asNibble = 0u, actNibble = 0u;
+	// per-pixel input, SYS_PF steps ahead, band-major: the lanes of the band read 512 contiguous bytes per load. Steps
+	// whose block lies outside the row are invalidated when consumed.
+	const int nBlocksU = opaque(nBlocks);
+	const uint32_t rowInval = opaque(rowValid ? 0u : 0x30000u);
+	const uint4* pbase = reinterpret_cast<const uint4*>(a.pre2) + sysPreIndex(band, 0, 0, lane, tEnd);
+	const int lastStep = opaque(tEnd - 1);
+	uint4 buf[SYS_PF][PX];
+	auto fetch = [&](int slot, int tf)
+	{
+		const uint4* p4 = pbase + (size_t)min(tf, lastStep) * (PX * 32);
+#pragma unroll
+		for(int i = 0; i < PX; ++i)
+			buf[slot][i] = __ldg(p4 + i * 32);
+	};
+#pragma unroll
+	for(int s = 0; s < SYS_PF; ++s)
+		fetch(s, s);
+
+	uint32_t hh = 0u, sLo = 0u;             // AS bits of my row: 64-bit history, bit 31 of hh = the newest column
+	uint32_t o0 = 0u, o1 = 0u, o2 = 0u;     // packet for the lane below
+	uint32_t d1a = 0u, d1b = 0u, d1c = 0u, d2a = 0u, d2b = 0u, d2c = 0u; // my packets of the last two steps
+	const long long tStart = clock64();
+	long long tFirst = 0;
+	int nWaits = 0;
+	int tb = opaque(-SKS * lane);           // block index of the current step
+
+#pragma unroll 1
+	for(int tc = 0; tc < tEnd; tc += SYS_PF)
+	{
+		// lane-0 packets of the SYS_PF steps of this chunk (one tag test for all of them)
+		uint4 pk[SYS_PF];
+		uint32_t bad = 0u;
+#pragma unroll
+		for(int s = 0; s < SYS_PF; ++s)
+		{
+			pk[s] = ldVolatileSharedAddr4(inAddr + 16u * s);
+			bad |= pk[s].w ^ (uint32_t)(tc + s + 1);
+		}
+		if(bad != 0u)
+		{
+			sysWaitPackets(inAddr, (uint32_t)tc, dead, tStart, a.timeouts);
+#pragma unroll
+			for(int s = 0; s < SYS_PF; ++s)
+				pk[s] = ldVolatileSharedAddr4(inAddr + 16u * s);
+			++nWaits;
+			if(a.trace && tc == 0) tFirst = clock64();
+		}
+#pragma unroll
+		for(int s = 0; s < SYS_PF; ++s)
+		{
+			const int t = tc + s;
+			uint32_t i0 = __shfl_up_sync(0xffffffffu, o0, 1);
+			uint32_t i1 = __shfl_up_sync(0xffffffffu, o1, 1);
+			uint32_t i2 = __shfl_up_sync(0xffffffffu, o2, 1);
+			if(isLane0) { i0 = pk[s].x; i1 = pk[s].y; i2 = pk[s].z; }
+
+			// outside the row (or a row beyond the launch range): "not a centre, not strong"
+			const uint32_t inval = (unsigned)(tb + s) < (unsigned)nBlocksU ? rowInval : 0x30000u;
+			const uint32_t hhBefore = hh;
+#pragma unroll
+			for(int i = 0; i < PX; ++i)
+			{
+				const uint4 pw = buf[s][i];
+				uint32_t above = (i0 & pw.x) | (i1 & pw.y) | (i2 & pw.z);
+				uint32_t same = pw.w << 26; // bits 0..5 of word 3 = columns c-6..c-1 -> bits 26..31 of the history
+				if(!ALWAYS)
+				{
+					const uint32_t keep = hash32((uint32_t)r, (uint32_t)(PX * (tb + s) + i), a.seed) <= thr ? 0xffffffffu : 0u;
+					above &= keep;
+					same &= keep;
+				}
+				const uint32_t flags = (~pw.w & 0x30000u) | inval; // bit 17: not a patch centre, bit 16: not strong
+				const uint32_t hitS = above | flags | (same & hh);  // zero <=> patch centre, not marked, strong: AS(p)
+				hh = (hh >> 1) | (hitS == 0u ? 0x80000000u : 0u);
+			}
+			fetch(s, tc + s + SYS_PF);
+			sLo = __funnelshift_r(sLo, hhBefore, 4);
+			// packet for the lane below (consumed at its step t + 1, block C - 8): my row at [C-14, C+1] + my packet of step t - 2
+			o0 = __byte_perm(hh >> 14, d2a, 0x5410);
+			o1 = __byte_perm(d2a, d2b, 0x5432);
+			o2 = __byte_perm(d2b, d2c, 0x5432);
+			d2a = d1a; d2b = d1b; d2c = d1c;
+			d1a = i0; d1b = i1; d1c = i2;
+			stVolatileSharedAddr4(outAddr + 16u * s, o0, o1, o2, (uint32_t)(t - 95) + 1u);
+			if(warpEmits)
+				stVolatileGlobal(ringPtr + s, myTag | (hh >> 28));
+		}
+		tb += SYS_PF;
+		inAddr += 16u * SYS_PF;
+		outAddr += 16u * SYS_PF;
+		ringPtr += SYS_PF;
+		// whole words of the AS bit-row, all lanes at once (every 8 steps = 32 columns)
+		const int n = PX * (tc + SYS_PF) - 4 * SKS * lane;
+		const int wd = ((n + 32) >> 5) - 1;
+		if(((tc + SYS_PF) & 7) == 0 && rowValid && wd >= 1 && wd < a.Wp)
+			a.asBits[rowBase + wd] = __funnelshift_rc(sLo, hh, shW);
+	}
+	if(a.trace && lane == 0)
+	{
+		unsigned int smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		unsigned long long gt;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+		printf("[mark trace] band %3d cta %3d sm %3u  first packet at %9lld  end at %9lld cycles  (%d steps, %d waits)  globaltimer end %llu ns\n",
+				band, cta, smid, tFirst ? tFirst - tStart : 0ll, clock64() - tStart, tEnd, nWaits, gt);
+	}
+	// the next band's remaining steps (it runs 96 steps behind) lie beyond the right edge of the image: empty packets
+	if(handsOn)
+		for(int t0 = tEnd - 95; t0 < tEnd; ++t0)
+			stVolatileShared4(pktS + (size_t)(warp + 1) * pktStride + SYS_PAD + t0, make_uint4(0u, 0u, 0u, (uint32_t)t0 + 1u));
+}
+
+// active(p) from the finished AS bit-rows (second, fully parallel half of the systolic path): a thread owns a block of 4
+// pixels, 8 consecutive lanes assemble one 32-bit word of the act bit-row.
+template <bool ALWAYS>
+__global__ void __launch_bounds__(256)
+k_active_from_as(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
+		const uint32_t* __restrict__ asBits, uint32_t* __restrict__ actBits, int Wp)
+{
+	constexpr int b = 6, PX = 4;
+	const int lane = threadIdx.x;
+	const int blk = blockIdx.x * 32 + lane;
+	const int r = g.rowBeg + blockIdx.y * blockDim.y + threadIdx.y;
+	const int C = PX * blk;
+	const bool ok = r < g.rowEnd && C < prePitch;
+	const uint32_t thr = (uint32_t)(fminf(skipProb, 0.99999994f) * 4294967296.f);
+	uint32_t nib = 0u;
+	if(ok)
+	{
+		const int posLo = C - b + MARK_PAD;
+		const int wi = posLo >> 5, sh = posLo & 31;
+		uint32_t win[6];
+#pragma unroll
+		for(int k = 1; k <= 6; ++k)
+		{
+			const int rr = r - k;
+			win[k - 1] = rr >= 0 ? __funnelshift_r(asBits[(size_t)rr * Wp + wi], asBits[(size_t)rr * Wp + wi + 1], sh) : 0u;
+		}
+		const uint32_t own = __funnelshift_r(asBits[(size_t)r * Wp + wi], asBits[(size_t)r * Wp + wi + 1], sh); // bit j = column C-6+j
+		const uint32_t w0 = __byte_perm(win[0], win[1], 0x5410), w1 = __byte_perm(win[2], win[3], 0x5410), w2 = __byte_perm(win[4], win[5], 0x5410);
+		const int rr = r - g.rowBeg, ln = rr & 31;
+		const uint4* p4 = reinterpret_cast<const uint4*>(pre2) + sysPreIndex(rr >> 5, blk + 3 * ln, 0, ln, sysTEnd(g.W));
 #pragma unroll
 		for(int i = 0; i < PX; ++i)
 		{
-			const uint32_t above = (i0 & pw[i].x) | (i1 & pw[i].y) | (i2 & pw[i].z);
-			const uint32_t hit = above | ((pw[i].w << 26) & hh); // same row: bits 0..5 of word 3 = columns c-6..c-1
-			const int c = C + i;
-			const bool centre = rowCentre && valid && c >= w && c <= W - 1 - w;
-			const bool skipIfMarked = ALWAYS || hash32((uint32_t)r, (uint32_t)c, seed) <= thr;
+			const uint4 pw = __ldg(p4 + i * 32);
+			const uint32_t hit = (w0 & pw.x) | (w1 & pw.y) | (w2 & pw.z) | (pw.w & 0x3fu & (own >> i));
+			const bool centre = (pw.w >> 17) & 1u;
+			const bool skipIfMarked = ALWAYS || hash32((uint32_t)r, (uint32_t)(C + i), seed) <= thr;
 			const bool act = centre && !(hit != 0u && skipIfMarked);
-			const bool as = act && ((pw[i].w >> 16) & 1u) != 0u;
-			hh = (hh >> 1) | (as ? 0x80000000u : 0u);
-			asNibble |= (as ? 1u : 0u) << i;
-			actNibble |= (act ? 1u : 0u) << i;
-		}
-		// packet for the lane below (consumed at its step t + 1, block C - 8): my row at [C-14, C+1] + my packet of step t - 2
-		o0 = __byte_perm(hh >> 14, d2a, 0x5410);
-		o1 = __byte_perm(d2a, d2b, 0x5432);
-		o2 = __byte_perm(d2b, d2c, 0x5432);
-		d2a = d1a; d2b = d1b; d2c = d1c;
-		d1a = i0; d1b = i1; d1c = i2;
-		if(valid)
-		{
-			const int pos = C + MARK_PAD; // multiple of 4: a block never straddles a word
-			curAS |= asNibble << (pos & 31);
-			curAct |= actNibble << (pos & 31);
-			if(emits)
-				stVolatileGlobal(myRing + (C >> 2), 0x80000000u | asNibble);
-			if((pos & 31) == 28 || C + PX >= W)
-			{
-				actBits[rowBase + (pos >> 5)] = curAct;
-				asBits[rowBase + (pos >> 5)] = curAS;
-				curAS = 0u;
-				curAct = 0u;
-			}
+			nib |= (act ? 1u : 0u) << i;
 		}
 	}
+	uint32_t v = nib << (4 * (lane & 7));
+	v |= __shfl_xor_sync(0xffffffffu, v, 1);
+	v |= __shfl_xor_sync(0xffffffffu, v, 2);
+	v |= __shfl_xor_sync(0xffffffffu, v, 4);
+	if((lane & 7) == 0 && r < g.rowEnd && C < g.W)
+		actBits[(size_t)r * Wp + ((C + MARK_PAD) >> 5)] = v;
 }
 
 // m = 0: every interior pixel is processed (the mask is never consulted, DenoisingUnit.cpp:165-166)
@@ -657,38 +827,79 @@ cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaS
 	return cudaGetLastError();
 }
 
+// epoch of the local hand-off ring: process-wide and monotonic, so a ring word left in (possibly recycled) device memory
+// by any earlier launch can never carry the tag of the current one
+static uint32_t nextLocalEpoch()
+{
+	static std::atomic<uint32_t> e{0};
+	return ++e;
+}
+
 bool g_forceGenericMarking = false; // test hook (BCD_B200_GENERIC_MARKING=1)
 int g_markingKernel = 1;            // b = 6: 1 = systolic kernel (default), 0 = shared-memory wavefront (BCD_B200_MARKING=v4)
+int g_markingTrace = 0;              // BCD_B200_MARK_TRACE=1
+int g_markingBandsPerCta = 4;       // systolic kernel: bands (warps) per CTA, 1 / 2 / 4 / 8 (BCD_B200_MARKING_NW)
 
-bool markingUsesFastLayout(int b) { return (b == 6 || b == 10 || b == 14) && !g_forceGenericMarking; }
+// layout of the marking input k_symmetrize must write: 0 generic, 1 `pre2` row-major (k_marking_fast), 2 `pre2` band-major
+// (k_marking_sys6)
+int markingPreLayout(int b)
+{
+	if(g_forceGenericMarking || !(b == 6 || b == 10 || b == 14))
+		return 0;
+	return (b == 6 && g_markingKernel == 1) ? 2 : 1;
+}
+size_t markingPreBytes(int W, int H, int b, int Pw)
+{
+	const size_t rowMajor = (size_t)(H > 0 ? H : 1) * prePitchOf(W) * (size_t)(Pw > fastMarkWords(b) ? Pw : fastMarkWords(b)) * 4 + 64;
+	const size_t bandMajor = b == 6 ? sysPreBytes(W, H) : 0;
+	return rowMajor > bandMajor ? rowMajor : bandMajor;
+}
 
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
-		unsigned int* timeouts)
+		unsigned int* timeouts, uint32_t epoch, const uint32_t* ringIn, uint32_t* ringOut)
 {
 	const int rows = g.rowEnd - g.rowBeg;
 	if(rows <= 0)
 		return cudaSuccess;
 	const int bands = divUp(rows, 32);
 	cudaError_t err;
-	if(g.b == 6 && !g_forceGenericMarking && g_markingKernel == 1 && bands <= 4 * 148)
+	if(g.b == 6 && !g_forceGenericMarking && g_markingKernel == 1)
 	{
-		// scratch layout (markingScratchWords): [0] time-out counter, [4 ..) hand-off ring [bands][6][ringPitch]
-		const int ringPitch = markingRingPitch(g.W);
-		if((err = cudaMemsetAsync(progress, 0, sizeof(uint32_t) * (4 + (size_t)bands * 6 * ringPitch), st)) != cudaSuccess) return err;
-		*launches += 1;
-		const size_t smem = ((size_t)2 * 32 * SYS_RS + 4 * SYS_PR + 4) * 4;
-		if(skipProb >= 1.f)
-		{
-			if((err = cudaFuncSetAttribute(k_marking_sys6<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-			k_marking_sys6<true><<<bands, 96, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress + 4, ringPitch, timeouts ? timeouts : progress);
-		}
-		else
-		{
-			if((err = cudaFuncSetAttribute(k_marking_sys6<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-			k_marking_sys6<false><<<bands, 96, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress + 4, ringPitch, timeouts ? timeouts : progress);
-		}
-		return cudaGetLastError();
+		SysArgs a;
+		a.pre2 = pre; a.prePitch = prePitch; a.g = g; a.skipProb = skipProb; a.seed = seed;
+		a.actBits = actBits; a.asBits = asBits; a.Wp = Wp;
+		a.ringPitch = markingRingPitch(g.W);
+		a.ring = progress + 4; // scratch layout (markingScratchWords): 4 spare words, then the hand-off ring
+		a.inRing = ringIn; a.outRing = ringOut;
+		a.tag = 0x80000000u | ((nextLocalEpoch() & 0x7fffffu) << 8);
+		a.tagPeer = 0x80000000u | ((epoch & 0x7fffffu) << 8);
+		a.timeouts = timeouts ? timeouts : progress;
+		a.nBlocks = (g.W + 3) / 4;
+		a.tEnd = (a.nBlocks + 3 * 31 + 8 + 7) & ~7;
+		a.bands = bands;
+		a.trace = g_markingTrace;
+		const bool always = skipProb >= 1.f;
+#define LAUNCH_SYS(NWV) \
+		do { \
+			const size_t smem = (size_t)((NWV) + 1) * sysPktStride(a.tEnd) * 16 + 16; \
+			if(smem <= 112 * 1024 && divUp(bands, NWV) <= 2 * 148) { \
+				auto kern = always ? k_marking_sys6<NWV, true> : k_marking_sys6<NWV, false>; \
+				if((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+				kern<<<divUp(bands, NWV), 32 * ((NWV) + 1), smem, st>>>(a); \
+				if((err = cudaGetLastError()) != cudaSuccess) return err; \
+				dim3 ablock(32, 8), agrid(divUp(divUp(prePitch, 4), 32), divUp(rows, 8)); \
+				if(always) k_active_from_as<true><<<agrid, ablock, 0, st>>>(pre, prePitch, g, skipProb, seed, asBits, actBits, Wp); \
+				else k_active_from_as<false><<<agrid, ablock, 0, st>>>(pre, prePitch, g, skipProb, seed, asBits, actBits, Wp); \
+				*launches += 2; \
+				return cudaGetLastError(); \
+			} \
+		} while(0)
+		if(g_markingBandsPerCta >= 8) LAUNCH_SYS(8);
+		if(g_markingBandsPerCta >= 4) LAUNCH_SYS(4);
+		if(g_markingBandsPerCta >= 2) LAUNCH_SYS(2);
+		LAUNCH_SYS(1);
+#undef LAUNCH_SYS
 	}
 	if((err = cudaMemsetAsync(progress, 0, sizeof(unsigned int) * bands, st)) != cudaSuccess) return err;
 	*launches += 1;

@@ -21,21 +21,26 @@ cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom&
 		cudaStream_t st, int* launches);
 cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,
 		uint32_t* mplus, cudaStream_t st, int* launches);
-cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre, int prePitch, bool fastLayout,
+cudaError_t launchSymmetrize(const uint32_t* mplus, const LevelGeom& g, uint32_t* smask, int* counts, uint32_t* pre, int prePitch, int fastLayout,
 		cudaStream_t st, int* launches, int rowLo = -1, int rowHi = -1); // rows [rowLo, rowHi) only (default: [g.yLo, g.yHi))
 // K2  marking strategy in raster order over the owned rows. asBits / actBits: H x Wp bit-rows (common.cuh), zeroed by
 // the caller (asBits rows above rowBeg may instead hold the upper row tile's hand-off); progress: >= ceil(rows/32).
 extern bool g_forceGenericMarking;
+extern int g_markingBandsPerCta;
+extern int g_markingTrace;
 extern int g_markingKernel; // b = 6: 1 = systolic kernel (default), 0 = shared-memory wavefront (test hook BCD_B200_MARKING=v4)
 // K3e for d <= 32: lanes per matrix (16 or 8: several matrices per warp, k_eig_sub.cu; 32: one warp per matrix). Test hook
 // BCD_B200_EIG_GROUP.
 extern int g_eigGroup;
 cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
 		int group, cudaStream_t st);
-bool markingUsesFastLayout(int b); // k_symmetrize must then write the `pre2` layout
+int markingPreLayout(int b); // what k_symmetrize must write: 0 generic, 1 `pre2` row-major, 2 `pre2` band-major (systolic kernel)
+size_t markingPreBytes(int W, int H, int b, int Pw); // capacity of the marking input for any kernel choice
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
-		unsigned int* timeouts = nullptr);
+		unsigned int* timeouts = nullptr, uint32_t epoch = 1, const uint32_t* ringIn = nullptr, uint32_t* ringOut = nullptr);
+// (systolic kernel, b = 6) epoch: tag of the hand-off ring words of this launch, different from the previous launches that
+// used the same scratch; ringIn / ringOut: inbox fed by the upper row tile / inbox of the lower row tile (markingRingWords)
 cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
 // work lists
 cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,

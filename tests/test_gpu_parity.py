@@ -274,6 +274,15 @@ def test_marking_on_large_frames_both_kernels(capi, size, monkeypatch):
             assert st["active"] == int(ref.sum()) and st["full"] == int((ref.astype(bool) & (counts >= 28)).sum())
             got[kern] = (active, out)
         assert np.array_equal(got["sys"][0], got["v4"][0])
+        # bands per CTA of the systolic kernel: 1 (every hand-off through the global ring), 2, 8 (default 4)
+        monkeypatch.setenv("BCD_B200_MARKING", "sys")
+        for nw in ("1", "2", "8"):
+            monkeypatch.setenv("BCD_B200_MARKING_NW", nw)
+            h, _ = _run(capi, inp, m=1.0)
+            active = h.read_active()
+            h.close()
+            assert np.array_equal(active, got["sys"][0]), "bands per CTA = %s" % nw
+        monkeypatch.setenv("BCD_B200_MARKING_NW", "4")
         # fractional m: both kernels use the same counter-based hash, so they must agree with each other
         frac = {}
         for kern in ("sys", "v4"):
