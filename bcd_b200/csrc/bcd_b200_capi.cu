@@ -735,6 +735,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 	{
 		const char* e = getenv("BCD_B200_DENSE_PAIR");
 		g_forceDensePair = e && e[0] == '1';
+		e = getenv("BCD_B200_PAIR");
+		g_pairKernel = (e && !strcmp(e, "v1")) ? 1 : 2;
 		e = getenv("BCD_B200_GENERIC_MARKING");
 		g_forceGenericMarking = e && e[0] == '1';
 		e = getenv("BCD_B200_MARKING");

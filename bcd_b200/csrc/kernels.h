@@ -17,6 +17,7 @@ struct DeviceCounters
 cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches);
 // K1a/b/c
 extern bool g_forceDensePair;
+extern int g_pairKernel; // 2 = current sparse kernel, 1 = its predecessor (test hook BCD_B200_PAIR=v1)
 cudaError_t launchPairTerms(const float* hist, const float* ns, const LevelGeom& g, float* sP, unsigned char* cP,
 		cudaStream_t st, int* launches);
 cudaError_t launchPatchSelect(const float* sP, const unsigned char* cP, const LevelGeom& g, float tau,

@@ -70,6 +70,41 @@ def test_pair_terms_bit_exact(capi, crop_a, crop_b, dense, monkeypatch):
         capi.Handle(0).close()  # reset the process-wide hook
 
 
+@pytest.mark.parametrize("kern", ["v2", "v1"])
+def test_pair_terms_uniform_and_ragged_sample_counts(capi, kern, monkeypatch):
+    """K1a's uniform-2^k-sample-count shortcut ((b1-b2)^2/(b1+b2), k_distance.cu) against the restated reference term,
+    bit for bit: frames where it applies everywhere (n = 64; n = 1/8), nowhere (n = 48; n = 2^20 fails the range flag),
+    and tile by tile (left half 64, right half 48, scattered odd pixels) — plus the previous kernel as the A/B twin."""
+    from bcd_b200 import host
+    monkeypatch.setenv("BCD_B200_PAIR", kern)
+    try:
+        base = host.synth(150, 41, spp=64)
+        H, W = base["nsamples"].shape[:2]
+        rng = np.random.default_rng(5)
+        cases = {}
+        for name, n in (("n64", 64.0), ("n_eighth", 0.125), ("n48", 48.0), ("n2^20", 1048576.0)):
+            cases[name] = np.full((H, W, 1), n, np.float32)
+        mixed = np.full((H, W, 1), 64.0, np.float32)
+        mixed[:, W // 2:] = 48.0
+        ys, xs = rng.integers(0, H, 12), rng.integers(0, W // 2, 12)
+        mixed[ys, xs, 0] = rng.integers(1, 200, 12).astype(np.float32)
+        cases["mixed"] = mixed
+        for name, ns in cases.items():
+            inp = dict(base)
+            inp["nsamples"] = np.ascontiguousarray(ns.reshape(base["nsamples"].shape))
+            h, _ = _run(capi, inp, m=0.0, scales=1)
+            sums, counts = h.read_pair_terms(b=6)
+            h.close()
+            ref_s, ref_c = O.port_pair_terms(inp["hist"], inp["nsamples"], b=6)
+            valid = ref_c != 255
+            assert np.array_equal(counts[valid], ref_c[valid]), name
+            bad = np.argwhere((sums.view(np.uint32) != ref_s.view(np.uint32)) & valid)
+            assert bad.shape[0] == 0, "%s: %d pair sums differ, first (j,y,x) %s" % (name, bad.shape[0], bad[:4].tolist())
+    finally:
+        monkeypatch.setenv("BCD_B200_PAIR", "v2")
+        capi.Handle(0).close()  # reset the process-wide hook
+
+
 def test_marking_bit_exact(capi, crop_a):
     h, _ = _run(capi, inputs_of(crop_a), m=1.0)
     active = h.read_active()
