@@ -112,7 +112,7 @@ __device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, boo
 {
 	constexpr int RMAX = (32 + G - 1) / G;
 	float* M = S.M;
-	const int lid = threadIdx.x & (G - 1);
+	const int lid = threadIdx.x & (G - 1), sgrp = (threadIdx.x & 31) / G;
 	// ---- scale the lower triangle into [-1,1], clear the strict upper triangle
 	float lmax = 0.f;
 	for(int e = lid; e < n * n; e += G)
@@ -230,23 +230,39 @@ __device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, boo
 		const uint32_t colStep = 4u * (uint32_t)n;
 		while(true)
 		{
-			if(!done)
-				for(int i = lid; i < end; i += G)
+			// deflation test (SelfAdjointEigenSolver.h:497-503) and, in the same pass, the bit set nz = {i < end :
+			// sub[i] != 0} of the matrix (one ballot per round of G entries) — the scans for `end` and `start`
+			// (:506-520) then are two bit searches instead of two serial walks through shared memory
+			uint32_t nz = 0u;
+#pragma unroll
+			for(int j = 0; j < RMAX; ++j)
+			{
+				const int i = lid + j * G;
+				bool keep = false;
+				if(!done && i < end)
 				{
 					const float a = fabsf(S.sub[i]);
 					if(a <= (fabsf(S.diag[i]) + fabsf(S.diag[i + 1])) * precision || a <= FLT_MIN)
 						S.sub[i] = 0.f;
+					else
+						keep = true; // a > FLT_MIN (or NaN): stays non-zero
 				}
+				const uint32_t bal = __ballot_sync(FULL, keep);
+				nz |= ((bal >> (sgrp * G)) & ((1u << G) - 1u)) << (j * G);
+			}
 			__syncwarp();
 			if(!done)
 			{
-				while(end > 0 && S.sub[end - 1] == 0.f) end--;
-				if(end <= 0) done = true;
-				else if(++iter > 30 * n) done = true;
+				if(nz == 0u) { end = 0; done = true; } // every sub[i], i < end, is zero
 				else
 				{
-					start = end - 1;
-					while(start > 0 && S.sub[start - 1] != 0.f) start--;
+					end = 32 - __clz(nz); // highest non-zero sub-diagonal entry + 1
+					if(++iter > 30 * n) done = true;
+					else
+					{
+						const uint32_t z = ~nz & ((1u << (end - 1)) - 1u); // zero entries below end - 1
+						start = z ? 32 - __clz(z) : 0;
+					}
 				}
 			}
 			if(__all_sync(FULL, done))
