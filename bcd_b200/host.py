@@ -8,7 +8,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbcdcore_b200.so")
-SYMBOLS = ["bcd_synth_generate", "bcd_host_accumulate", "bcd_host_cxx_denoise"]
+SYMBOLS = ["bcd_synth_generate", "bcd_host_accumulate", "bcd_host_cxx_denoise", "bcd_host_exr_load", "bcd_host_exr_fetch",
+           "bcd_host_exr_write", "bcd_host_exr_last_error", "bcd_host_params_load", "bcd_host_params_write"]
 DEFAULT_SEED = 20170627
 _lib = None
 
@@ -25,6 +26,12 @@ def lib():
         L.bcd_host_accumulate.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp, fp, fp]
         L.bcd_host_cxx_denoise.argtypes = [fp, fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float,
                                            C.c_int, C.c_float, C.c_int, C.c_int, fp, C.POINTER(C.c_int)]
+        L.bcd_host_exr_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.bcd_host_exr_fetch.argtypes = [fp]
+        L.bcd_host_exr_write.argtypes = [C.c_char_p, C.c_int, fp, C.c_int, C.c_int, C.c_int]
+        L.bcd_host_exr_last_error.restype = C.c_char_p
+        L.bcd_host_params_load.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.bcd_host_params_write.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -65,3 +72,48 @@ def cxx_denoise(color, nsamples, hist, cov, tau=1.0, w=1, b=6, eps=1e-8, random_
                                     hist.shape[2], tau, w, b, eps, int(random_order), m, scales, device,
                                     out.ctypes.data, C.byref(calls))
     return bool(ok), out, calls.value
+
+
+# ---- EXR files and .bcd.json presets through bcd::ImageIO / bcd::ParametersIO (include/bcd/io/*.h) ----------------------
+class ExrError(RuntimeError):
+    pass
+
+
+def exr_load(path, multi_channel):
+    """bcd::ImageIO::loadMultiChannelsEXR (Bin_%04d channels) or loadEXR (R, G, B) -> (H, W, depth) float32."""
+    w, h, d = C.c_int(), C.c_int(), C.c_int()
+    if not lib().bcd_host_exr_load(os.fsencode(path), int(bool(multi_channel)), C.byref(w), C.byref(h), C.byref(d)):
+        raise ExrError(lib().bcd_host_exr_last_error().decode("utf-8", "replace"))
+    out = np.empty((h.value, w.value, d.value), np.float32)
+    lib().bcd_host_exr_fetch(out.ctypes.data)
+    return out
+
+
+def exr_write(path, image, multi_channel):
+    """bcd::ImageIO::writeMultiChannelsEXR (FLOAT Bin_%04d, ZIP) or writeEXR (HALF RGBA, ZIP) of an (H, W, depth) array."""
+    image = np.ascontiguousarray(image, np.float32)
+    H, W, D = image.shape
+    if not lib().bcd_host_exr_write(os.fsencode(path), int(bool(multi_channel)), image.ctypes.data, W, H, D):
+        raise ExrError(lib().bcd_host_exr_last_error().decode("utf-8", "replace"))
+
+
+PARAM_KEYS = ("performSpikeRemovalPrefiltering", "spikeRemovalThresholdStDevFactor", "nbOfScales", "histoDistanceThreshold",
+              "useCuda", "nbOfCores", "patchRadius", "searchWindowRadius", "randomPixelOrder",
+              "markedPixelsSkippingProbability", "minEigenValue")
+PARAM_DEFAULTS = (1.0, 1.5, 3.0, 1.0, 1.0, 0.0, 1.0, 6.0, 1.0, 1.0, 1e-8)  # ParametersIO.h / IDenoiser.h defaults
+
+
+def params_load(path, defaults=PARAM_DEFAULTS):
+    """bcd::ParametersIO::load -> dict of the 11 numeric fields + the three input file names, or None on failure."""
+    v = (C.c_double * 11)(*defaults)
+    bufs = [C.create_string_buffer(4096) for _ in range(3)]
+    if not lib().bcd_host_params_load(os.fsencode(path), v, bufs[0], bufs[1], bufs[2], 4096):
+        return None
+    out = dict(zip(PARAM_KEYS, list(v)))
+    out.update(inputColorFile=bufs[0].value.decode(), inputHistoFile=bufs[1].value.decode(), inputCovarFile=bufs[2].value.decode())
+    return out
+
+
+def params_write(path, values, color="", hist="", cov=""):
+    v = (C.c_double * 11)(*[float(values[k]) for k in PARAM_KEYS])
+    return bool(lib().bcd_host_params_write(os.fsencode(path), v, os.fsencode(color), os.fsencode(hist), os.fsencode(cov)))

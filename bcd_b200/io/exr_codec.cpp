@@ -1,0 +1,740 @@
+// See exr_codec.h. File layout (OpenEXR 2.x, single-part scan-line image), all integers little-endian:
+//   magic 0x01312f76 | version byte 2 + flag bits (0x200 tiled, 0x800 deep, 0x1000 multi-part)
+//   attributes: name\0 type\0 int32 size, payload ... terminated by an empty name
+//   offset table: one uint64 per chunk | chunks: int32 y, int32 byteCount, payload
+// A chunk holds 1 (NONE, RLE, ZIPS), 16 (ZIP) or 32 (PIZ) scan lines; decompressed it is, line by line, the channels
+// in alphabetical order, `width` little-endian values each. A payload as long as the raw block is stored raw.
+#include "exr_codec.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace bcdio
+{
+
+// ------------------------------------------------------------------------------------------------ half <-> float
+float halfToFloat(unsigned short h)
+{
+	const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+	uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
+	if(exp == 0)
+	{
+		if(man == 0)
+			bits = sign;
+		else
+		{
+			int e = -1; // normalise the subnormal
+			do { ++e; man <<= 1; } while(!(man & 0x400u));
+			bits = sign | (uint32_t)(127 - 15 - e) << 23 | (man & 0x3ffu) << 13;
+		}
+	}
+	else if(exp == 31)
+		bits = sign | 0x7f800000u | man << 13;
+	else
+		bits = sign | (exp + 127 - 15) << 23 | man << 13;
+	float f;
+	memcpy(&f, &bits, 4);
+	return f;
+}
+
+unsigned short floatToHalf(float f)
+{
+	uint32_t x;
+	memcpy(&x, &f, 4);
+	const uint32_t sign = (x >> 16) & 0x8000u;
+	const int e = (int)((x >> 23) & 0xffu) - 127 + 15;
+	uint32_t m = x & 0x007fffffu;
+	if(e <= 0)
+	{
+		if(e < -10)
+			return (unsigned short)sign; // rounds to zero
+		m |= 0x00800000u; // subnormal half: shift the significand, round to nearest even
+		const int t = 14 - e;
+		const uint32_t a = (1u << (t - 1)) - 1u, b = (m >> t) & 1u;
+		return (unsigned short)(sign | ((m + a + b) >> t));
+	}
+	if(e == 0xff - 127 + 15)
+	{
+		if(m == 0)
+			return (unsigned short)(sign | 0x7c00u); // infinity
+		m >>= 13;
+		return (unsigned short)(sign | 0x7c00u | m | (m == 0)); // NaN stays a NaN
+	}
+	m = m + 0x00000fffu + ((m >> 13) & 1u); // round to nearest even
+	int ee = e;
+	if(m & 0x00800000u)
+	{
+		m = 0;
+		ee += 1;
+	}
+	if(ee > 30)
+		return (unsigned short)(sign | 0x7c00u); // overflow
+	return (unsigned short)(sign | (uint32_t)ee << 10 | (m >> 13));
+}
+
+namespace
+{
+
+struct Reader
+{
+	const uint8_t* p;
+	const uint8_t* end;
+	bool ok;
+	Reader(const uint8_t* b, size_t n) : p(b), end(b + n), ok(true) {}
+	bool need(size_t n)
+	{
+		if((size_t)(end - p) < n) ok = false;
+		return ok;
+	}
+	uint8_t u8() { if(!need(1)) return 0; return *p++; }
+	uint32_t u32()
+	{
+		if(!need(4)) return 0;
+		const uint32_t v = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+		p += 4;
+		return v;
+	}
+	int32_t i32() { return (int32_t)u32(); }
+	uint64_t u64()
+	{
+		const uint64_t lo = u32(), hi = u32();
+		return lo | hi << 32;
+	}
+	std::string str()
+	{
+		std::string s;
+		while(need(1) && *p)
+			s.push_back((char)*p++);
+		if(ok) ++p;
+		return s;
+	}
+};
+
+int linesPerChunk(int compression)
+{
+	switch(compression)
+	{
+		case EXR_NONE: case EXR_RLE: case EXR_ZIPS: return 1;
+		case EXR_ZIP: return 16;
+		case EXR_PIZ: return 32;
+		default: return 0;
+	}
+}
+
+int bytesOf(int type) { return type == EXR_HALF ? 2 : 4; }
+
+// ---- the byte predictor + even/odd split shared by RLE and ZIP (decoding direction)
+void undoPredictorAndSplit(std::vector<uint8_t>& t, uint8_t* out)
+{
+	const size_t n = t.size();
+	for(size_t i = 1; i < n; ++i)
+		t[i] = (uint8_t)(t[i - 1] + t[i] - 128);
+	const size_t half = (n + 1) / 2;
+	for(size_t i = 0, a = 0, b = half; i < n;)
+	{
+		out[i++] = t[a++];
+		if(i < n) out[i++] = t[b++];
+	}
+}
+
+void applySplitAndPredictor(const uint8_t* raw, size_t n, std::vector<uint8_t>& t)
+{
+	t.resize(n);
+	const size_t half = (n + 1) / 2;
+	for(size_t i = 0, a = 0, b = half; i < n;)
+	{
+		t[a++] = raw[i++];
+		if(i < n) t[b++] = raw[i++];
+	}
+	int prev = n ? t[0] : 0;
+	for(size_t i = 1; i < n; ++i)
+	{
+		const int cur = t[i];
+		t[i] = (uint8_t)(cur - prev + 128 + 256);
+		prev = cur;
+	}
+}
+
+bool unzipBlock(const uint8_t* src, size_t n, size_t rawSize, uint8_t* out)
+{
+	std::vector<uint8_t> t(rawSize);
+	uLongf got = (uLongf)rawSize;
+	if(uncompress(t.data(), &got, src, (uLong)n) != Z_OK || got != rawSize)
+		return false;
+	undoPredictorAndSplit(t, out);
+	return true;
+}
+
+bool unrleBlock(const uint8_t* src, size_t n, size_t rawSize, uint8_t* out)
+{
+	std::vector<uint8_t> t;
+	t.reserve(rawSize);
+	size_t i = 0;
+	while(i < n)
+	{
+		const int c = (int8_t)src[i++];
+		if(c < 0)
+		{
+			const size_t cnt = (size_t)(-c);
+			if(i + cnt > n || t.size() + cnt > rawSize) return false;
+			t.insert(t.end(), src + i, src + i + cnt);
+			i += cnt;
+		}
+		else
+		{
+			const size_t cnt = (size_t)c + 1;
+			if(i >= n || t.size() + cnt > rawSize) return false;
+			t.insert(t.end(), cnt, src[i++]);
+		}
+	}
+	if(t.size() != rawSize) return false;
+	undoPredictorAndSplit(t, out);
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------- PIZ
+// Huffman stream (ImfHuf): 20-byte header {minSymbol, maxSymbol, -, bitCount, -}, the code lengths of the symbols
+// minSymbol..maxSymbol packed 6 bits each (59..62: run of 2..5 zero lengths, 63: 8 more bits = run - 6), then the
+// MSB-first code stream. Codes are canonical: within a length, by ascending symbol; the first code of length l-1 is
+// (first(l) + count(l)) >> 1, so longer codes are numerically smaller. Symbol maxSymbol is the run-length escape:
+// the next 8 bits repeat the previous output value.
+struct BitIn
+{
+	const uint8_t* p;
+	const uint8_t* end;
+	uint64_t acc;
+	int n;
+	BitIn(const uint8_t* b, const uint8_t* e) : p(b), end(e), acc(0), n(0) {}
+	void fill(int want) // make `want` (<= 56) bits available, zero-padded past the end
+	{
+		while(n < want)
+		{
+			acc = (acc << 8) | (p < end ? *p : 0);
+			++p;
+			n += 8;
+		}
+	}
+	uint32_t peek(int k) { fill(k); return (uint32_t)((acc >> (n - k)) & ((1ull << k) - 1)); }
+	uint64_t peek64(int k) { fill(k); return (acc >> (n - k)) & ((1ull << k) - 1); }
+	void drop(int k) { n -= k; }
+	uint32_t get(int k) { const uint32_t v = peek(k); drop(k); return v; }
+};
+
+bool hufDecode(const uint8_t* comp, size_t nComp, uint16_t* raw, size_t nRaw, std::string& err)
+{
+	if(nComp == 0)
+	{
+		if(nRaw != 0) err = "PIZ: empty Huffman block";
+		return nRaw == 0;
+	}
+	if(nComp < 20) { err = "PIZ: truncated Huffman header"; return false; }
+	Reader hd(comp, 20);
+	const uint32_t im = hd.u32(), iM = hd.u32();
+	hd.u32();
+	const uint32_t nBits = hd.u32();
+	const uint32_t NSYM = 65537;
+	if(im >= NSYM || iM >= NSYM || im > iM) { err = "PIZ: bad Huffman symbol range"; return false; }
+	std::vector<uint8_t> len(NSYM, 0);
+	BitIn tb(comp + 20, comp + nComp);
+	for(uint32_t s = im; s <= iM; ++s)
+	{
+		const uint32_t l = tb.get(6);
+		if(l == 63 || l >= 59)
+		{
+			const uint32_t run = l == 63 ? tb.get(8) + 6 : l - 59 + 2;
+			if(s + run > iM + 1) { err = "PIZ: Huffman table too long"; return false; }
+			s += run - 1;
+		}
+		else
+			len[s] = (uint8_t)l;
+	}
+	// the table reader pulls whole bytes on demand: the code stream starts after the last byte it touched
+	const uint8_t* data = tb.p - (tb.n / 8);
+	if(data > comp + nComp || (uint64_t)nBits > 8ull * (uint64_t)(comp + nComp - data)) { err = "PIZ: bad Huffman bit count"; return false; }
+	uint64_t count[59] = {0}, first[59] = {0};
+	for(uint32_t s = 0; s < NSYM; ++s)
+		count[len[s]]++;
+	{
+		uint64_t c = 0;
+		for(int l = 58; l > 0; --l)
+		{
+			first[l] = c;
+			c = (c + count[l]) >> 1;
+		}
+	}
+	std::vector<uint32_t> start(60, 0), bySym;
+	for(int l = 1; l <= 58; ++l)
+		start[l + 1] = start[l] + (uint32_t)count[l];
+	bySym.resize(start[59]);
+	{
+		std::vector<uint32_t> fillPos(start.begin(), start.end());
+		for(uint32_t s = 0; s < NSYM; ++s)
+			if(len[s]) bySym[fillPos[len[s]]++] = s;
+	}
+	const int FAST = 12;
+	std::vector<uint32_t> fast(1u << FAST, 0); // symbol << 6 | length, 0 = longer code
+	for(int l = 1; l <= FAST; ++l)
+		for(uint64_t k = 0; k < count[l]; ++k)
+		{
+			const uint64_t code = first[l] + k;
+			if(code >> l) { err = "PIZ: inconsistent Huffman lengths"; return false; }
+			const uint32_t lo = (uint32_t)(code << (FAST - l)), entry = bySym[start[l] + (uint32_t)k] << 6 | (uint32_t)l;
+			for(uint32_t j = 0; j < (1u << (FAST - l)); ++j)
+				fast[lo + j] = entry;
+		}
+	BitIn in(data, data + (nBits + 7) / 8);
+	uint64_t used = 0;
+	size_t o = 0;
+	while(o < nRaw)
+	{
+		uint32_t sym = 0;
+		int l = 0;
+		const uint32_t e = fast[in.peek(FAST)];
+		if(e)
+		{
+			sym = e >> 6;
+			l = (int)(e & 63);
+		}
+		else
+		{
+			for(l = FAST + 1; l <= 56; ++l)
+			{
+				if(!count[l]) continue;
+				const uint64_t code = in.peek64(l);
+				if(code >= first[l] && code - first[l] < count[l])
+				{
+					sym = bySym[start[l] + (uint32_t)(code - first[l])];
+					break;
+				}
+			}
+			if(l > 56) { err = "PIZ: invalid Huffman code"; return false; }
+		}
+		in.drop(l);
+		used += (uint64_t)l;
+		if(used > nBits) { err = "PIZ: Huffman stream too short"; return false; }
+		if(sym == iM)
+		{
+			const uint32_t run = in.get(8);
+			used += 8;
+			if(used > nBits || o == 0 || o + run > nRaw) { err = "PIZ: bad run in Huffman stream"; return false; }
+			const uint16_t v = raw[o - 1];
+			for(uint32_t k = 0; k < run; ++k)
+				raw[o++] = v;
+		}
+		else
+			raw[o++] = (uint16_t)sym;
+	}
+	return true;
+}
+
+// inverse of the 2 x 2 Haar-like lifting step of ImfWav (14-bit variant: plain shorts; 16-bit: modulo 2^16)
+inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b)
+{
+	const int ls = (int16_t)l, hi = (int16_t)h;
+	const int ai = ls + (hi & 1) + (hi >> 1);
+	a = (uint16_t)(int16_t)ai;
+	b = (uint16_t)(int16_t)(ai - hi);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b)
+{
+	const int m = l, d = h;
+	const int bb = (m - (d >> 1)) & 0xffff;
+	a = (uint16_t)((d + bb - 0x8000) & 0xffff);
+	b = (uint16_t)bb;
+}
+
+void waveletDecode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t maxValue)
+{
+	const bool w14 = maxValue < (1 << 14);
+	const int n = nx > ny ? ny : nx;
+	int p = 1;
+	while(p <= n) p <<= 1;
+	p >>= 1;
+	int p2 = p;
+	p >>= 1;
+	auto dec = [w14](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) { if(w14) wdec14(l, h, a, b); else wdec16(l, h, a, b); };
+	for(; p >= 1; p2 = p, p >>= 1)
+	{
+		const long oy1 = (long)oy * p, oy2 = (long)oy * p2, ox1 = (long)ox * p, ox2 = (long)ox * p2;
+		uint16_t* py = in;
+		uint16_t* const ey = in + (long)oy * (ny - p2);
+		for(; py <= ey; py += oy2)
+		{
+			uint16_t* px = py;
+			uint16_t* const ex = py + (long)ox * (nx - p2);
+			for(; px <= ex; px += ox2)
+			{
+				uint16_t* p01 = px + ox1;
+				uint16_t* p10 = px + oy1;
+				uint16_t* p11 = p10 + ox1;
+				uint16_t i00, i01, i10, i11;
+				dec(*px, *p10, i00, i10);
+				dec(*p01, *p11, i01, i11);
+				dec(i00, i01, *px, *p01);
+				dec(i10, i11, *p10, *p11);
+			}
+			if(nx & p) // odd column at this level: vertical step only
+			{
+				uint16_t* p10 = px + oy1;
+				uint16_t i00;
+				dec(*px, *p10, i00, *p10);
+				*px = i00;
+			}
+		}
+		if(ny & p) // odd line: horizontal step only
+		{
+			uint16_t* px = py;
+			uint16_t* const ex = py + (long)ox * (nx - p2);
+			for(; px <= ex; px += ox2)
+			{
+				uint16_t* p01 = px + ox1;
+				uint16_t i00;
+				dec(*px, *p01, i00, *p01);
+				*px = i00;
+			}
+		}
+	}
+}
+
+bool unpizBlock(const uint8_t* src, size_t n, int width, int lines, const std::vector<int>& types, uint8_t* out,
+		std::string& err)
+{
+	const size_t nch = types.size();
+	std::vector<size_t> startOf(nch + 1, 0);
+	for(size_t c = 0; c < nch; ++c)
+		startOf[c + 1] = startOf[c] + (size_t)width * lines * (bytesOf(types[c]) / 2);
+	const size_t total = startOf[nch];
+	Reader r(src, n);
+	const uint32_t lo = (uint32_t)r.u8() | (uint32_t)r.u8() << 8, hi = (uint32_t)r.u8() | (uint32_t)r.u8() << 8;
+	if(!r.ok || hi >= 8192) { err = "PIZ: bad bitmap range"; return false; }
+	std::vector<uint8_t> bitmap(8192, 0);
+	if(lo <= hi)
+	{
+		if(!r.need(hi - lo + 1)) { err = "PIZ: truncated bitmap"; return false; }
+		memcpy(bitmap.data() + lo, r.p, hi - lo + 1);
+		r.p += hi - lo + 1;
+	}
+	std::vector<uint16_t> lut(65536, 0);
+	uint32_t k = 0;
+	for(uint32_t i = 0; i < 65536; ++i)
+		if(i == 0 || (bitmap[i >> 3] & (1u << (i & 7))))
+			lut[k++] = (uint16_t)i;
+	const uint16_t maxValue = (uint16_t)(k - 1);
+	const int32_t length = r.i32();
+	if(!r.ok || length < 0 || !r.need((size_t)length)) { err = "PIZ: truncated Huffman block"; return false; }
+	std::vector<uint16_t> tmp(total);
+	if(!hufDecode(r.p, (size_t)length, tmp.data(), total, err))
+		return false;
+	for(size_t c = 0; c < nch; ++c)
+	{
+		const int size = bytesOf(types[c]) / 2;
+		for(int j = 0; j < size; ++j)
+			waveletDecode(tmp.data() + startOf[c] + j, width, size, lines, width * size, maxValue);
+	}
+	for(size_t i = 0; i < total; ++i)
+		tmp[i] = lut[tmp[i]];
+	// back to the scan-line interleaved byte layout
+	std::vector<size_t> cur(startOf.begin(), startOf.end() - 1);
+	uint8_t* o = out;
+	for(int y = 0; y < lines; ++y)
+		for(size_t c = 0; c < nch; ++c)
+		{
+			const size_t cnt = (size_t)width * (bytesOf(types[c]) / 2);
+			for(size_t i = 0; i < cnt; ++i)
+			{
+				const uint16_t v = tmp[cur[c]++];
+				*o++ = (uint8_t)(v & 0xff);
+				*o++ = (uint8_t)(v >> 8);
+			}
+		}
+	return true;
+}
+
+bool readWholeFile(const char* path, std::vector<uint8_t>& buf)
+{
+	FILE* f = fopen(path, "rb");
+	if(!f) return false;
+	fseek(f, 0, SEEK_END);
+	const long n = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	if(n < 0) { fclose(f); return false; }
+	buf.resize((size_t)n);
+	const size_t got = n ? fread(buf.data(), 1, (size_t)n, f) : 0;
+	fclose(f);
+	return got == (size_t)n;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------------- read
+bool exrRead(const char* path, ExrFile& out, std::string& err)
+{
+	std::vector<uint8_t> buf;
+	if(!readWholeFile(path, buf)) { err = std::string("cannot read '") + path + "'"; return false; }
+	Reader r(buf.data(), buf.size());
+	if(r.u32() != 20000630u || !r.ok) { err = std::string("'") + path + "' is not an OpenEXR file"; return false; }
+	const uint32_t version = r.u32();
+	if((version & 0xff) != 2) { err = "unsupported OpenEXR version"; return false; }
+	if(version & 0x200) { err = "tiled OpenEXR files are not supported"; return false; }
+	if(version & 0x800) { err = "deep OpenEXR files are not supported"; return false; }
+	if(version & 0x1000) { err = "multi-part OpenEXR files are not supported"; return false; }
+	bool haveCh = false, haveDw = false, haveComp = false;
+	int maxX = 0, maxY = 0;
+	out = ExrFile();
+	while(r.ok)
+	{
+		const std::string name = r.str();
+		if(name.empty()) break;
+		const std::string type = r.str();
+		const int32_t size = r.i32();
+		if(!r.ok || size < 0 || !r.need((size_t)size)) { err = "truncated header"; return false; }
+		Reader a(r.p, (size_t)size);
+		r.p += size;
+		if(name == "channels" && type == "chlist")
+		{
+			while(a.ok)
+			{
+				const std::string ch = a.str();
+				if(ch.empty()) break;
+				const int32_t pt = a.i32();
+				a.u8(); a.u8(); a.u8(); a.u8(); // pLinear + reserved
+				const int32_t xs = a.i32(), ys = a.i32();
+				if(!a.ok) break;
+				if(pt < 0 || pt > 2) { err = "unknown pixel type in channel list"; return false; }
+				if(xs != 1 || ys != 1) { err = "sub-sampled channels are not supported"; return false; }
+				out.names.push_back(ch);
+				out.types.push_back(pt);
+			}
+			haveCh = true;
+		}
+		else if(name == "compression" && type == "compression")
+		{
+			out.compression = a.u8();
+			haveComp = true;
+		}
+		else if(name == "dataWindow" && type == "box2i")
+		{
+			out.minX = a.i32(); out.minY = a.i32(); maxX = a.i32(); maxY = a.i32();
+			haveDw = true;
+		}
+	}
+	if(!r.ok || !haveCh || !haveDw || !haveComp) { err = "incomplete OpenEXR header"; return false; }
+	const int lpc = linesPerChunk(out.compression);
+	if(lpc == 0)
+	{
+		static const char* names[] = {"NONE", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB"};
+		err = std::string("unsupported compression ") + (out.compression < 10 ? names[out.compression] : "?")
+			+ " (supported: NONE, RLE, ZIPS, ZIP, PIZ)";
+		return false;
+	}
+	const long w = (long)maxX - out.minX + 1, h = (long)maxY - out.minY + 1;
+	if(w <= 0 || h <= 0 || w > (1 << 20) || h > (1 << 20)) { err = "bad data window"; return false; }
+	out.width = (int)w;
+	out.height = (int)h;
+	const size_t nch = out.names.size();
+	size_t lineBytes = 0;
+	for(size_t c = 0; c < nch; ++c)
+		lineBytes += (size_t)w * bytesOf(out.types[c]);
+	out.planes.assign(nch, std::vector<float>((size_t)w * h));
+	const int nChunks = (int)((h + lpc - 1) / lpc);
+	std::vector<uint64_t> offsets(nChunks);
+	for(int i = 0; i < nChunks; ++i)
+		offsets[i] = r.u64();
+	if(!r.ok) { err = "truncated offset table"; return false; }
+	std::vector<uint8_t> raw;
+	const uint8_t* seq = r.p; // fall back to reading the chunks in file order when the table was never written
+	for(int i = 0; i < nChunks; ++i)
+	{
+		const uint8_t* cp = offsets[i] ? buf.data() + offsets[i] : seq;
+		if(offsets[i] >= buf.size()) { err = "bad chunk offset"; return false; }
+		Reader c(cp, (size_t)(buf.data() + buf.size() - cp));
+		const int32_t y = c.i32(), n = c.i32();
+		if(!c.ok || n < 0 || !c.need((size_t)n)) { err = "truncated chunk"; return false; }
+		seq = c.p + n;
+		const long ly = (long)y - out.minY;
+		if(ly < 0 || ly >= h || ly % lpc) { err = "bad chunk coordinate"; return false; }
+		const int lines = (int)std::min<long>(lpc, h - ly);
+		const size_t rawSize = lineBytes * lines;
+		raw.resize(rawSize);
+		if((size_t)n == rawSize)
+			memcpy(raw.data(), c.p, rawSize);
+		else
+		{
+			bool ok = false;
+			switch(out.compression)
+			{
+				case EXR_RLE: ok = unrleBlock(c.p, (size_t)n, rawSize, raw.data()); break;
+				case EXR_ZIPS: case EXR_ZIP: ok = unzipBlock(c.p, (size_t)n, rawSize, raw.data()); break;
+				case EXR_PIZ: ok = unpizBlock(c.p, (size_t)n, (int)w, lines, out.types, raw.data(), err); break;
+				default: break;
+			}
+			if(!ok)
+			{
+				if(err.empty()) err = "corrupt compressed chunk";
+				return false;
+			}
+		}
+		const uint8_t* s = raw.data();
+		for(int l = 0; l < lines; ++l)
+			for(size_t ch = 0; ch < nch; ++ch)
+			{
+				float* dst = out.planes[ch].data() + (size_t)(ly + l) * w;
+				if(out.types[ch] == EXR_HALF)
+					for(long x = 0; x < w; ++x, s += 2)
+						dst[x] = halfToFloat((unsigned short)(s[0] | s[1] << 8));
+				else if(out.types[ch] == EXR_FLOAT)
+					for(long x = 0; x < w; ++x, s += 4)
+					{
+						const uint32_t b = (uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24;
+						memcpy(dst + x, &b, 4);
+					}
+				else
+					for(long x = 0; x < w; ++x, s += 4)
+						dst[x] = (float)((uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24);
+			}
+	}
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------ write
+namespace
+{
+void put32(std::vector<uint8_t>& b, uint32_t v)
+{
+	for(int i = 0; i < 4; ++i) b.push_back((uint8_t)(v >> (8 * i)));
+}
+void putStr(std::vector<uint8_t>& b, const char* s)
+{
+	while(*s) b.push_back((uint8_t)*s++);
+	b.push_back(0);
+}
+void putF32(std::vector<uint8_t>& b, float f)
+{
+	uint32_t v;
+	memcpy(&v, &f, 4);
+	put32(b, v);
+}
+void attr(std::vector<uint8_t>& b, const char* name, const char* type, const std::vector<uint8_t>& payload)
+{
+	putStr(b, name);
+	putStr(b, type);
+	put32(b, (uint32_t)payload.size());
+	b.insert(b.end(), payload.begin(), payload.end());
+}
+} // namespace
+
+bool exrWrite(const char* path, int width, int height, const std::vector<std::string>& names,
+		const std::vector<const float*>& planes, ExrPixelType type, ExrCompression compression, std::string& err)
+{
+	if(width <= 0 || height <= 0 || names.empty() || names.size() != planes.size()) { err = "bad image for exrWrite"; return false; }
+	if(type != EXR_HALF && type != EXR_FLOAT) { err = "exrWrite: HALF or FLOAT channels only"; return false; }
+	if(compression != EXR_NONE && compression != EXR_ZIP && compression != EXR_ZIPS) { err = "exrWrite: NONE, ZIPS or ZIP only"; return false; }
+	std::vector<size_t> order(names.size()); // the channel list is alphabetical in the file
+	for(size_t i = 0; i < order.size(); ++i) order[i] = i;
+	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return names[a] < names[b]; });
+	std::vector<uint8_t> head;
+	put32(head, 20000630u);
+	put32(head, 2u);
+	{
+		std::vector<uint8_t> p;
+		for(size_t i : order)
+		{
+			putStr(p, names[i].c_str());
+			put32(p, (uint32_t)type);
+			put32(p, 0u); // pLinear + reserved
+			put32(p, 1u);
+			put32(p, 1u);
+		}
+		p.push_back(0);
+		attr(head, "channels", "chlist", p);
+	}
+	attr(head, "compression", "compression", std::vector<uint8_t>(1, (uint8_t)compression));
+	{
+		std::vector<uint8_t> p;
+		put32(p, 0u); put32(p, 0u); put32(p, (uint32_t)(width - 1)); put32(p, (uint32_t)(height - 1));
+		attr(head, "dataWindow", "box2i", p);
+		attr(head, "displayWindow", "box2i", p);
+	}
+	attr(head, "lineOrder", "lineOrder", std::vector<uint8_t>(1, 0));
+	{
+		std::vector<uint8_t> p;
+		putF32(p, 1.f);
+		attr(head, "pixelAspectRatio", "float", p);
+		attr(head, "screenWindowWidth", "float", p);
+		std::vector<uint8_t> c;
+		putF32(c, 0.f); putF32(c, 0.f);
+		attr(head, "screenWindowCenter", "v2f", c);
+	}
+	head.push_back(0);
+	const int lpc = linesPerChunk(compression), nChunks = (height + lpc - 1) / lpc;
+	const size_t px = type == EXR_HALF ? 2 : 4, lineBytes = (size_t)width * px * names.size();
+	std::vector<std::vector<uint8_t> > chunks(nChunks);
+	std::vector<uint8_t> raw, t;
+	for(int i = 0; i < nChunks; ++i)
+	{
+		const int y0 = i * lpc, lines = std::min(lpc, height - y0);
+		raw.resize(lineBytes * lines);
+		uint8_t* o = raw.data();
+		for(int l = 0; l < lines; ++l)
+			for(size_t ci : order)
+			{
+				const float* src = planes[ci] + (size_t)(y0 + l) * width;
+				if(type == EXR_HALF)
+					for(int x = 0; x < width; ++x)
+					{
+						const unsigned short hv = floatToHalf(src[x]);
+						*o++ = (uint8_t)(hv & 0xff);
+						*o++ = (uint8_t)(hv >> 8);
+					}
+				else
+					for(int x = 0; x < width; ++x)
+					{
+						uint32_t v;
+						memcpy(&v, src + x, 4);
+						for(int k = 0; k < 4; ++k) *o++ = (uint8_t)(v >> (8 * k));
+					}
+			}
+		std::vector<uint8_t>& c = chunks[i];
+		put32(c, (uint32_t)y0);
+		bool stored = false;
+		if(compression != EXR_NONE)
+		{
+			applySplitAndPredictor(raw.data(), raw.size(), t);
+			uLongf cap = compressBound((uLong)t.size());
+			std::vector<uint8_t> z(cap);
+			if(compress(z.data(), &cap, t.data(), (uLong)t.size()) == Z_OK && cap < raw.size())
+			{
+				put32(c, (uint32_t)cap);
+				c.insert(c.end(), z.begin(), z.begin() + cap);
+				stored = true;
+			}
+		}
+		if(!stored)
+		{
+			put32(c, (uint32_t)raw.size());
+			c.insert(c.end(), raw.begin(), raw.end());
+		}
+	}
+	FILE* f = fopen(path, "wb");
+	if(!f) { err = std::string("cannot write '") + path + "'"; return false; }
+	bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+	uint64_t pos = head.size() + 8ull * nChunks;
+	for(int i = 0; i < nChunks && ok; ++i)
+	{
+		uint8_t b[8];
+		for(int k = 0; k < 8; ++k) b[k] = (uint8_t)(pos >> (8 * k));
+		ok = fwrite(b, 1, 8, f) == 8;
+		pos += chunks[i].size();
+	}
+	for(int i = 0; i < nChunks && ok; ++i)
+		ok = fwrite(chunks[i].data(), 1, chunks[i].size(), f) == chunks[i].size();
+	ok = (fclose(f) == 0) && ok;
+	if(!ok) err = std::string("error while writing '") + path + "'";
+	return ok;
+}
+
+} // namespace bcdio

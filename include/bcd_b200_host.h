@@ -33,6 +33,20 @@ int bcd_host_cxx_denoise(const float* color, const float* nsamples, const float*
                          float tau, int patch_radius, int search_radius, float min_eig, int random_order, float skip_prob,
                          int nb_scales, int device, float* out_rgb, int* progress_calls);
 
+/* bcd::ImageIO from C (tests): load returns 1 and the image size (HWC float32; multi_channel = 0: R,G,B file -> depth 3,
+ * or 1 for a grey file; 1: Bin_%04d file), fetch copies the pixels of the image loaded last by this thread; write
+ * returns 1 on success. bcd_host_exr_last_error: message of the last failure. */
+int bcd_host_exr_load(const char* path, int multi_channel, int* width, int* height, int* depth);
+int bcd_host_exr_fetch(float* out_hwc);
+int bcd_host_exr_write(const char* path, int multi_channel, const float* hwc, int width, int height, int depth);
+const char* bcd_host_exr_last_error(void);
+
+/* bcd::ParametersIO from C (tests). v[11] = {performSpikeRemoval, spikeRemovalThresholdStDevFactor, nbOfScales,
+ * histoDistanceThreshold, useCuda, nbOfCores, patchRadius, searchWindowRadius, randomPixelOrder,
+ * markedPixelsSkippingProbability, minEigenValue}: on load, in = the values a missing key keeps, out = the result. */
+int bcd_host_params_load(const char* path, double* v, char* color_file, char* hist_file, char* cov_file, int cap);
+int bcd_host_params_write(const char* path, const double* v, const char* color_file, const char* hist_file, const char* cov_file);
+
 #ifdef __cplusplus
 }
 #endif

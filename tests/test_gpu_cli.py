@@ -1,0 +1,81 @@
+"""SURVEY §8 row f2 on the GPU: the command-line front end end to end — EXR files in, bcd_cli, EXR file out — against
+the same run made through the C ABI on what the files hold (the colour file is HALF, like the reference's), and
+against the unmodified reference's output of the crop (tests/golden) at the precision the HALF files allow."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import inputs_of
+import oracles as O
+from bcd_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BCD_CLI = os.path.join(ROOT, "bin", "bcd_cli")
+
+
+def as_half(a):
+    with np.errstate(over="ignore"):
+        return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from bcd_b200 import capi
+    if capi.lib().bcd_b200_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return capi
+
+
+def write_inputs(tmp_path, inp):
+    host.exr_write(str(tmp_path / "frame.exr"), inp["color"], False)
+    host.exr_write(str(tmp_path / "frame_hist.exr"), np.concatenate([inp["hist"], inp["nsamples"]], axis=2), True)
+    host.exr_write(str(tmp_path / "frame_cov.exr"), inp["cov"], True)
+
+
+def cli(args):
+    r = subprocess.run([BCD_CLI] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    return r
+
+
+def test_cli_single_scale_matches_c_abi_and_reference(capi, crop_a, tmp_path):
+    inp = inputs_of(crop_a)
+    write_inputs(tmp_path, inp)
+    out = str(tmp_path / "out.exr")
+    # -h / -c are derived from the colour file name (main.cpp:345-371); -r 1 is accepted (raster order is realised)
+    r = cli(["-o", out, "-i", str(tmp_path / "frame.exr"), "-s", "1", "-m", "0", "-p", "0", "-r", "1"])
+    assert "assuming" in r.stdout and "Written denoised output in file" in r.stdout
+    got = host.exr_load(out, False)
+    on_disk = dict(inp, color=as_half(inp["color"]))
+    direct = np.maximum(capi.denoise(**on_disk, m=0.0, scales=1), 0.0)
+    assert O.rel_linf(got, as_half(direct)) <= 1e-3          # one binary16 ulp: float atomics may flip a rounding
+    assert (got == as_half(direct)).mean() > 0.99
+    assert O.rel_linf(got, crop_a["ref_s1_m0"]) <= 3e-3     # the reference's output, through HALF files both ways
+
+
+def test_cli_full_pipeline_with_prefilter_and_preset(capi, crop_a, tmp_path):
+    inp = inputs_of(crop_a)
+    write_inputs(tmp_path, inp)
+    preset = str(tmp_path / "shot.bcd.json")
+    vals = dict(zip(host.PARAM_KEYS, (1, 2.0, 3, 1.0, 1, 0, 1, 6, 0, 1.0, 1e-8)))
+    assert host.params_write(preset, vals, str(tmp_path / "frame.exr"), str(tmp_path / "frame_hist.exr"), str(tmp_path / "frame_cov.exr"))
+    out = str(tmp_path / "out.exr")
+    cli(["-a", preset, "-o", out])
+    got = host.exr_load(out, False)
+    h = capi.Handle(0)
+    try:
+        h.upload(**dict(inp, color=as_half(inp["color"])))
+        h.spike_removal(factor=2.0)
+        h.run(m=1.0, scales=3)
+        direct = np.maximum(h.download(), 0.0)
+    finally:
+        h.close()
+    assert O.rel_linf(got, as_half(direct)) <= 1e-3
+    # an option after the preset overrides it
+    cli(["-a", preset, "-s", "1", "-p", "0", "-m", "0", "-o", out])
+    single = host.exr_load(out, False)
+    assert O.rel_linf(single, crop_a["ref_s1_m0"]) <= 3e-3
