@@ -120,9 +120,22 @@ __device__ void gatherPatches(const float* __restrict__ color, const LevelGeom& 
 	if(i0 >= groups)
 		return;
 	const int k = jj / 3, ch = jj - 3 * k;
-	const int off = ((k / pw - g.w) * g.W + (k % pw - g.w)) * 3 + ch;
-	for(int i = i0; i < n; i += groups)
-		X[i * d + jj] = __ldg(color + (size_t)qbase[i] * 3 + off);
+	// element index in 32-bit unsigned arithmetic (W * H <= 2^30, checkImages: 3 W H < 2^32; a negative offset wraps back)
+	const unsigned off = (unsigned)(((k / pw - g.w) * g.W + (k % pw - g.w)) * 3 + ch);
+	// the gather is latency-bound (L2 hits behind an index load): four independent loads in flight per thread
+	int i = i0;
+	for(; i + 3 * groups < n; i += 4 * groups)
+	{
+		const unsigned e0 = (unsigned)qbase[i] * 3u + off, e1 = (unsigned)qbase[i + groups] * 3u + off;
+		const unsigned e2 = (unsigned)qbase[i + 2 * groups] * 3u + off, e3 = (unsigned)qbase[i + 3 * groups] * 3u + off;
+		const float v0 = __ldg(color + e0), v1 = __ldg(color + e1), v2 = __ldg(color + e2), v3 = __ldg(color + e3);
+		X[i * d + jj] = v0;
+		X[(i + groups) * d + jj] = v1;
+		X[(i + 2 * groups) * d + jj] = v2;
+		X[(i + 3 * groups) * d + jj] = v3;
+	}
+	for(; i < n; i += groups)
+		X[i * d + jj] = __ldg(color + ((unsigned)qbase[i] * 3u + off));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -396,7 +409,8 @@ k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov
 // DT = compile-time d (27): lane r of a group keeps row r of Minv in registers for the whole pixel (the products
 // then need one broadcast LDS.128 of the 4 centred patches per 4 FMAs and no Minv traffic); DT = 0: Minv in shared memory.
 template <int NT, int GS, int STEP, int DT>
-__global__ void __launch_bounds__(NT)
+// d = 27: 72 registers (7 CTAs of 128 threads per SM; without the bound step 1 takes 96 and only 5 fit)
+__global__ void __launch_bounds__(NT, DT > 0 ? 7 : 1)
 k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ smask, LevelGeom g,
 		const int* __restrict__ list, int first, int count,
 		float* __restrict__ A, const float* __restrict__ MinvG, float* __restrict__ meanG,
@@ -502,10 +516,13 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 			if(STEP == 2)
 			{
 				__syncthreads();
-				for(int e = gl; e < nv * np; e += GS)
+				// compile-time patch geometry for the common widths: the two divisions become multiplications
+				constexpr int NPC = DT / 3, PWC = DT == 27 ? 3 : DT == 75 ? 5 : DT == 147 ? 7 : 0;
+				const int npv = PWC ? NPC : np, pwv = PWC ? PWC : pw;
+				for(int e = gl; e < nv * npv; e += GS)
 				{
-					const int pi = e / np, k = e - pi * np;
-					const size_t x = (size_t)(s.qbase[ib + pi] + (k / pw - g.w) * g.W + (k % pw - g.w));
+					const int pi = e / npv, k = e - pi * npv;
+					const size_t x = (size_t)(s.qbase[ib + pi] + (k / pwv - g.w) * g.W + (k % pwv - g.w));
 					const float4 zr = zv4[3 * k], zg = zv4[3 * k + 1], zb = zv4[3 * k + 2];
 					const float r = pi == 0 ? zr.x : pi == 1 ? zr.y : pi == 2 ? zr.z : zr.w;
 					const float gg = pi == 0 ? zg.x : pi == 1 ? zg.y : pi == 2 ? zg.z : zg.w;
