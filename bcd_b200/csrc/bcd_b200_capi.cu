@@ -76,6 +76,9 @@ struct LevelBufs
 	DevBuf out;                                                                      // W*H*3
 	// per-level state of the hot path (kept per level so that the stages of different levels can overlap)
 	DevBuf smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr;
+	// private pair-term planes / half masks of a coarser level whose selection runs band by band under a streamed upload,
+	// interleaved with the level-0 bands that use the shared scratch (allocated on first use)
+	DevBuf sPl, cPl, mplusl;
 	DeviceCounters* hostCtr = nullptr; // pinned read-back of ctr
 	DeviceCounters counters;           // host copy used to size the filter launches
 	cudaEvent_t evSel = nullptr, evMark = nullptr;
@@ -114,6 +117,8 @@ struct bcd_b200_handle
 		cudaStream_t sel = nullptr;
 		cudaEvent_t evPair[16] = {};
 		cudaEvent_t evSelDone = nullptr;
+		int coarseDone = 0; // levels 1..coarseDone had their selection streamed behind the level-0 bands of this run
+		cudaStream_t coarse = nullptr; // the stream of that work
 	} up;
 	int filterChunk = 0;
 	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
@@ -249,16 +254,19 @@ int finishUpload(bcd_b200_handle* h)
 constexpr int UPLOAD_HALO = 16;
 
 // K1b + K1c on the rows [r0, r1) of the level (the whole selection region when r0 < 0)
-int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st)
+int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st, bool privateScratch = false)
 {
 	LevelBufs& L = h->levels[k];
 	LevelGeom g = levelGeom(h, k, p);
 	const int fastLayout = markingPreLayout(g.b);
 	LevelGeom gb = g;
 	if(r0 >= 0) { gb.yLo = r0; gb.yHi = r1; }
+	const float* sP = privateScratch ? L.sPl.as<float>() : h->sP.as<float>();
+	const unsigned char* cP = privateScratch ? L.cPl.as<unsigned char>() : h->cP.as<unsigned char>();
+	uint32_t* mplus = privateScratch ? L.mplusl.as<uint32_t>() : h->mplus.as<uint32_t>();
 	STAGE_ON(h, st, BCD_B200_STAGE_SELECT, {
-		CU(launchPatchSelect(h->sP.as<float>(), h->cP.as<unsigned char>(), gb, p.tau, h->mplus.as<uint32_t>(), st, &h->launches));
-		CU(launchSymmetrize(h->mplus.as<uint32_t>(), g, L.smask.as<uint32_t>(), L.counts.as<int>(),
+		CU(launchPatchSelect(sP, cP, gb, p.tau, mplus, st, &h->launches));
+		CU(launchSymmetrize(mplus, g, L.smask.as<uint32_t>(), L.counts.as<int>(),
 				L.pre.as<uint32_t>(), prePitchOf(g.W), fastLayout, st, &h->launches, gb.yLo, gb.yHi));
 	});
 	return 0;
@@ -279,7 +287,60 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // upload band: the pair terms of band [r0, r1) read histogram rows < min(H, r1 + b) (band heights are multiples of the
 // tile height), and the patch selection of a band follows as soon as the pair terms of the next band (its w halo rows)
 // are there — so only the last band's kernels run after the transfer.
-int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+bool g_streamCoarse = true; // BCD_B200_STREAM_COARSE=0: coarser levels start their selection after the upload (A/B hook)
+
+// Under a streamed upload the coarser levels do not have to wait for the frame either: rows < rowEnd >> k of level k
+// can be downscaled as soon as the level-0 chunk ending at rowEnd has landed (histogram + sample counts only), and
+// their pair terms / selection follow band by band like level 0's — on the main stream, in the gaps the transfer-bound
+// level-0 bands leave. State of one coarser level while the bands go through:
+struct CoarseStream { int histRows = 0, pairRows = 0, selLo = 0, selHi = 0; };
+
+int coarseBand(bcd_b200_handle* h, const bcd_b200_params& p, int k, int availRows, bool last, CoarseStream& cs)
+{
+	const LevelBufs& Lp = h->levels[k - 1];
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	cudaStream_t st = h->up.coarse; // its own stream: small kernels that fill the gaps of the level-0 chain, never delay it
+	int rc;
+	const int avail = last ? g.H : std::min(g.H, availRows);
+	// pair terms of rows [pairRows, pairEnd) read histogram rows < pairEnd + b; bands end on multiples of 8 rows and are
+	// at least COARSE_MIN_BAND rows tall (a band of a few rows cannot fill the device)
+	constexpr int COARSE_MIN_BAND = 64;
+	const int pairEnd = last ? g.H : std::max(cs.pairRows, (avail - UPLOAD_HALO) & ~7);
+	if(!last && pairEnd - cs.pairRows < COARSE_MIN_BAND)
+		return 0;
+	if(avail > cs.histRows)
+	{
+		STAGE_ON(h, st, BCD_B200_STAGE_PYRAMID, {
+			CU(launchDownscale(Lp.color, Lp.ns, Lp.hist, Lp.cov, Lp.W, Lp.H, h->B, L.ownColor.as<float>(), L.ownNs.as<float>(),
+					L.ownHist.as<float>(), L.ownCov.as<float>(), st, &h->launches, 1, cs.histRows, avail - cs.histRows));
+		});
+		cs.histRows = avail;
+	}
+	if(pairEnd > cs.pairRows)
+	{
+		LevelGeom gb = g;
+		gb.yLo = cs.pairRows;
+		gb.yHi = pairEnd;
+		STAGE_ON(h, st, BCD_B200_STAGE_PAIR, {
+			CU(launchPairTerms(L.hist, L.ns, gb, L.sPl.as<float>(), L.cPl.as<unsigned char>(), st, &h->launches));
+		});
+		// the selection of the previous band needed this band's pair terms for its w halo rows
+		if(cs.selHi > cs.selLo && (rc = patchSelectRows(h, k, p, cs.selLo, cs.selHi, st, true))) return rc;
+		cs.selLo = cs.pairRows;
+		cs.selHi = pairEnd;
+		cs.pairRows = pairEnd;
+	}
+	if(last)
+	{
+		if(cs.selHi > cs.selLo && (rc = patchSelectRows(h, k, p, cs.selLo, cs.selHi, st, true))) return rc;
+		cs.selLo = cs.selHi;
+		CU(cudaEventRecord(L.evSel, st));
+	}
+	return 0;
+}
+
+int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p, int coarseLevels = 0)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
@@ -288,6 +349,22 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	if(h->up.pending && h->up.bands <= 1)
 		if((rc = finishUpload(h))) return rc;
 	if((rc = clearPre(h, k, p))) return rc;
+	h->up.coarseDone = 0;
+	CoarseStream coarse[16];
+	if(k == 0 && h->up.pending && coarseLevels > 0 && g_streamCoarse && !h->tiled)
+	{
+		for(int l = 1; l <= coarseLevels; ++l)
+		{
+			LevelBufs& Ll = h->levels[l];
+			const LevelGeom gl = levelGeom(h, l, p);
+			const size_t npl = std::max<size_t>((size_t)gl.W * gl.H, 1);
+			CU(Ll.sPl.reserve(npl * gl.J * sizeof(float)));
+			CU(Ll.cPl.reserve(npl * gl.J));
+			CU(Ll.mplusl.reserve(npl * gl.Jw * 4));
+			if((rc = clearPre(h, l, p))) return rc;
+		}
+		h->up.coarseDone = coarseLevels;
+	}
 	if(k == 0 && h->up.pending)
 	{
 		// chunk i of the upload ends UPLOAD_HALO rows below band i of the kernels, so band i waits for chunk i only; the
@@ -297,6 +374,8 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		cudaStream_t sel = up.sel;
 		CU(cudaEventRecord(up.evOrder, st)); // `pre` cleared, previous users of the scratch done
 		CU(cudaStreamWaitEvent(sel, up.evOrder, 0));
+		if(up.coarseDone > 0)
+			CU(cudaStreamWaitEvent(up.coarse, up.evOrder, 0));
 		int r0 = g.yLo, prev0 = 0, prev1 = 0;
 		const int nb = up.bands;
 		for(int i = 0; i < nb; ++i)
@@ -304,20 +383,29 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 			// band = rows of chunk i minus the look-ahead, clipped to the rows the selection runs on (row tiles)
 			const int r1 = std::min(g.yHi, i == nb - 1 ? g.H : up.rowEnd[i] - UPLOAD_HALO);
 			CU(cudaStreamWaitEvent(st, up.ev[i], 0));
-			if(r1 <= r0)
-				continue;
-			LevelGeom gb = g;
-			gb.yLo = r0;
-			gb.yHi = r1;
-			STAGE(h, BCD_B200_STAGE_PAIR, {
-				CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
-			});
-			CU(cudaEventRecord(up.evPair[i], st));
-			CU(cudaStreamWaitEvent(sel, up.evPair[i], 0));
-			if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
-			prev0 = r0;
-			prev1 = r1;
-			r0 = r1;
+			if(r1 > r0)
+			{
+				LevelGeom gb = g;
+				gb.yLo = r0;
+				gb.yHi = r1;
+				STAGE(h, BCD_B200_STAGE_PAIR, {
+					CU(launchPairTerms(L.hist, L.ns, gb, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+				});
+				CU(cudaEventRecord(up.evPair[i], st));
+				CU(cudaStreamWaitEvent(sel, up.evPair[i], 0));
+				if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+				prev0 = r0;
+				prev1 = r1;
+				r0 = r1;
+			}
+			// the coarser levels follow on the main stream: level l can use the rows < rowEnd[i] >> l
+			// (level l + 1 is built from the rows of level l that have been downscaled so far)
+			CU(cudaStreamWaitEvent(up.coarse, up.ev[i], 0));
+			for(int l = 1; l <= up.coarseDone; ++l)
+			{
+				const int avail = l == 1 ? up.rowEnd[i] >> 1 : coarse[l - 1].histRows >> 1;
+				if((rc = coarseBand(h, p, l, avail, i == nb - 1, coarse[l]))) return rc;
+			}
 		}
 		if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
 		CU(cudaEventRecord(up.evSelDone, sel));
@@ -735,6 +823,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 	{
 		const char* e = getenv("BCD_B200_DENSE_PAIR");
 		g_forceDensePair = e && e[0] == '1';
+		e = getenv("BCD_B200_STREAM_COARSE");
+		g_streamCoarse = !(e && e[0] == '0');
 		e = getenv("BCD_B200_PAIR");
 		g_pairKernel = (e && !strcmp(e, "v1")) ? 1 : 2;
 		e = getenv("BCD_B200_GENERIC_MARKING");
@@ -786,13 +876,14 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	for(int i = 0; i < 16; ++i) if(h->up.evPair[i]) cudaEventDestroy(h->up.evPair[i]);
 	if(h->up.evSelDone) cudaEventDestroy(h->up.evSelDone);
 	if(h->up.sel) { cudaStreamSynchronize(h->up.sel); cudaStreamDestroy(h->up.sel); }
+	if(h->up.coarse) { cudaStreamSynchronize(h->up.coarse); cudaStreamDestroy(h->up.coarse); }
 	if(h->up.evAll) cudaEventDestroy(h->up.evAll);
 	if(h->up.evOrder) cudaEventDestroy(h->up.evOrder);
 	if(h->up.copy) cudaStreamDestroy(h->up.copy);
 	for(auto& L : h->levels)
 	{
 		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.altColor, &L.altNs, &L.altHist, &L.altCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
-				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr};
+				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr, &L.sPl, &L.cPl, &L.mplusl};
 		for(DevBuf* b : lb) b->release();
 		if(L.hostCtr) cudaFreeHost(L.hostCtr);
 		if(L.evSel) cudaEventDestroy(L.evSel);
@@ -871,6 +962,7 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 			CU(cudaStreamCreateWithPriority(&up.sel, cudaStreamNonBlocking, hi));
 		}
 		CU(cudaEventCreateWithFlags(&up.evSelDone, cudaEventDisableTiming));
+		CU(cudaStreamCreateWithFlags(&up.coarse, cudaStreamNonBlocking));
 		for(int i = 0; i < 16; ++i)
 		{
 			CU(cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming));
@@ -988,11 +1080,24 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	// Phase 1 — everything that needs only histograms and sample counts, finest level first: under a streamed upload
 	// the level-0 kernels start as soon as the first row bands have landed, and the coarser levels' selection runs while
 	// covariance and colour are still in flight. Each level's marking chain (K2) follows on its own high-priority stream.
+	int streamedCoarse = 0; // levels 1..streamedCoarse: selection already enqueued behind the level-0 bands
 	for(int k = 0; k < s; ++k)
 	{
-		if(k > 0 && (rc = pyramidLevel(h, k, 1))) return rc;
-		if((rc = levelClear(h, k, *p))) return rc;
-		if((rc = levelPairAndPatchSelect(h, k, *p))) return rc;
+		if(k == 0 || k > streamedCoarse)
+		{
+			if(k > 0 && (rc = pyramidLevel(h, k, 1))) return rc;
+			if((rc = levelClear(h, k, *p))) return rc;
+			if((rc = levelPairAndPatchSelect(h, k, *p, k == 0 ? s - 1 : 0))) return rc;
+			if(k == 0) streamedCoarse = h->up.coarseDone;
+		}
+		else
+		{
+			// accumulator / bit-rows / counters are untouched by the selection, but the marking stream must not start
+			// before they are cleared: re-record the level's selection event behind the clear
+			CU(cudaStreamWaitEvent(st, h->levels[k].evSel, 0)); // selection of level k (coarse stream) done
+			if((rc = levelClear(h, k, *p))) return rc;
+			CU(cudaEventRecord(h->levels[k].evSel, st));
+		}
 		if((rc = levelMarkEnqueue(h, k, *p))) return rc;
 	}
 	// Phase 2 — colour + covariance: rest of the pyramid (MultiscaleDenoiser.cpp:41-48), per-pixel covariances, filters.

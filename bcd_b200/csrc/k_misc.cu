@@ -230,12 +230,15 @@ cudaError_t launchSpikeFilter(const float* color, const float* ns, const float* 
 __device__ __forceinline__ int clampi(int v, int n) { return v <= 0 ? 0 : (v >= n ? n - 1 : v); }
 
 // mode 0: sum (histogram, nSamples)  1: 0.25 * sum (colour)
-__global__ void k_downscale(const float* __restrict__ in, int W, int H, int D, int mode, float* __restrict__ out)
+// rows [rowBeg, rowBeg + rows) of the downscaled image
+__global__ void k_downscale(const float* __restrict__ in, int W, int H, int D, int mode, float* __restrict__ out,
+		int rowBeg, int rows)
 {
-	const int Wd = W / 2, Hd = H / 2;
-	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= (size_t)Wd * Hd * D)
+	const int Wd = W / 2;
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= (size_t)Wd * rows * D)
 		return;
+	i += (size_t)rowBeg * Wd * D;
 	const int z = (int)(i % D);
 	const size_t pix = i / D;
 	const int c = (int)(pix % Wd), l = (int)(pix / Wd);
@@ -269,21 +272,22 @@ __global__ void k_downscale_cov(const float* __restrict__ cov, const float* __re
 }
 
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
-		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts)
+		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts, int rowBeg, int rows)
 {
-	const size_t npd = (size_t)(W / 2) * (H / 2);
-	if(npd == 0)
+	if(rows < 0) { rowBeg = 0; rows = H / 2; } // the whole level (only part 1 takes a row range)
+	const size_t npd = (size_t)(W / 2) * (H / 2), npr = (size_t)(W / 2) * rows;
+	if(npd == 0 || npr == 0)
 		return cudaSuccess;
 	auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
 	if(parts & 1) // what the selection stage of the coarser level reads
 	{
-		k_downscale<<<blocks(npd), 256, 0, st>>>(ns, W, H, 1, 0, nsD);
-		k_downscale<<<blocks(npd * B), 256, 0, st>>>(hist, W, H, B, 0, histD);
+		k_downscale<<<blocks(npr), 256, 0, st>>>(ns, W, H, 1, 0, nsD, rowBeg, rows);
+		k_downscale<<<blocks(npr * B), 256, 0, st>>>(hist, W, H, B, 0, histD, rowBeg, rows);
 		*launches += 2;
 	}
 	if(parts & 2) // what its filters read
 	{
-		k_downscale<<<blocks(npd * 3), 256, 0, st>>>(color, W, H, 3, 1, colorD);
+		k_downscale<<<blocks(npd * 3), 256, 0, st>>>(color, W, H, 3, 1, colorD, 0, H / 2);
 		k_downscale_cov<<<blocks(npd * 6), 256, 0, st>>>(cov, ns, W, H, covD);
 		*launches += 2;
 	}
@@ -327,7 +331,7 @@ cudaError_t launchMerge(float* hi, int W, int H, const float* lowOut, float* tmp
 	const size_t npd = (size_t)(W / 2) * (H / 2);
 	if(npd == 0)
 		return cudaSuccess;
-	k_downscale<<<(unsigned)((npd * 3 + 255) / 256), 256, 0, st>>>(hi, W, H, 3, 1, tmpLow);
+	k_downscale<<<(unsigned)((npd * 3 + 255) / 256), 256, 0, st>>>(hi, W, H, 3, 1, tmpLow, 0, H / 2);
 	k_merge<<<(unsigned)(((size_t)W * H * 3 + 255) / 256), 256, 0, st>>>(hi, W, H, tmpLow, lowOut);
 	*launches += 2;
 	return cudaGetLastError();

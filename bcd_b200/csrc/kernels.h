@@ -71,7 +71,8 @@ cudaError_t launchSpikeFilter(const float* color, const float* ns, const float* 
 		float factor, int intAbs, int* src, float* colorOut, float* nsOut, float* histOut, float* covOut, cudaStream_t st, int* launches);
 // K5 pyramid down, K6 merge
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
-		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts = 3);
+		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts = 3,
+		int rowBeg = 0, int rows = -1); // rows >= 0: only these rows of the coarser level (part 1)
 cudaError_t launchMerge(float* hi, int W, int H, const float* lowOut, float* tmpLow, cudaStream_t st, int* launches);
 
 } // namespace bcdk

@@ -255,6 +255,33 @@ def test_streamed_upload_matches_serial_upload(capi, crop_a):
     assert np.array_equal(back["hist"], inp["hist"]) and np.array_equal(back["color"], inp["color"])
 
 
+@pytest.mark.parametrize("size", [(640, 400), (333, 517)])
+def test_streamed_upload_streams_the_coarser_levels_too(capi, size, monkeypatch):
+    """Under bcd_b200_upload_async the selection of the coarser pyramid levels also runs band by band behind the arriving
+    rows (bcd_b200_capi.cu: coarseBand), on frames tall enough for a dozen upload chunks and odd sizes: identical work
+    counters on every level, identical level-0 selection, same output as the serial upload and as the A/B hook."""
+    from bcd_b200 import host
+    W, H = size
+    inp = host.synth(W, H, spp=16)
+    got = {}
+    for mode in ("serial", "streamed", "streamed_no_coarse"):
+        monkeypatch.setenv("BCD_B200_STREAM_COARSE", "0" if mode == "streamed_no_coarse" else "1")
+        h = capi.Handle(0)
+        try:
+            (h.upload if mode == "serial" else h.upload_async)(**inp)
+            h.run(m=1.0, scales=3)
+            got[mode] = (h.download(), h.stats(), h.read_selection())
+        finally:
+            h.close()
+    monkeypatch.setenv("BCD_B200_STREAM_COARSE", "1")
+    capi.Handle(0).close()  # reset the process-wide hook
+    for mode in ("streamed", "streamed_no_coarse"):
+        for key in ("interior", "strong", "active", "full", "fallback", "sum_n_full"):
+            assert got[mode][1][key] == got["serial"][1][key], (mode, key)
+        assert np.array_equal(got[mode][2][0], got["serial"][2][0]) and np.array_equal(got[mode][2][1], got["serial"][2][1])
+        assert O.rel_linf(got[mode][0], got["serial"][0]) <= 1e-5  # float atomics only
+
+
 @pytest.mark.parametrize("group", [8, 16, 32])
 def test_eig_chain_layouts_agree_with_reference(capi, crop_a, crop_b, group, monkeypatch):
     """K3e: 4 / 2 / 1 matrices per warp (k_eig_sub.cu, k_filter.cu) — each within tolerance of the reference golden,
