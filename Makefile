@@ -12,7 +12,7 @@ KOBJ = $(CSRC)/k_distance.o $(CSRC)/k_misc.o $(CSRC)/k_marking.o $(CSRC)/k_filte
 HOSTSRC = $(wildcard bcd_b200/host/*.cpp) $(wildcard bcd_b200/io/*.cpp)
 HOSTINC = -Iinclude -Iinclude/bcd/core -Iinclude/bcd/io -Ibcd_b200/io
 
-all: bcd_b200/libbcd_b200.so bcd_b200/libbcdcore_b200.so bin/bcd_cli bin/raw2bcd oracle
+all: bcd_b200/libbcd_b200.so bcd_b200/libbcdcore_b200.so bin/bcd_cli bin/raw2bcd oracle ref_frontends
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/bcd_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
@@ -32,8 +32,26 @@ bin/%: apps/%.cpp bcd_b200/libbcdcore_b200.so
 oracle:
 	$(MAKE) -C oracle all
 
+# TEST INFRASTRUCTURE — the reference's own front-end sources (src/cli/main.cpp, src/raw_converter/main.cpp), UNMODIFIED,
+# compiled against this repository's headers and linked against its libraries: the source-compatibility proof of the
+# drop-in (tests/test_reference_frontends.py, tests/test_gpu_cli.py). Only where /root/reference exists; the binaries
+# land in oracle/_ref/ (git-ignored, they travel to the GPU box). Eigen is on the include path because main.cpp includes
+# <Eigen/Dense> without using it.
+REF ?= /root/reference
+ref_frontends: bcd_b200/libbcdcore_b200.so
+	@if [ -d $(REF)/src/cli ]; then $(MAKE) --no-print-directory oracle/_ref/ref_bcd_cli oracle/_ref/ref_raw2bcd; \
+	 else echo "ref_frontends: $(REF) not present; using prebuilt oracle/_ref/ref_bcd_cli if any"; fi
+
+oracle/_ref/ref_bcd_cli: $(REF)/src/cli/main.cpp bcd_b200/libbcdcore_b200.so $(wildcard include/bcd/core/*.h include/bcd/io/*.h)
+	@mkdir -p oracle/_ref
+	$(CXX) -std=c++11 -O2 -w -include cmath $(HOSTINC) -I$(REF)/ext/eigen -o $@ $< -Lbcd_b200 -lbcdcore_b200 -lbcd_b200 -Wl,-rpath,'$$ORIGIN/../../bcd_b200'
+
+oracle/_ref/ref_raw2bcd: $(REF)/src/raw_converter/main.cpp bcd_b200/libbcdcore_b200.so $(wildcard include/bcd/core/*.h include/bcd/io/*.h)
+	@mkdir -p oracle/_ref
+	$(CXX) -std=c++11 -O2 -w -include cmath $(HOSTINC) -o $@ $< -Lbcd_b200 -lbcdcore_b200 -lbcd_b200 -Wl,-rpath,'$$ORIGIN/../../bcd_b200'
+
 clean:
 	rm -f $(CSRC)/*.o $(CSRC)/*.log bcd_b200/*.so bin/bcd_cli bin/raw2bcd
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle ref_frontends clean

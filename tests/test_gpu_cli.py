@@ -79,3 +79,22 @@ def test_cli_full_pipeline_with_prefilter_and_preset(capi, crop_a, tmp_path):
     cli(["-a", preset, "-s", "1", "-p", "0", "-m", "0", "-o", out])
     single = host.exr_load(out, False)
     assert O.rel_linf(single, crop_a["ref_s1_m0"]) <= 3e-3
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_bcd_cli")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/ref_bcd_cli not built (needs /root/reference at build time)")
+def test_reference_cli_source_linked_against_bcd_b200(capi, crop_a, tmp_path):
+    """The reference's unmodified src/cli/main.cpp, compiled against our headers and linked against our libraries
+    (Makefile: ref_frontends), denoises on the GPU: same pixels as bin/bcd_cli and the reference's golden output."""
+    inp = inputs_of(crop_a)
+    write_inputs(tmp_path, inp)
+    ref_out, our_out = str(tmp_path / "ref_out.exr"), str(tmp_path / "our_out.exr")
+    args = ["-i", str(tmp_path / "frame.exr"), "-s", "1", "-m", "0", "-p", "0", "-r", "0"]
+    r = subprocess.run([REF_CLI, "-o", ref_out] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0 and "Written denoised output in file" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+    cli(["-o", our_out] + args)
+    a, b = host.exr_load(ref_out, False), host.exr_load(our_out, False)
+    assert O.rel_linf(a, b) <= 1e-3 and (a == b).mean() > 0.99       # float atomics may flip a binary16 rounding
+    assert O.rel_linf(a, crop_a["ref_s1_m0"]) <= 3e-3
