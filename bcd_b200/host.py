@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbcdcore_b200.so")
 SYMBOLS = ["bcd_synth_generate", "bcd_host_accumulate", "bcd_host_cxx_denoise", "bcd_host_exr_load", "bcd_host_exr_fetch",
-           "bcd_host_exr_write", "bcd_host_exr_last_error", "bcd_host_params_load", "bcd_host_params_write"]
+           "bcd_host_exr_write", "bcd_host_exr_write_ex", "bcd_host_exr_last_error", "bcd_host_params_load", "bcd_host_params_write"]
 DEFAULT_SEED = 20170627
 _lib = None
 
@@ -29,6 +29,7 @@ def lib():
         L.bcd_host_exr_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.bcd_host_exr_fetch.argtypes = [fp]
         L.bcd_host_exr_write.argtypes = [C.c_char_p, C.c_int, fp, C.c_int, C.c_int, C.c_int]
+        L.bcd_host_exr_write_ex.argtypes = [C.c_char_p, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.bcd_host_exr_last_error.restype = C.c_char_p
         L.bcd_host_params_load.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         L.bcd_host_params_write.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p]
@@ -95,6 +96,15 @@ def exr_write(path, image, multi_channel):
     H, W, D = image.shape
     if not lib().bcd_host_exr_write(os.fsencode(path), int(bool(multi_channel)), image.ctypes.data, W, H, D):
         raise ExrError(lib().bcd_host_exr_last_error().decode("utf-8", "replace"))
+
+
+def exr_write_ex(path, image, multi_channel, pixel_type, compression):
+    """The codec's writer with an explicit pixel type (1 HALF, 2 FLOAT) and compression (0 NONE, 2 ZIPS, 3 ZIP, 4 PIZ)."""
+    image = np.ascontiguousarray(image, np.float32)
+    H, W, D = image.shape
+    if not lib().bcd_host_exr_write_ex(os.fsencode(path), int(bool(multi_channel)), image.ctypes.data, W, H, D,
+                                       int(pixel_type), int(compression)):
+        raise ExrError("exr_write_ex failed")
 
 
 PARAM_KEYS = ("performSpikeRemovalPrefiltering", "spikeRemovalThresholdStDevFactor", "nbOfScales", "histoDistanceThreshold",

@@ -108,7 +108,7 @@ namespace bcd
 		std::vector<std::string> names = {"R", "G", "B", "A"};
 		std::vector<const float*> ptrs = {planes.data(), planes.data() + np, planes.data() + 2 * np, planes.data() + 3 * np};
 		std::string err;
-		if(!bcdio::exrWrite(i_pFilePath, w, h, names, ptrs, bcdio::EXR_HALF, bcdio::EXR_ZIP, err))
+		if(!bcdio::exrWrite(i_pFilePath, w, h, names, ptrs, bcdio::EXR_HALF, bcdio::EXR_PIZ, err)) // RgbaOutputFile's default
 			return failWith(err, i_pFilePath);
 		t_lastError.clear();
 		return true;

@@ -4,9 +4,12 @@
 #include "DeepImage.h"
 #include "ImageIO.h"
 #include "ParametersIO.h"
+#include "exr_codec.h"
 
+#include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 using namespace bcd;
 
@@ -54,6 +57,29 @@ int bcd_host_exr_write(const char* path, int multi_channel, const float* hwc, in
 }
 
 const char* bcd_host_exr_last_error(void) { return ImageIO::lastError().c_str(); }
+
+int bcd_host_exr_write_ex(const char* path, int multi_channel, const float* hwc, int width, int height, int depth,
+		int pixel_type, int compression)
+{
+	if(!hwc || width <= 0 || height <= 0 || depth <= 0 || (!multi_channel && depth != 3)) return 0;
+	const size_t np = (size_t)width * height;
+	std::vector<float> planes((size_t)depth * np);
+	for(size_t i = 0; i < np; ++i)
+		for(int z = 0; z < depth; ++z)
+			planes[z * np + i] = hwc[i * depth + z];
+	std::vector<std::string> names;
+	std::vector<const float*> ptrs;
+	for(int z = 0; z < depth; ++z)
+	{
+		char buf[32];
+		if(multi_channel) snprintf(buf, sizeof buf, "Bin_%04d", z);
+		else snprintf(buf, sizeof buf, "%c", "RGB"[z]);
+		names.push_back(buf);
+		ptrs.push_back(planes.data() + z * np);
+	}
+	std::string err;
+	return bcdio::exrWrite(path, width, height, names, ptrs, (bcdio::ExrPixelType)pixel_type, (bcdio::ExrCompression)compression, err) ? 1 : 0;
+}
 
 int bcd_host_params_load(const char* path, double* v, char* color_file, char* hist_file, char* cov_file, int cap)
 {

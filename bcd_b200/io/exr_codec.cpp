@@ -454,6 +454,274 @@ bool unpizBlock(const uint8_t* src, size_t n, int width, int lines, const std::v
 	return true;
 }
 
+// ---- PIZ, encoding direction (mirror images of the decoders above)
+struct BitOut
+{
+	std::vector<uint8_t>& b;
+	uint64_t acc;
+	int n;
+	uint64_t total;
+	explicit BitOut(std::vector<uint8_t>& buf) : b(buf), acc(0), n(0), total(0) {}
+	void put(int k, uint64_t v) // k <= 58 bits, MSB first
+	{
+		total += (uint64_t)k;
+		while(k > 0)
+		{
+			const int take = std::min(k, 32);
+			acc = (acc << take) | ((v >> (k - take)) & ((1ull << take) - 1));
+			n += take;
+			k -= take;
+			while(n >= 8)
+			{
+				b.push_back((uint8_t)(acc >> (n - 8)));
+				n -= 8;
+			}
+		}
+	}
+	void flush()
+	{
+		if(n > 0) b.push_back((uint8_t)(acc << (8 - n)));
+		n = 0;
+	}
+};
+
+// Huffman code lengths by pairwise merging of the two rarest subtrees (a heap over subtree weights; every merge adds one
+// bit to the symbols of both subtrees, kept as linked lists)
+void huffmanLengths(const std::vector<uint64_t>& freq, std::vector<uint8_t>& len)
+{
+	const size_t n = freq.size();
+	len.assign(n, 0);
+	std::vector<uint32_t> syms;
+	for(uint32_t i = 0; i < n; ++i)
+		if(freq[i]) syms.push_back(i);
+	if(syms.size() == 1) { len[syms[0]] = 1; return; }
+	std::vector<uint32_t> next(n), tail(n);
+	std::vector<uint64_t> weight(n);
+	for(uint32_t i : syms) { next[i] = i; tail[i] = i; weight[i] = freq[i]; } // a list ends when next == itself
+	auto cmp = [&](uint32_t a, uint32_t b) { return weight[a] > weight[b] || (weight[a] == weight[b] && a > b); };
+	std::vector<uint32_t> heap(syms);
+	std::make_heap(heap.begin(), heap.end(), cmp);
+	while(heap.size() > 1)
+	{
+		std::pop_heap(heap.begin(), heap.end(), cmp);
+		const uint32_t a = heap.back();
+		heap.pop_back();
+		std::pop_heap(heap.begin(), heap.end(), cmp);
+		const uint32_t b = heap.back();
+		heap.pop_back();
+		for(uint32_t head : {a, b})
+			for(uint32_t j = head;; j = next[j])
+			{
+				++len[j];
+				if(next[j] == j) break;
+			}
+		next[tail[a]] = b; // concatenate b's list behind a's
+		tail[a] = tail[b];
+		weight[a] += weight[b];
+		heap.push_back(a);
+		std::push_heap(heap.begin(), heap.end(), cmp);
+	}
+}
+
+void hufEncode(const uint16_t* raw, size_t nRaw, std::vector<uint8_t>& out)
+{
+	if(nRaw == 0) return;
+	const uint32_t NSYM = 65537;
+	std::vector<uint64_t> freq(NSYM, 0);
+	for(size_t i = 0; i < nRaw; ++i)
+		freq[raw[i]]++;
+	uint32_t im = 0, iM = 0;
+	while(!freq[im]) ++im;
+	for(uint32_t i = im; i < 65536; ++i)
+		if(freq[i]) iM = i;
+	++iM; // the run-length escape is the symbol after the largest one in use
+	freq[iM] = 1;
+	std::vector<uint8_t> len;
+	huffmanLengths(freq, len);
+	uint64_t count[59] = {0}, first[59] = {0};
+	for(uint32_t s = im; s <= iM; ++s)
+		count[len[s]]++;
+	{
+		uint64_t c = 0;
+		for(int l = 58; l > 0; --l)
+		{
+			first[l] = c;
+			c = (c + count[l]) >> 1;
+		}
+	}
+	std::vector<uint64_t> code(NSYM, 0);
+	{
+		uint64_t nextCode[59];
+		for(int l = 0; l < 59; ++l) nextCode[l] = first[l];
+		for(uint32_t s = im; s <= iM; ++s)
+			if(len[s]) code[s] = nextCode[len[s]]++;
+	}
+	const size_t headerAt = out.size();
+	out.resize(headerAt + 20, 0);
+	// packed code lengths
+	const size_t tableAt = out.size();
+	{
+		BitOut tb(out);
+		for(uint32_t s = im; s <= iM; ++s)
+		{
+			if(len[s] == 0)
+			{
+				uint32_t run = 1;
+				while(s < iM && run < 255 + 6 && len[s + 1] == 0) { ++s; ++run; }
+				if(run >= 6) { tb.put(6, 63); tb.put(8, run - 6); continue; }
+				if(run >= 2) { tb.put(6, 59 + run - 2); continue; }
+			}
+			tb.put(6, len[s]);
+		}
+		tb.flush();
+	}
+	const uint32_t tableLength = (uint32_t)(out.size() - tableAt);
+	BitOut db(out);
+	auto send = [&](uint32_t s, uint32_t extra) // symbol s repeated extra + 1 times
+	{
+		if((uint64_t)len[s] + len[iM] + 8 < (uint64_t)len[s] * extra)
+		{
+			db.put(len[s], code[s]);
+			db.put(len[iM], code[iM]);
+			db.put(8, extra);
+		}
+		else
+			for(uint32_t k = 0; k <= extra; ++k)
+				db.put(len[s], code[s]);
+	};
+	uint32_t s = raw[0], extra = 0;
+	for(size_t i = 1; i < nRaw; ++i)
+	{
+		if(raw[i] == s && extra < 255)
+			++extra;
+		else
+		{
+			send(s, extra);
+			extra = 0;
+		}
+		s = raw[i];
+	}
+	send(s, extra);
+	db.flush();
+	const uint32_t hdr[5] = {im, iM, tableLength, (uint32_t)db.total, 0u};
+	for(int k = 0; k < 5; ++k)
+		for(int b8 = 0; b8 < 4; ++b8)
+			out[headerAt + 4 * k + b8] = (uint8_t)(hdr[k] >> (8 * b8));
+}
+
+inline void wenc14(uint16_t a, uint16_t b, uint16_t& l, uint16_t& h)
+{
+	const int as = (int16_t)a, bs = (int16_t)b;
+	l = (uint16_t)(int16_t)((as + bs) >> 1);
+	h = (uint16_t)(int16_t)(as - bs);
+}
+inline void wenc16(uint16_t a, uint16_t b, uint16_t& l, uint16_t& h)
+{
+	const int ao = (a + 0x8000) & 0xffff;
+	int m = (ao + b) >> 1;
+	int d = ao - b;
+	if(d < 0) m = (m + 0x8000) & 0xffff;
+	d &= 0xffff;
+	l = (uint16_t)m;
+	h = (uint16_t)d;
+}
+
+void waveletEncode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t maxValue)
+{
+	const bool w14 = maxValue < (1 << 14);
+	const int n = nx > ny ? ny : nx;
+	auto enc = [w14](uint16_t a, uint16_t b, uint16_t& l, uint16_t& h) { if(w14) wenc14(a, b, l, h); else wenc16(a, b, l, h); };
+	for(int p = 1, p2 = 2; p2 <= n; p = p2, p2 <<= 1)
+	{
+		const long oy1 = (long)oy * p, oy2 = (long)oy * p2, ox1 = (long)ox * p, ox2 = (long)ox * p2;
+		uint16_t* py = in;
+		uint16_t* const ey = in + (long)oy * (ny - p2);
+		for(; py <= ey; py += oy2)
+		{
+			uint16_t* px = py;
+			uint16_t* const ex = py + (long)ox * (nx - p2);
+			for(; px <= ex; px += ox2)
+			{
+				uint16_t* p01 = px + ox1;
+				uint16_t* p10 = px + oy1;
+				uint16_t* p11 = p10 + ox1;
+				uint16_t i00, i01, i10, i11;
+				enc(*px, *p01, i00, i01);
+				enc(*p10, *p11, i10, i11);
+				enc(i00, i10, *px, *p10);
+				enc(i01, i11, *p01, *p11);
+			}
+			if(nx & p)
+			{
+				uint16_t* p10 = px + oy1;
+				uint16_t i00;
+				enc(*px, *p10, i00, *p10);
+				*px = i00;
+			}
+		}
+		if(ny & p)
+		{
+			uint16_t* px = py;
+			uint16_t* const ex = py + (long)ox * (nx - p2);
+			for(; px <= ex; px += ox2)
+			{
+				uint16_t* p01 = px + ox1;
+				uint16_t i00;
+				enc(*px, *p01, i00, *p01);
+				*px = i00;
+			}
+		}
+	}
+}
+
+// raw: scan-line interleaved little-endian block (lines x channels x width); sizes[c] = bytes per value of channel c
+void pizBlock(const uint8_t* raw, int width, int lines, const std::vector<int>& sizes, std::vector<uint8_t>& out)
+{
+	const size_t nch = sizes.size();
+	std::vector<size_t> startOf(nch + 1, 0);
+	for(size_t c = 0; c < nch; ++c)
+		startOf[c + 1] = startOf[c] + (size_t)width * lines * (sizes[c] / 2);
+	const size_t total = startOf[nch];
+	std::vector<uint16_t> tmp(total);
+	{
+		std::vector<size_t> cur(startOf.begin(), startOf.end() - 1);
+		const uint8_t* s = raw;
+		for(int y = 0; y < lines; ++y)
+			for(size_t c = 0; c < nch; ++c)
+				for(size_t i = 0, cnt = (size_t)width * (sizes[c] / 2); i < cnt; ++i, s += 2)
+					tmp[cur[c]++] = (uint16_t)(s[0] | s[1] << 8);
+	}
+	std::vector<uint8_t> bitmap(8192, 0);
+	for(size_t i = 0; i < total; ++i)
+		bitmap[tmp[i] >> 3] |= (uint8_t)(1u << (tmp[i] & 7));
+	bitmap[0] &= (uint8_t)~1u; // zero is always in the table, never in the bitmap
+	int lo = 8191, hi = 0;
+	for(int i = 0; i < 8192; ++i)
+		if(bitmap[i]) { lo = std::min(lo, i); hi = std::max(hi, i); }
+	std::vector<uint16_t> lut(65536, 0);
+	uint32_t k = 0;
+	for(uint32_t i = 0; i < 65536; ++i)
+		if(i == 0 || (bitmap[i >> 3] & (1u << (i & 7))))
+			lut[i] = (uint16_t)k++;
+	const uint16_t maxValue = (uint16_t)(k - 1);
+	for(size_t i = 0; i < total; ++i)
+		tmp[i] = lut[tmp[i]];
+	for(size_t c = 0; c < nch; ++c)
+		for(int j = 0, size = sizes[c] / 2; j < size; ++j)
+			waveletEncode(tmp.data() + startOf[c] + j, width, size, lines, width * size, maxValue);
+	out.clear();
+	out.push_back((uint8_t)(lo & 0xff)); out.push_back((uint8_t)(lo >> 8));
+	out.push_back((uint8_t)(hi & 0xff)); out.push_back((uint8_t)(hi >> 8));
+	if(lo <= hi)
+		out.insert(out.end(), bitmap.begin() + lo, bitmap.begin() + hi + 1);
+	const size_t lengthAt = out.size();
+	out.resize(lengthAt + 4, 0);
+	hufEncode(tmp.data(), total, out);
+	const uint32_t length = (uint32_t)(out.size() - lengthAt - 4);
+	for(int b8 = 0; b8 < 4; ++b8)
+		out[lengthAt + b8] = (uint8_t)(length >> (8 * b8));
+}
+
 bool readWholeFile(const char* path, std::vector<uint8_t>& buf)
 {
 	FILE* f = fopen(path, "rb");
@@ -632,7 +900,7 @@ bool exrWrite(const char* path, int width, int height, const std::vector<std::st
 {
 	if(width <= 0 || height <= 0 || names.empty() || names.size() != planes.size()) { err = "bad image for exrWrite"; return false; }
 	if(type != EXR_HALF && type != EXR_FLOAT) { err = "exrWrite: HALF or FLOAT channels only"; return false; }
-	if(compression != EXR_NONE && compression != EXR_ZIP && compression != EXR_ZIPS) { err = "exrWrite: NONE, ZIPS or ZIP only"; return false; }
+	if(compression != EXR_NONE && compression != EXR_ZIP && compression != EXR_ZIPS && compression != EXR_PIZ) { err = "exrWrite: NONE, ZIPS, ZIP or PIZ only"; return false; }
 	std::vector<size_t> order(names.size()); // the channel list is alphabetical in the file
 	for(size_t i = 0; i < order.size(); ++i) order[i] = i;
 	std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return names[a] < names[b]; });
@@ -701,7 +969,18 @@ bool exrWrite(const char* path, int width, int height, const std::vector<std::st
 		std::vector<uint8_t>& c = chunks[i];
 		put32(c, (uint32_t)y0);
 		bool stored = false;
-		if(compression != EXR_NONE)
+		if(compression == EXR_PIZ)
+		{
+			std::vector<uint8_t> z;
+			pizBlock(raw.data(), width, lines, std::vector<int>(names.size(), (int)px), z);
+			if(z.size() < raw.size())
+			{
+				put32(c, (uint32_t)z.size());
+				c.insert(c.end(), z.begin(), z.end());
+				stored = true;
+			}
+		}
+		else if(compression != EXR_NONE)
 		{
 			applySplitAndPredictor(raw.data(), raw.size(), t);
 			uLongf cap = compressBound((uLong)t.size());

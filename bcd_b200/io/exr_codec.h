@@ -3,7 +3,7 @@
 //   * colour images:         HALF R,G,B,A scan lines, PIZ compressed (RgbaOutputFile defaults, io_exr.cpp:156-164)
 //   * histogram / covariance: FLOAT channels Bin_0000 .. Bin_NNNN, ZIP compressed (Header defaults, io_exr.cpp:215-236)
 // Reads single-part scan-line files with UINT / HALF / FLOAT channels compressed with NONE, RLE, ZIPS, ZIP or PIZ;
-// writes HALF or FLOAT channels with NONE or ZIP. Tiled, deep, multi-part files and the lossy codecs (PXR24, B44,
+// writes HALF or FLOAT channels with NONE, ZIPS, ZIP or PIZ. Tiled, deep, multi-part files and the lossy codecs (PXR24, B44,
 // DWA) are rejected with a message. The format follows the published OpenEXR file layout; parity is pinned against the
 // reference's own library built in place (oracle/_ref/libexr_ref.so, tests/test_exr_io.py).
 #ifndef BCD_B200_EXR_CODEC_H

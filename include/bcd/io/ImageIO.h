@@ -23,8 +23,7 @@ namespace bcd
 		/// Channels Bin_0000, Bin_0001, ... (as many as are present consecutively) -> W x H x n image.
 		static bool loadMultiChannelsEXR(DeepImage<float>& o_rImage, const char* i_pFilePath);
 
-		/// HALF R, G, B, A (A = 1) like the reference's RgbaOutputFile; a 1-channel image is written as grey.
-		/// Compression is ZIP (lossless) where the reference's library default is PIZ (also lossless).
+		/// HALF R, G, B, A (A = 1), PIZ compressed, like the reference's RgbaOutputFile; a 1-channel image is written as grey.
 		static bool writeEXR(const DeepImage<float>& i_rImage, const char* i_pFilePath);
 		/// FLOAT channels Bin_0000 ... Bin_{depth-1}, ZIP compressed, like the reference.
 		static bool writeMultiChannelsEXR(const DeepImage<float>& i_rImage, const char* i_pFilePath);

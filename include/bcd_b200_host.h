@@ -40,6 +40,10 @@ int bcd_host_exr_load(const char* path, int multi_channel, int* width, int* heig
 int bcd_host_exr_fetch(float* out_hwc);
 int bcd_host_exr_write(const char* path, int multi_channel, const float* hwc, int width, int height, int depth);
 const char* bcd_host_exr_last_error(void);
+/* the codec's writer with an explicit pixel type (1 HALF, 2 FLOAT) and compression (0 NONE, 2 ZIPS, 3 ZIP, 4 PIZ);
+ * multi_channel = 0 needs depth 3 (channels R, G, B) */
+int bcd_host_exr_write_ex(const char* path, int multi_channel, const float* hwc, int width, int height, int depth,
+                          int pixel_type, int compression);
 
 /* bcd::ParametersIO from C (tests). v[11] = {performSpikeRemoval, spikeRemovalThresholdStDevFactor, nbOfScales,
  * histoDistanceThreshold, useCuda, nbOfCores, patchRadius, searchWindowRadius, randomPixelOrder,
