@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
 
 namespace bcdio
 {
@@ -739,7 +740,7 @@ bool readWholeFile(const char* path, std::vector<uint8_t>& buf)
 } // namespace
 
 // ------------------------------------------------------------------------------------------------------- read
-bool exrRead(const char* path, ExrFile& out, std::string& err)
+static bool exrReadBody(const char* path, ExrFile& out, std::string& err)
 {
 	std::vector<uint8_t> buf;
 	if(!readWholeFile(path, buf)) { err = std::string("cannot read '") + path + "'"; return false; }
@@ -804,6 +805,9 @@ bool exrRead(const char* path, ExrFile& out, std::string& err)
 	out.width = (int)w;
 	out.height = (int)h;
 	const size_t nch = out.names.size();
+	// every chunk costs at least its 8-byte header and its table entry: a header whose window cannot fit the file is refused
+	// before anything is allocated
+	if(nch == 0 || nch > 100000 || (uint64_t)((h + lpc - 1) / lpc) * 16 > (uint64_t)buf.size()) { err = "data window does not fit the file"; return false; }
 	size_t lineBytes = 0;
 	for(size_t c = 0; c < nch; ++c)
 		lineBytes += (size_t)w * bytesOf(out.types[c]);
@@ -817,8 +821,8 @@ bool exrRead(const char* path, ExrFile& out, std::string& err)
 	const uint8_t* seq = r.p; // fall back to reading the chunks in file order when the table was never written
 	for(int i = 0; i < nChunks; ++i)
 	{
-		const uint8_t* cp = offsets[i] ? buf.data() + offsets[i] : seq;
 		if(offsets[i] >= buf.size()) { err = "bad chunk offset"; return false; }
+		const uint8_t* cp = offsets[i] ? buf.data() + offsets[i] : seq;
 		Reader c(cp, (size_t)(buf.data() + buf.size() - cp));
 		const int32_t y = c.i32(), n = c.i32();
 		if(!c.ok || n < 0 || !c.need((size_t)n)) { err = "truncated chunk"; return false; }
@@ -866,6 +870,20 @@ bool exrRead(const char* path, ExrFile& out, std::string& err)
 			}
 	}
 	return true;
+}
+
+bool exrRead(const char* path, ExrFile& out, std::string& err)
+{
+	try
+	{
+		return exrReadBody(path, out, err);
+	}
+	catch(const std::bad_alloc&) // a header that announces more pixels than memory can hold
+	{
+		out = ExrFile();
+		err = "image too large for the available memory";
+		return false;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------ write
