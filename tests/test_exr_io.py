@@ -290,6 +290,37 @@ def test_preset_round_trip_and_partial_files(tmp_path):
     assert host.params_load(str(tmp_path / "nope.bcd.json")) is None
 
 
+def test_preset_parser_survives_mutated_text(tmp_path):
+    """Random edits of a valid preset (deleted / duplicated / replaced characters, truncation): load() returns a dict or
+    None, never hangs or crashes, and whatever it accepts keeps the numeric fields finite-or-default typed."""
+    good = open(os.path.join(GOLD, "ref_preset.bcd.json")).read()
+    rng = np.random.default_rng(42)
+    alphabet = list('{}[]",:\\ \n\ttruefalsn0123456789.eE+-u') + ["\\u12", '\\"', "nbOfScales"]
+    p = tmp_path / "m.bcd.json"
+    ok = 0
+    for _ in range(1500):
+        t = list(good)
+        for _ in range(int(rng.integers(1, 6))):
+            i = int(rng.integers(0, len(t)))
+            kind = int(rng.integers(0, 4))
+            if kind == 0:
+                del t[i]
+            elif kind == 1:
+                t.insert(i, alphabet[int(rng.integers(0, len(alphabet)))])
+            elif kind == 2:
+                t[i] = alphabet[int(rng.integers(0, len(alphabet)))]
+            else:
+                t = t[:i]
+            if not t:
+                break
+        p.write_text("".join(t))
+        got = host.params_load(str(p))
+        if got is not None:
+            ok += 1
+            assert set(host.PARAM_KEYS) <= set(got)
+    assert 0 < ok < 1500
+
+
 # --------------------------------------------------------------------------------------------- command lines
 def run(cmd):
     return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
