@@ -408,6 +408,16 @@ k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov
 // ---------------------------------------------------------------------------------------------------------------
 // DT = compile-time d (27): lane r of a group keeps row r of Minv in registers for the whole pixel (the products
 // then need one broadcast LDS.128 of the 4 centred patches per 4 FMAs and no Minv traffic); DT = 0: Minv in shared memory.
+// Synchronisation among the GS threads that share one xcv4 / tv4 / zv4 scratch: a group of 32 is a warp (the d = 27
+// configuration), which lets the four warps of a CTA run through their patches independently instead of in lock-step;
+// wider groups span warps and need the CTA barrier.
+template <int GS>
+__device__ __forceinline__ void groupSync()
+{
+	if(GS == 32) __syncwarp();
+	else __syncthreads();
+}
+
 template <int NT, int GS, int STEP, int DT>
 // d = 27: 72 registers (7 CTAs of 128 threads per SM; without the bound step 1 takes 96 and only 5 fit)
 __global__ void __launch_bounds__(NT, DT > 0 ? 7 : 1)
@@ -460,7 +470,7 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 				const float m = s.mean[c];
 				xcv4[c] = make_float4(__fsub_rn(X0[c], m), __fsub_rn(X1[c], m), __fsub_rn(X2[c], m), __fsub_rn(X3[c], m));
 			}
-			__syncthreads();
+			groupSync<GS>();
 			if(DT > 0)
 			{
 				if(gl < DT)
@@ -488,7 +498,7 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 					}
 					tv4[r] = make_float4(-a0, -a1, -a2, -a3);
 				}
-			__syncthreads();
+			groupSync<GS>();
 			for(int jj = gl; jj < d; jj += GS)
 			{
 				const int k = jj / 3, a3i = jj - 3 * k;
@@ -515,7 +525,7 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 			}
 			if(STEP == 2)
 			{
-				__syncthreads();
+				groupSync<GS>();
 				// compile-time patch geometry for the common widths: the two divisions become multiplications
 				constexpr int NPC = DT / 3, PWC = DT == 27 ? 3 : DT == 75 ? 5 : DT == 147 ? 7 : 0;
 				const int npv = PWC ? NPC : np, pwv = PWC ? PWC : pw;
@@ -533,8 +543,10 @@ k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ sma
 			// STEP 1: rows written above are read again (as X0..X3) only by their own group, in the next slot's
 			// gather or in meanCenterCov after the barrier below. The next iteration rewrites xcv4 before its first
 			// barrier (its readers passed the second barrier), tv4/zv4 only after that barrier.
+			// A short last group reads row n-1 through its clamped X1..X3 while the owner of that row may be rewriting it:
+			// those lanes' results are discarded (nv), so the groups need no barrier between them inside the loop.
 			if(STEP == 1)
-				__syncthreads(); // X0..X3 of a short last group alias row n-1, which another group may be writing
+				groupSync<GS>();
 		}
 		__syncthreads();
 		if(STEP == 1)
