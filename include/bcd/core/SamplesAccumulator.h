@@ -12,17 +12,15 @@ namespace bcd
 
 	struct HistogramParameters
 	{
-		HistogramParameters() : m_nbOfBins(20), m_gamma(2.2f), m_maxValue(2.5f) {}
-
-		int m_nbOfBins;
-		float m_gamma;    ///< bins are uniform in value^(1/gamma)
-		float m_maxValue; ///< value mapped to the last regular bin boundary
+		int m_nbOfBins = 20;     ///< per colour channel
+		float m_gamma = 2.2f;    ///< bins are uniform in value^(1/gamma)
+		float m_maxValue = 2.5f; ///< value mapped to the last regular bin boundary
 	};
 
 	struct SamplesStatisticsImages
 	{
 		SamplesStatisticsImages() = default;
-		SamplesStatisticsImages(int i_width, int i_height, int i_nbOfBins);
+		SamplesStatisticsImages(int width, int height, int nbOfBins);
 
 		DeepImage<float> m_nbOfSamplesImage;
 		DeepImage<float> m_meanImage;
@@ -33,9 +31,9 @@ namespace bcd
 	class SamplesAccumulator
 	{
 	public:
-		SamplesAccumulator(int i_width, int i_height, const HistogramParameters& i_rHistogramParameters);
+		SamplesAccumulator(int width, int height, const HistogramParameters& histo);
 
-		void addSample(int i_line, int i_column, float i_sampleR, float i_sampleG, float i_sampleB, float i_weight = 1.f);
+		void addSample(int line, int column, float r, float g, float b, float weight = 1.f);
 
 		/// Finalised copy of the statistics (the accumulator stays usable).
 		SamplesStatisticsImages getSamplesStatistics() const;
@@ -43,14 +41,14 @@ namespace bcd
 		SamplesStatisticsImages extractSamplesStatistics();
 
 	private:
-		void finalise(SamplesStatisticsImages& io_rStats) const;
+		void finalise(SamplesStatisticsImages& stats) const;
 
 	private:
 		int m_width;
 		int m_height;
-		HistogramParameters m_histogramParameters;
-		SamplesStatisticsImages m_samplesStatisticsImages;
-		DeepImage<float> m_squaredWeightSumsImage;
+		HistogramParameters m_histo;
+		SamplesStatisticsImages m_stats;
+		DeepImage<float> m_sumW2;
 		bool m_isValid;
 	};
 

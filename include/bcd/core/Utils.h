@@ -1,5 +1,5 @@
-// bcd_b200 — helper functions of the reference's core library kept for the front ends
-// (superboubek/bcd include/bcd/core/Utils.h:20-41; behaviour of src/core/Utils.cpp:21-113), written from scratch.
+// bcd_b200 — the four helpers of the reference's core library that its front ends use (API contract: superboubek/bcd
+// include/bcd/core/Utils.h:20-41; behaviour: src/core/Utils.cpp:21-113). Written from scratch in bcd_b200/host/Utils.cpp.
 #ifndef BCD_B200_UTILS_H
 #define BCD_B200_UTILS_H
 
@@ -13,23 +13,20 @@ namespace bcd
 	class Utils
 	{
 	public:
-		/// The histogram files carry the per-pixel sample count as one extra, last channel (src/raw_converter/main.cpp:
-		/// 176-184): splits a (W, H, D+1) image into histogram (D) and count (1).
-		static bool separateNbOfSamplesFromHistogram(
-				DeepImage<float>& o_rHistoImage,
-				DeepImage<float>& o_rNbOfSamplesImage,
-				const DeepImage<float>& i_rHistoAndNbOfSamplesImage);
+		// ---- paths ('/' separated), as the preset files use them
+		/// Everything up to and including the last '/': "a/b/c.exr" -> "a/b/", "c.exr" -> "".
+		static std::string extractFolderPath(const std::string& filePath);
+		/// `filePath` as seen from `folderPath` (which ends with '/'); both in the same frame, absolute or not:
+		/// ("/s/b/f.exr", "/s/a/") -> "../b/f.exr".
+		static std::string getRelativePathFromFolder(const std::string& filePath, const std::string& folderPath);
 
-		/// Inverse of separateNbOfSamplesFromHistogram.
-		static DeepImage<float> mergeHistogramAndNbOfSamples(
-				const DeepImage<float>& i_rHistoImage,
-				const DeepImage<float>& i_rNbOfSamplesImage);
-
-		/// "a/b/c.exr" -> "a/b/", "c.exr" -> "" ('/' separated).
-		static std::string extractFolderPath(const std::string& i_rFilePath);
-
-		/// Path of a file relative to a folder (both given in the same absolute or relative frame; the folder ends with '/').
-		static std::string getRelativePathFromFolder(const std::string& i_rFileAbsolutePath, const std::string& i_rFolderAbsolutePath);
+		// ---- the histogram files carry the per-pixel sample count as one extra, last channel
+		//      (src/raw_converter/main.cpp:176-184, src/cli/main.cpp:185)
+		/// (W, H, D) histogram + (W, H, 1) count -> (W, H, D + 1).
+		static DeepImage<float> mergeHistogramAndNbOfSamples(const DeepImage<float>& histogram, const DeepImage<float>& nbOfSamples);
+		/// (W, H, D + 1) -> (W, H, D) histogram and (W, H, 1) count; false when the input has no channel at all.
+		static bool separateNbOfSamplesFromHistogram(DeepImage<float>& histogramOut, DeepImage<float>& nbOfSamplesOut,
+				const DeepImage<float>& histogramAndNbOfSamples);
 	};
 
 } // namespace bcd

@@ -1,6 +1,7 @@
-// bcd_b200 — `.bcd.json` pipeline presets with the reference's public surface
-// (superboubek/bcd include/bcd/io/ParametersIO.h:17-79; behaviour of src/io/ParametersIO.cpp:36-162). The reference
-// parses with the vendored nlohmann::json; here a small flat-object JSON reader/writer does the same job.
+// bcd_b200 — `.bcd.json` pipeline presets. API contract from superboubek/bcd include/bcd/io/ParametersIO.h:17-79
+// (holder and field names, ParametersIO::load / write and their selector argument); file format and behaviour from
+// src/io/ParametersIO.cpp:36-162. The reference parses with the vendored nlohmann::json; here a small flat-object JSON
+// reader / writer in bcd_b200/io/ParametersIO.cpp does the same job.
 #ifndef BCD_B200_PARAMETERS_IO_H
 #define BCD_B200_PARAMETERS_IO_H
 
@@ -11,27 +12,35 @@
 namespace bcd
 {
 
+	/// Which groups of keys load() / write() touch (all by default).
+	struct PipelineParametersSelector
+	{
+		bool m_inputFileNames = true;
+		bool m_prefilteringParameters = true;
+		bool m_denoiserParameters = true;
+	};
+
+	/// The three EXR inputs of a shot (stored relative to the preset's folder, handed back prefixed with it).
 	struct InputFileNames
 	{
-		std::string m_colors;
-		std::string m_histograms;
-		std::string m_covariances;
+		std::string m_colors, m_histograms, m_covariances;
 	};
 
+	/// Spike-removal prefilter switch and its threshold in standard deviations.
 	struct PrefilteringParameters
 	{
-		PrefilteringParameters() : m_performSpikeRemoval(true), m_spikeRemovalThresholdStDevFactor(1.5f) {}
-		bool m_performSpikeRemoval;
-		float m_spikeRemovalThresholdStDevFactor;
+		bool m_performSpikeRemoval = true;
+		float m_spikeRemovalThresholdStDevFactor = 1.5f;
 	};
 
+	/// Pyramid depth + the per-scale denoiser tunables.
 	struct MultiscaleDenoiserParameters
 	{
-		MultiscaleDenoiserParameters() : m_nbOfScales(3), m_monoscaleParameters() {}
-		int m_nbOfScales;
+		int m_nbOfScales = 3;
 		DenoiserParameters m_monoscaleParameters;
 	};
 
+	/// Everything a preset can hold.
 	struct PipelineParameters
 	{
 		InputFileNames m_inputFileNames;
@@ -39,34 +48,27 @@ namespace bcd
 		MultiscaleDenoiserParameters m_denoiserParameters;
 	};
 
-	struct PipelineParametersSelector
-	{
-		PipelineParametersSelector() : m_inputFileNames(true), m_prefilteringParameters(true), m_denoiserParameters(true) {}
-		bool m_inputFileNames;
-		bool m_prefilteringParameters;
-		bool m_denoiserParameters;
-	};
-
 	class ParametersIO
 	{
-	private:
-		ParametersIO() {}
-
 	public:
+		/// "bcd.json" — what the reference's tools append to a preset's name.
 		static const std::string& getPipelineParametersFileExtension()
 		{
-			static const std::string extension = "bcd.json";
-			return extension;
+			static const std::string s_extension("bcd.json");
+			return s_extension;
 		}
 
-		/// Keys that are absent leave the corresponding field of o_rParams untouched; file names are stored relative to
-		/// the preset's folder and come back prefixed with it. False (with a message on cerr) for an unreadable or
-		/// malformed file.
+		/// A key that is absent leaves the corresponding field of o_rParams untouched. False (message on cerr) for an
+		/// unreadable or malformed file.
 		static bool load(PipelineParameters& o_rParams, const std::string& i_rFilePath,
 				PipelineParametersSelector i_selector = PipelineParametersSelector());
 
+		/// Sorted keys, four-space indentation (the layout nlohmann's dump(4) gives the reference's files).
 		static bool write(const PipelineParameters& i_rParams, const std::string& i_rFilePath,
 				PipelineParametersSelector i_selector = PipelineParametersSelector());
+
+	private:
+		ParametersIO();
 	};
 
 } // namespace bcd
