@@ -34,10 +34,13 @@ namespace bcd
 		const float* src = histogram.getDataPtr();
 		const float* count = nbOfSamples.getDataPtr();
 		float* dst = merged.getDataPtr();
-		for(size_t p = 0, np = (size_t)histogram.getWidth() * histogram.getHeight(); p < np; ++p, dst += depth + 1)
+		const long np = (long)histogram.getWidth() * histogram.getHeight();
+#pragma omp parallel for schedule(static)
+		for(long p = 0; p < np; ++p)
 		{
-			if(depth) memcpy(dst, src + p * depth, (size_t)depth * sizeof(float));
-			dst[depth] = count[p];
+			float* o = dst + (size_t)p * (depth + 1);
+			if(depth) memcpy(o, src + (size_t)p * depth, (size_t)depth * sizeof(float));
+			o[depth] = count[p];
 		}
 		return merged;
 	}
@@ -54,10 +57,13 @@ namespace bcd
 		const float* src = histogramAndNbOfSamples.getDataPtr();
 		float* hist = histogramOut.getDataPtr();
 		float* count = nbOfSamplesOut.getDataPtr();
-		for(size_t p = 0, np = (size_t)width * height; p < np; ++p, src += depth + 1)
+		const long np = (long)width * height;
+#pragma omp parallel for schedule(static)
+		for(long p = 0; p < np; ++p)
 		{
-			if(depth) memcpy(hist + p * depth, src, (size_t)depth * sizeof(float));
-			count[p] = src[depth];
+			const float* in = src + (size_t)p * (depth + 1);
+			if(depth) memcpy(hist + (size_t)p * depth, in, (size_t)depth * sizeof(float));
+			count[p] = in[depth];
 		}
 		return true;
 	}

@@ -4,6 +4,7 @@
 #include "DeepImage.h"
 #include "exr_codec.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <iostream>
 #include <vector>
@@ -35,28 +36,28 @@ namespace bcd
 	bool ImageIO::loadEXR(DeepImage<float>& o_rImage, const char* i_pFilePath)
 	{
 		std::cout << "Loading " << i_pFilePath << std::endl;
-		bcdio::ExrFile f;
+		bcdio::ExrReader rd;
 		std::string err;
-		if(!bcdio::exrRead(i_pFilePath, f, err))
+		if(!bcdio::exrOpen(i_pFilePath, rd, err))
 			return failWith(err, i_pFilePath);
-		const size_t np = (size_t)f.width * f.height;
-		const std::vector<float> zeros(np, 0.f);
-		const float* rgb[3];
-		const char* names[3] = {"R", "G", "B"};
-		for(int z = 0; z < 3; ++z)
-		{
-			const int c = f.find(names[z]);
-			rgb[z] = c >= 0 ? f.planes[c].data() : zeros.data();
-		}
+		const int w = rd.info.width, h = rd.info.height;
+		const size_t np = (size_t)w * h;
+		// R, G, B straight into interleaved pixels; a channel the file does not have stays 0
+		std::vector<float> rgb(np * 3, 0.f);
+		const std::vector<int> channelOfSlot = {rd.info.find("R"), rd.info.find("G"), rd.info.find("B")};
+		if(!bcdio::exrDecodeInterleaved(rd, channelOfSlot, rgb.data(), err))
+			return failWith(err, i_pFilePath);
 		bool grey = true; // a colour file whose three channels agree everywhere is a 1-channel image (ImageIO.cpp:41-52)
 		for(size_t i = 0; i < np && grey; ++i)
-			grey = rgb[0][i] == rgb[1][i] && rgb[0][i] == rgb[2][i];
+			grey = rgb[3 * i] == rgb[3 * i + 1] && rgb[3 * i] == rgb[3 * i + 2];
 		const int depth = grey ? 1 : 3;
-		o_rImage.resize(f.width, f.height, depth);
+		o_rImage.resize(w, h, depth);
 		float* dst = o_rImage.getDataPtr();
-		for(size_t i = 0; i < np; ++i)
-			for(int z = 0; z < depth; ++z)
-				dst[i * depth + z] = rgb[z][i];
+		if(grey)
+			for(size_t i = 0; i < np; ++i)
+				dst[i] = rgb[3 * i];
+		else
+			std::copy(rgb.begin(), rgb.end(), dst);
 		t_lastError.clear();
 		return true;
 	}
@@ -64,28 +65,24 @@ namespace bcd
 	bool ImageIO::loadMultiChannelsEXR(DeepImage<float>& o_rImage, const char* i_pFilePath)
 	{
 		std::cout << "Loading " << i_pFilePath << std::endl;
-		bcdio::ExrFile f;
+		bcdio::ExrReader rd;
 		std::string err;
-		if(!bcdio::exrRead(i_pFilePath, f, err))
+		if(!bcdio::exrOpen(i_pFilePath, rd, err))
 			return failWith(err, i_pFilePath);
-		std::vector<int> chan;
+		std::vector<int> channelOfSlot; // Bin_0000, Bin_0001, ... as long as they are there
 		for(int i = 0;; ++i)
 		{
-			const int c = f.find(binName(i));
+			const int c = rd.info.find(binName(i));
 			if(c < 0) break;
-			chan.push_back(c);
+			channelOfSlot.push_back(c);
 		}
-		if(chan.empty())
+		if(channelOfSlot.empty())
 			return failWith("no Bin_0000 channel", i_pFilePath);
-		const int depth = (int)chan.size();
-		const size_t np = (size_t)f.width * f.height;
-		o_rImage.resize(f.width, f.height, depth);
-		float* dst = o_rImage.getDataPtr();
-		for(int z = 0; z < depth; ++z)
+		o_rImage.resize(rd.info.width, rd.info.height, (int)channelOfSlot.size());
+		if(!bcdio::exrDecodeInterleaved(rd, channelOfSlot, o_rImage.getDataPtr(), err))
 		{
-			const float* src = f.planes[chan[z]].data();
-			for(size_t i = 0; i < np; ++i)
-				dst[i * depth + z] = src[i];
+			o_rImage.clearAndFreeMemory();
+			return failWith(err, i_pFilePath);
 		}
 		t_lastError.clear();
 		return true;
@@ -122,9 +119,11 @@ namespace bcd
 		const size_t np = (size_t)w * h;
 		std::vector<float> planes((size_t)d * np);
 		const float* src = i_rImage.getDataPtr();
-		for(size_t i = 0; i < np; ++i)
-			for(int z = 0; z < d; ++z)
-				planes[z * np + i] = src[i * d + z];
+#pragma omp parallel for schedule(static)
+		for(long l = 0; l < (long)h; ++l)
+			for(size_t i = (size_t)l * w; i < (size_t)(l + 1) * w; ++i)
+				for(int z = 0; z < d; ++z)
+					planes[z * np + i] = src[i * d + z];
 		std::vector<std::string> names;
 		std::vector<const float*> ptrs;
 		for(int z = 0; z < d; ++z)

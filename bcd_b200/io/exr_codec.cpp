@@ -740,9 +740,10 @@ bool readWholeFile(const char* path, std::vector<uint8_t>& buf)
 } // namespace
 
 // ------------------------------------------------------------------------------------------------------- read
-static bool exrReadBody(const char* path, ExrFile& out, std::string& err)
+static bool exrOpenBody(const char* path, ExrReader& rd, std::string& err)
 {
-	std::vector<uint8_t> buf;
+	std::vector<uint8_t>& buf = rd.file;
+	ExrFile& out = rd.info;
 	if(!readWholeFile(path, buf)) { err = std::string("cannot read '") + path + "'"; return false; }
 	Reader r(buf.data(), buf.size());
 	if(r.u32() != 20000630u || !r.ok) { err = std::string("'") + path + "' is not an OpenEXR file"; return false; }
@@ -811,14 +812,16 @@ static bool exrReadBody(const char* path, ExrFile& out, std::string& err)
 	size_t lineBytes = 0;
 	for(size_t c = 0; c < nch; ++c)
 		lineBytes += (size_t)w * bytesOf(out.types[c]);
-	out.planes.assign(nch, std::vector<float>((size_t)w * h));
+	rd.lineBytes = lineBytes;
 	const int nChunks = (int)((h + lpc - 1) / lpc);
 	std::vector<uint64_t> offsets(nChunks);
 	for(int i = 0; i < nChunks; ++i)
 		offsets[i] = r.u64();
 	if(!r.ok) { err = "truncated offset table"; return false; }
-	std::vector<uint8_t> raw;
-	const uint8_t* seq = r.p; // fall back to reading the chunks in file order when the table was never written
+	// pass 1 (serial): locate and validate every chunk; a table that was never written falls back to file order
+	std::vector<ExrReader::Chunk>& refs = rd.chunks;
+	refs.resize(nChunks);
+	const uint8_t* seq = r.p;
 	for(int i = 0; i < nChunks; ++i)
 	{
 		if(offsets[i] >= buf.size()) { err = "bad chunk offset"; return false; }
@@ -829,54 +832,136 @@ static bool exrReadBody(const char* path, ExrFile& out, std::string& err)
 		seq = c.p + n;
 		const long ly = (long)y - out.minY;
 		if(ly < 0 || ly >= h || ly % lpc) { err = "bad chunk coordinate"; return false; }
-		const int lines = (int)std::min<long>(lpc, h - ly);
-		const size_t rawSize = lineBytes * lines;
-		raw.resize(rawSize);
-		if((size_t)n == rawSize)
-			memcpy(raw.data(), c.p, rawSize);
-		else
-		{
-			bool ok = false;
-			switch(out.compression)
-			{
-				case EXR_RLE: ok = unrleBlock(c.p, (size_t)n, rawSize, raw.data()); break;
-				case EXR_ZIPS: case EXR_ZIP: ok = unzipBlock(c.p, (size_t)n, rawSize, raw.data()); break;
-				case EXR_PIZ: ok = unpizBlock(c.p, (size_t)n, (int)w, lines, out.types, raw.data(), err); break;
-				default: break;
-			}
-			if(!ok)
-			{
-				if(err.empty()) err = "corrupt compressed chunk";
-				return false;
-			}
-		}
-		const uint8_t* s = raw.data();
-		for(int l = 0; l < lines; ++l)
-			for(size_t ch = 0; ch < nch; ++ch)
-			{
-				float* dst = out.planes[ch].data() + (size_t)(ly + l) * w;
-				if(out.types[ch] == EXR_HALF)
-					for(long x = 0; x < w; ++x, s += 2)
-						dst[x] = halfToFloat((unsigned short)(s[0] | s[1] << 8));
-				else if(out.types[ch] == EXR_FLOAT)
-					for(long x = 0; x < w; ++x, s += 4)
-					{
-						const uint32_t b = (uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24;
-						memcpy(dst + x, &b, 4);
-					}
-				else
-					for(long x = 0; x < w; ++x, s += 4)
-						dst[x] = (float)((uint32_t)s[0] | (uint32_t)s[1] << 8 | (uint32_t)s[2] << 16 | (uint32_t)s[3] << 24);
-			}
+		refs[i].offset = (size_t)(c.p - buf.data());
+		refs[i].size = (size_t)n;
+		refs[i].line = ly;
+		refs[i].lines = (int)std::min<long>(lpc, h - ly);
 	}
 	return true;
+}
+
+// Decompresses every chunk (in parallel: they are independent) and converts the channels to float. `planes` (one
+// width x height plane per file channel) and / or `hwc` (interleaved, `depth` floats per pixel; slotOfChannel[c] is the
+// position of file channel c inside a pixel or -1) receive the values.
+static bool exrDecodeBody(const ExrReader& rd, std::vector<std::vector<float> >* planes, float* hwc, int depth,
+		const std::vector<int>& slotOfChannel, std::string& err)
+{
+	const ExrFile& out = rd.info;
+	const std::vector<ExrReader::Chunk>& refs = rd.chunks;
+	const long w = out.width;
+	const size_t nch = out.names.size(), lineBytes = rd.lineBytes;
+	const int nChunks = (int)refs.size();
+	bool failed = false;
+	std::string firstErr;
+#pragma omp parallel for schedule(dynamic, 1) if(nChunks > 4)
+	for(int i = 0; i < nChunks; ++i)
+	{
+		if(failed)
+			continue;
+		std::string cerr;
+		bool ok = true;
+		try
+		{
+			const ExrReader::Chunk& cr = refs[i];
+			const uint8_t* cdata = rd.file.data() + cr.offset;
+			const size_t rawSize = lineBytes * cr.lines;
+			std::vector<uint8_t> raw(rawSize);
+			if(cr.size == rawSize)
+				memcpy(raw.data(), cdata, rawSize);
+			else
+			{
+				switch(out.compression)
+				{
+					case EXR_RLE: ok = unrleBlock(cdata, cr.size, rawSize, raw.data()); break;
+					case EXR_ZIPS: case EXR_ZIP: ok = unzipBlock(cdata, cr.size, rawSize, raw.data()); break;
+					case EXR_PIZ: ok = unpizBlock(cdata, cr.size, (int)w, cr.lines, out.types, raw.data(), cerr); break;
+					default: ok = false; break;
+				}
+				if(!ok && cerr.empty()) cerr = "corrupt compressed chunk";
+			}
+			std::vector<float> row(hwc ? (size_t)w : 0);
+			const uint8_t* s = raw.data();
+			for(int l = 0; ok && l < cr.lines; ++l)
+				for(size_t ch = 0; ch < nch; ++ch)
+				{
+					const int slot = hwc ? slotOfChannel[ch] : -1;
+					float* dst = planes ? (*planes)[ch].data() + (size_t)(cr.line + l) * w : row.data();
+					const size_t bytes = (size_t)w * bytesOf(out.types[ch]);
+					if(!planes && slot < 0) { s += bytes; continue; } // channel nobody asked for
+					if(out.types[ch] == EXR_HALF)
+						for(long x = 0; x < w; ++x)
+							dst[x] = halfToFloat((unsigned short)(s[2 * x] | s[2 * x + 1] << 8));
+					else if(out.types[ch] == EXR_FLOAT)
+						memcpy(dst, s, (size_t)w * 4); // little-endian file, little-endian host
+					else
+						for(long x = 0; x < w; ++x)
+							dst[x] = (float)((uint32_t)s[4 * x] | (uint32_t)s[4 * x + 1] << 8 | (uint32_t)s[4 * x + 2] << 16 | (uint32_t)s[4 * x + 3] << 24);
+					s += bytes;
+					if(slot >= 0)
+					{
+						float* o = hwc + (size_t)(cr.line + l) * w * depth + slot;
+						for(long x = 0; x < w; ++x)
+							o[(size_t)x * depth] = dst[x];
+					}
+				}
+		}
+		catch(const std::bad_alloc&)
+		{
+			ok = false;
+			cerr = "image too large for the available memory";
+		}
+		if(!ok)
+		{
+#pragma omp critical(bcdio_exr_read_error)
+			{
+				if(!failed) firstErr = cerr;
+				failed = true;
+			}
+		}
+	}
+	if(failed)
+	{
+		err = firstErr;
+		return false;
+	}
+	return true;
+}
+
+bool exrOpen(const char* path, ExrReader& rd, std::string& err)
+{
+	try
+	{
+		rd = ExrReader();
+		return exrOpenBody(path, rd, err);
+	}
+	catch(const std::bad_alloc&)
+	{
+		rd = ExrReader();
+		err = "image too large for the available memory";
+		return false;
+	}
+}
+
+bool exrDecodeInterleaved(const ExrReader& rd, const std::vector<int>& channelOfSlot, float* hwc, std::string& err)
+{
+	const int depth = (int)channelOfSlot.size();
+	std::vector<int> slotOfChannel(rd.info.names.size(), -1);
+	for(int z = 0; z < depth; ++z)
+		if(channelOfSlot[z] >= 0 && channelOfSlot[z] < (int)slotOfChannel.size())
+			slotOfChannel[channelOfSlot[z]] = z;
+	return exrDecodeBody(rd, nullptr, hwc, depth, slotOfChannel, err);
 }
 
 bool exrRead(const char* path, ExrFile& out, std::string& err)
 {
 	try
 	{
-		return exrReadBody(path, out, err);
+		ExrReader rd;
+		if(!exrOpenBody(path, rd, err)) { out = ExrFile(); return false; }
+		out = rd.info;
+		out.planes.assign(out.names.size(), std::vector<float>((size_t)out.width * out.height));
+		if(!exrDecodeBody(rd, &out.planes, nullptr, 0, std::vector<int>(), err)) { out = ExrFile(); return false; }
+		return true;
 	}
 	catch(const std::bad_alloc&) // a header that announces more pixels than memory can hold
 	{
@@ -959,9 +1044,11 @@ bool exrWrite(const char* path, int width, int height, const std::vector<std::st
 	const int lpc = linesPerChunk(compression), nChunks = (height + lpc - 1) / lpc;
 	const size_t px = type == EXR_HALF ? 2 : 4, lineBytes = (size_t)width * px * names.size();
 	std::vector<std::vector<uint8_t> > chunks(nChunks);
-	std::vector<uint8_t> raw, t;
+	// the chunks are independent: pack and compress them on all host threads (deflate is the slow part)
+#pragma omp parallel for schedule(dynamic, 1) if(nChunks > 4)
 	for(int i = 0; i < nChunks; ++i)
 	{
+		std::vector<uint8_t> raw, t;
 		const int y0 = i * lpc, lines = std::min(lpc, height - y0);
 		raw.resize(lineBytes * lines);
 		uint8_t* o = raw.data();
@@ -977,12 +1064,10 @@ bool exrWrite(const char* path, int width, int height, const std::vector<std::st
 						*o++ = (uint8_t)(hv >> 8);
 					}
 				else
-					for(int x = 0; x < width; ++x)
-					{
-						uint32_t v;
-						memcpy(&v, src + x, 4);
-						for(int k = 0; k < 4; ++k) *o++ = (uint8_t)(v >> (8 * k));
-					}
+				{
+					memcpy(o, src, (size_t)width * 4); // little-endian host
+					o += (size_t)width * 4;
+				}
 			}
 		std::vector<uint8_t>& c = chunks[i];
 		put32(c, (uint32_t)y0);

@@ -35,7 +35,22 @@ struct ExrFile
 	}
 };
 
-// Both return false and fill `err` on failure; nothing is thrown and the process is never terminated (the reference's
+// Two-step reading for callers that want the pixels interleaved (HWC) without the intermediate planes: exrOpen parses
+// the header and the chunk table (info.planes stays empty), exrDecodeInterleaved decompresses straight into
+// hwc[(y * width + x) * depth + z] where depth = channelOfSlot.size() and channelOfSlot[z] is the index of the file
+// channel that goes to position z (or -1: the position is left untouched, e.g. pre-filled with zeros).
+struct ExrReader
+{
+	struct Chunk { size_t offset, size; long line; int lines; };
+	std::vector<unsigned char> file; // the whole file
+	ExrFile info;
+	std::vector<Chunk> chunks;
+	size_t lineBytes = 0;
+};
+bool exrOpen(const char* path, ExrReader& rd, std::string& err);
+bool exrDecodeInterleaved(const ExrReader& rd, const std::vector<int>& channelOfSlot, float* hwc, std::string& err);
+
+// All of them return false and fill `err` on failure; nothing is thrown and the process is never terminated (the reference's
 // wrappers call exit(-1), io_exr.cpp:117-120 — not reproduced).
 bool exrRead(const char* path, ExrFile& out, std::string& err);
 bool exrWrite(const char* path, int width, int height, const std::vector<std::string>& names,
