@@ -359,13 +359,20 @@ def main():
     tp = os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")
     if os.path.exists(tp):
         try:
+            # the ncu capture is the level-0 launch; DRAM traffic of this kernel is proportional to the pixel count, so the
+            # launch set of one step (all levels) is the capture scaled by npix_all / npix_level0 — same units as `achieved`
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            if traffic is not None and (W, H) == (1920, 1080):
+                traffic = traffic * npix_all / float(W * H)
+            else:
+                traffic = None  # captured at 1080p only
         except Exception:
             traffic = None
     roofline = {"kernel": "k_pair_terms_sparse (stage 'pair', %d launches/step)" % a.scales, "bound": "hbm",
                 "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                 "peak_source": pk_src + " (burst copy figure; kernel timed alone by CUDA events)", "traffic": traffic,
                 "ms_per_launch_set": pair_ms,
+                "traffic_source": "profiles/pair_kernel_traffic.json (ncu --set full, level-0 launch) scaled to the launch set of a step",
                 "note": "FP32-issue-bound kernel: HBM fraction is low by construction (SURVEY 8d); see roofline_fp32"}
     terms = npix_all * J * B                                # bin terms actually evaluated per step
     fp32_peak = 148 * 128 * 2 * (clocks.get("sm_mhz") or 1900.0) * 1e6 / 1e12  # FMA TFLOP/s at the sampled clock
