@@ -1,6 +1,7 @@
 # Builds every native artefact in-tree (they travel to the GPU box with the snapshot; none is committed).
 #   bcd_b200/libbcd_b200.so      C ABI (include/bcd_b200.h) + sm_100a kernels            [nvcc]
 #   bcd_b200/libbcdcore_b200.so  bcd:: C++ API mirror (include/bcd/core/*.h) + synthetic-input generator [g++]
+#   bcd_b200/libbcdsynth.so      the synthetic-input generator alone (no CUDA dependency)                [g++]
 #   bin/bcd_cli, bin/raw2bcd     command-line front ends (EXR in, EXR out)                  [g++]
 #   oracle/liboracle.so, oracle/_ref/libbcd_ref.so, oracle/_ref/libexr_ref.so   parity oracles (test infrastructure)   [gcc/g++]
 NVCC ?= /usr/local/cuda/bin/nvcc
@@ -8,13 +9,13 @@ CXX = g++
 ARCH = -gencode arch=compute_100a,code=sm_100a
 NVFLAGS = $(ARCH) -O3 -lineinfo --fmad=false -std=c++17 -ccbin $(CXX) -Xcompiler -fPIC -Xptxas -v
 CSRC = bcd_b200/csrc
-KOBJ = $(CSRC)/k_distance.o $(CSRC)/k_misc.o $(CSRC)/k_marking.o $(CSRC)/k_filter.o $(CSRC)/k_eig_sub.o $(CSRC)/bcd_b200_capi.o
+KOBJ = $(CSRC)/k_distance.o $(CSRC)/k_misc.o $(CSRC)/k_marking.o $(CSRC)/k_filter.o $(CSRC)/k_eig_sub.o $(CSRC)/k_peer.o $(CSRC)/bcd_b200_capi.o $(CSRC)/bcd_b200_multi.o
 HOSTSRC = $(wildcard bcd_b200/host/*.cpp) $(wildcard bcd_b200/io/*.cpp)
 HOSTINC = -Iinclude -Iinclude/bcd/core -Iinclude/bcd/io -Ibcd_b200/io
 
-all: bcd_b200/libbcd_b200.so bcd_b200/libbcdcore_b200.so bin/bcd_cli bin/raw2bcd oracle ref_frontends
+all: bcd_b200/libbcd_b200.so bcd_b200/libbcdcore_b200.so bcd_b200/libbcdsynth.so bin/bcd_cli bin/raw2bcd oracle ref_frontends
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h include/bcd_b200.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/kernels.h $(CSRC)/engine.h include/bcd_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
 bcd_b200/libbcd_b200.so: $(KOBJ)
@@ -23,6 +24,11 @@ bcd_b200/libbcd_b200.so: $(KOBJ)
 bcd_b200/libbcdcore_b200.so: $(HOSTSRC) $(wildcard include/bcd/core/*.h include/bcd/io/*.h bcd_b200/io/*.h) include/bcd_b200.h include/bcd_b200_host.h bcd_b200/libbcd_b200.so
 	$(CXX) -std=c++11 -O2 -fopenmp -fPIC -shared $(HOSTINC) -o $@ $(HOSTSRC) \
 		-Lbcd_b200 -lbcd_b200 -lz -Wl,-rpath,'$$ORIGIN'
+
+# the synthetic-input generator G alone (bcd_synth_generate + SamplesAccumulator), with no dependency on the CUDA library:
+# bench.py's reference arm generates its frame with it, so that nothing of the product path is mapped into that process
+bcd_b200/libbcdsynth.so: bcd_b200/host/synth.cpp bcd_b200/host/SamplesAccumulator.cpp $(wildcard include/bcd/core/*.h) include/bcd_b200_host.h
+	$(CXX) -std=c++11 -O2 -fopenmp -fPIC -shared -DBCD_SYNTH_ONLY $(HOSTINC) -o $@ bcd_b200/host/synth.cpp bcd_b200/host/SamplesAccumulator.cpp
 
 # front ends (reference: src/cli/main.cpp, src/raw_converter/main.cpp)
 bin/%: apps/%.cpp bcd_b200/libbcdcore_b200.so

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbcd_b200.so")
 
 STAGE_NAMES = ["prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
-               "finalize", "pyramid"]
+               "finalize", "pyramid", "exchange"]
 
 # every symbol include/bcd_b200.h declares (tests/test_capi_symbols.py cross-checks this list against the header)
 SYMBOLS = [
@@ -28,6 +28,10 @@ SYMBOLS = [
     "bcd_b200_tile_plan", "bcd_b200_tile_begin", "bcd_b200_tile_select", "bcd_b200_tile_mark", "bcd_b200_tile_filter",
     "bcd_b200_tile_finalize", "bcd_b200_tile_merge", "bcd_b200_tile_xfer_bytes", "bcd_b200_tile_export",
     "bcd_b200_tile_import", "bcd_b200_tile_end", "bcd_b200_tile_download",
+    # peer mode of the row tiles + the group API (bcd_b200_multi.cu)
+    "bcd_b200_tile_setup", "bcd_b200_tile_connect", "bcd_b200_tile_run",
+    "bcd_b200_group_create", "bcd_b200_group_destroy", "bcd_b200_group_set_pinning", "bcd_b200_group_denoise",
+    "bcd_b200_group_get_stats", "bcd_b200_group_get_timings", "bcd_b200_group_tiles", "bcd_b200_denoise_multi",
 ]
 
 
@@ -96,6 +100,16 @@ def lib():
         L.bcd_b200_download_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_spike_removal_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_float, C.c_int, C.c_int]
+        L.bcd_b200_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int]
+        L.bcd_b200_group_destroy.argtypes = [C.c_void_p]
+        L.bcd_b200_group_destroy.restype = None
+        L.bcd_b200_group_set_pinning.argtypes = [C.c_void_p, C.c_int]
+        L.bcd_b200_group_denoise.argtypes = [C.c_void_p, C.POINTER(Images), C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bcd_b200_group_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.bcd_b200_group_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+        L.bcd_b200_group_tiles.argtypes = [C.c_void_p]
+        L.bcd_b200_denoise_multi.argtypes = [C.POINTER(Images), C.POINTER(Params), C.c_void_p, C.POINTER(C.c_int32), C.c_int,
+                                             C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -129,6 +143,65 @@ def denoise(color, nsamples, hist, cov, params=None, device=0, **kw):
     out = np.empty((img.height, img.width, 3), np.float32)
     _check(lib().bcd_b200_denoise(C.byref(img), C.byref(p), out.ctypes.data, device, None, None))
     return out
+
+
+def denoise_multi(color, nsamples, hist, cov, devices, params=None, **kw):
+    """One-shot multi-GPU call: bcd_b200_denoise_multi (row tiles over peer memory; devices may repeat a GPU)."""
+    p = params if params is not None else make_params(**kw)
+    img, keep = _host_images(color, nsamples, hist, cov)
+    out = np.empty((img.height, img.width, 3), np.float32)
+    ids = (C.c_int32 * len(devices))(*devices)
+    _check(lib().bcd_b200_denoise_multi(C.byref(img), C.byref(p), out.ctypes.data, ids, len(devices), None, None))
+    return out
+
+
+class Group:
+    """N GPUs behind one host-buffer call (bcd_b200_group_*): what bcd::Denoiser / bcd::MultiscaleDenoiser hold."""
+
+    def __init__(self, devices, pin=None):
+        self._g = C.c_void_p()
+        ids = (C.c_int32 * len(devices))(*devices)
+        _check(lib().bcd_b200_group_create(C.byref(self._g), ids, len(devices)))
+        if pin is not None:
+            _check(lib().bcd_b200_group_set_pinning(self._g, int(bool(pin))))
+
+    def close(self):
+        if self._g:
+            lib().bcd_b200_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def denoise(self, color, nsamples, hist, cov, params=None, out=None, **kw):
+        p = params if params is not None else make_params(**kw)
+        img, keep = _host_images(color, nsamples, hist, cov)
+        if out is None:
+            out = np.empty((img.height, img.width, 3), np.float32)
+        _check(lib().bcd_b200_group_denoise(self._g, C.byref(img), C.byref(p), out.ctypes.data, None, None))
+        return out
+
+    def denoise_ptrs(self, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B, out_ptr, params):
+        img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, H, B)
+        _check(lib().bcd_b200_group_denoise(self._g, C.byref(img), C.byref(params), C.c_void_p(out_ptr), None, None))
+
+    def tiles(self):
+        return int(lib().bcd_b200_group_tiles(self._g))
+
+    def stats(self):
+        s = Stats()
+        _check(lib().bcd_b200_group_get_stats(self._g, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def timings(self):
+        t = Timings()
+        _check(lib().bcd_b200_group_get_timings(self._g, C.byref(t)))
+        d = {n: float(t.stage_ms[i]) for i, n in enumerate(STAGE_NAMES)}
+        d["total"] = float(t.total_ms)
+        return d
 
 
 class Handle:

@@ -6,8 +6,7 @@
 // Everything data-parallel happens in the kernels (k_*.cu); this file only owns device buffers, streams, events,
 // error reporting and the order of launches. There is no CPU fallback: without a CUDA device every entry point fails.
 
-#include "../../include/bcd_b200.h"
-#include "kernels.h"
+#include "engine.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -21,8 +20,20 @@ using namespace bcdk;
 
 namespace
 {
-
 thread_local std::string g_lastError;
+
+// A handle keeps several streams busy at once (main, one per pyramid level, copy, banded selection) and, in row-tile
+// peer mode, kernels that wait for a neighbour sit at the head of some of them: streams that shared a hardware queue (8
+// by default) would serialise behind such a wait. Ask for more queues unless the host application has decided already;
+// this only has an effect when the library is loaded before the CUDA context exists.
+struct ConnectionsDefault
+{
+	ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connectionsDefault;
+}
+
+namespace bcdeng
+{
 
 int fail(int code, const char* fmt, ...)
 {
@@ -35,149 +46,46 @@ int fail(int code, const char* fmt, ...)
 	return code;
 }
 
-#define CU(call) \
-	do { \
-		cudaError_t e_ = (call); \
-		if(e_ != cudaSuccess) \
-			return fail(BCD_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-	} while(0)
+} // namespace bcdeng
 
-// grow-only device buffer
-struct DevBuf
+using namespace bcdeng;
+
+namespace bcdeng
 {
-	void* p = nullptr;
-	size_t cap = 0;
-	cudaError_t reserve(size_t bytes)
+
+// timed spans: (begin event, end event, stage) triples over a grow-only pool of events; resolved by collectTimings after
+// the final synchronisation of the run (no host wait in between)
+int takeEvent(bcd_b200_handle* h, int* idx)
+{
+	if(h->eventsUsed >= h->events.size())
 	{
-		if(bytes <= cap)
-			return cudaSuccess;
-		if(p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
-		cudaError_t e = cudaMalloc(&p, bytes);
-		if(e == cudaSuccess) cap = bytes;
-		return e;
+		cudaEvent_t e;
+		CU(cudaEventCreate(&e));
+		h->events.push_back(e);
 	}
-	void release()
-	{
-		if(p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
-	}
-	template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct LevelBufs
-{
-	int W = 0, H = 0;
-	const float *color = nullptr, *ns = nullptr, *hist = nullptr, *cov = nullptr; // inputs of this level
-	DevBuf ownColor, ownNs, ownHist, ownCov;                                         // storage when owned
-	DevBuf altColor, altNs, altHist, altCov;                                         // second set (spike prefilter output)
-	DevBuf out;                                                                      // W*H*3
-	// per-level state of the hot path (kept per level so that the stages of different levels can overlap)
-	DevBuf smask, counts, pre, active, asBits, progress, fullList, fallbackList, acc, pixcov, ctr;
-	// private pair-term planes / half masks of a coarser level whose selection runs band by band under a streamed upload,
-	// interleaved with the level-0 bands that use the shared scratch (allocated on first use)
-	DevBuf sPl, cPl, mplusl;
-	DeviceCounters* hostCtr = nullptr; // pinned read-back of ctr
-	DeviceCounters counters;           // host copy used to size the filter launches
-	cudaEvent_t evSel = nullptr, evMark = nullptr;
-};
-
-} // namespace
-
-struct bcd_b200_handle
-{
-	int device = 0;
-	cudaStream_t ownStream = nullptr, stream = nullptr;
-	int W = 0, H = 0, B = 0;
-	bool haveInputs = false;
-	std::vector<LevelBufs> levels; // [0] = full resolution
-	// scratch shared by all levels (sized for level 0)
-	DevBuf sP, cP, mplus, tmpLow;          // scratch of the selection stage / merge (levels run it one after the other)
-	DevBuf fA, fMinv, fMean, fNoise, fX;   // scratch of the filter chain (chunked)
-	// marking (K2) runs on a second, high-priority stream so that the latency-bound raster-order chain of level k
-	// overlaps the selection of level k-1 and the filters of the coarser levels on the main stream
-	cudaStream_t ownAux = nullptr, aux = nullptr;
-	std::vector<cudaStream_t> ownAuxLevel; // levels >= 1 get their own marking stream (the chains of different levels are independent)
-	std::vector<cudaStream_t> userAuxLevel; // caller-owned marking stream per level (bcd_b200_set_level_aux_stream), or null
-	// streamed upload (bcd_b200_upload_async): the histogram arrives in row bands on a copy stream, one event per band;
-	// the level-0 pair-term kernel (K1a) is launched band by band behind those events, so the PCIe transfer of the
-	// (dominant) histogram overlaps the dominant kernel
-	struct Upload
-	{
-		cudaStream_t copy = nullptr;
-		bool pending = false;
-		bool histOrdered = false; // the main stream has waited for every histogram chunk of the pending upload
-		int bands = 0;
-		int rowEnd[16];
-		cudaEvent_t ev[16] = {};
-		cudaEvent_t evAll = nullptr, evOrder = nullptr;
-		// banded level-0 selection: K1b/K1c of band i-1 run on `sel` next to K1a of band i+1 on the main stream
-		cudaStream_t sel = nullptr;
-		cudaEvent_t evPair[16] = {};
-		cudaEvent_t evSelDone = nullptr;
-		int coarseDone = 0; // levels 1..coarseDone had their selection streamed behind the level-0 bands of this run
-		cudaStream_t coarse = nullptr; // the stream of that work
-	} up;
-	int filterChunk = 0;
-	LevelGeom g0;      // geometry of level 0 in the last run (debug read-backs)
-	bool ran = false;
-	bcd_b200_stats stats;
-	bcd_b200_timings timings;
-	std::vector<cudaEvent_t> events; // pairs (begin, end) per timed stage instance
-	std::vector<int> eventStage;
-	cudaEvent_t fev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t evTotal[2] = {nullptr, nullptr};
-	size_t eventsUsed = 0;
-	int launches = 0;
-	// row-tile mode (multi-GPU): the resident inputs are rows [subRow0, subRow1) of an imageH-row frame and this
-	// handle produces the output rows [ownRow0, ownRow1) (frame coordinates)
-	// row-tile mode builds the pyramid lazily: histogram part of level k before its selection, colour part before its
-	// filter (highest level built so far), so that a streamed upload overlaps the level-0 selection here too
-	int pyrHistDone = 0, pyrColorDone = 0;
-	bool pixcovDone[16] = {};
-	bool tiled = false;
-	int imageH = 0, subRow0 = 0, subRow1 = 0, ownRow0 = 0, ownRow1 = 0;
-	bcd_b200_params runParams;
-};
-
-namespace
-{
+	*idx = (int)h->eventsUsed++;
+	return 0;
+}
 
 int stageBegin(bcd_b200_handle* h, int stage, cudaStream_t st)
 {
-	if(h->eventsUsed + 2 > h->events.size())
-	{
-		for(int i = 0; i < 2; ++i)
-		{
-			cudaEvent_t e;
-			CU(cudaEventCreate(&e));
-			h->events.push_back(e);
-		}
-		h->eventStage.push_back(stage);
-	}
-	h->eventStage[h->eventsUsed / 2] = stage;
-	CU(cudaEventRecord(h->events[h->eventsUsed], st));
+	int b;
+	int rc = takeEvent(h, &b);
+	if(rc) return rc;
+	CU(cudaEventRecord(h->events[b], st));
+	h->spans.push_back({b, -1, stage});
 	return 0;
 }
 
 int stageEnd(bcd_b200_handle* h, cudaStream_t st)
 {
-	CU(cudaEventRecord(h->events[h->eventsUsed + 1], st));
-	h->eventsUsed += 2;
+	int e;
+	int rc = takeEvent(h, &e);
+	if(rc) return rc;
+	CU(cudaEventRecord(h->events[e], st));
+	h->spans.back().e = e;
 	return 0;
 }
-
-#define STAGE_ON(h, st_, stage, ...) \
-	do { \
-		int rc_ = stageBegin(h, stage, st_); \
-		if(rc_) return rc_; \
-		__VA_ARGS__; \
-		rc_ = stageEnd(h, st_); \
-		if(rc_) return rc_; \
-	} while(0)
-#define STAGE(h, stage, ...) STAGE_ON(h, (h)->stream, stage, __VA_ARGS__)
 
 // Geometry of level k as seen by this handle. Single GPU: the whole level. Row tile: the local sub-image with the
 // owned patch-centre rows [rowBeg, rowEnd) and the rows [yLo, yHi) on which the selection stage has to run
@@ -495,6 +403,16 @@ int levelMarkEnqueue(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
+void addCounters(bcd_b200_handle* h, const DeviceCounters& c)
+{
+	h->stats.interior += (int64_t)c.interior;
+	h->stats.strong += (int64_t)c.strong;
+	h->stats.active += (int64_t)c.active;
+	h->stats.full += (int64_t)c.full;
+	h->stats.fallback += (int64_t)c.fallback;
+	h->stats.sum_n_full += (int64_t)c.sum_n_full;
+}
+
 // stage 2b (host): wait for the work counters of the level (the only host synchronisation per level)
 int levelMarkWait(bcd_b200_handle* h, int k)
 {
@@ -504,12 +422,7 @@ int levelMarkWait(bcd_b200_handle* h, int k)
 	L.counters = c;
 	if(c.markTimeouts)
 		return fail(BCD_B200_ERR_CUDA, "marking kernel: %u bounded waits expired at level %d (hand-off between row bands lost)", c.markTimeouts, k);
-	h->stats.interior += (int64_t)c.interior;
-	h->stats.strong += (int64_t)c.strong;
-	h->stats.active += (int64_t)c.active;
-	h->stats.full += (int64_t)c.full;
-	h->stats.fallback += (int64_t)c.fallback;
-	h->stats.sum_n_full += (int64_t)c.sum_n_full;
+	addCounters(h, c);
 	return 0;
 }
 
@@ -520,50 +433,61 @@ int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return levelMarkWait(h, k);
 }
 
-// stage 3 (main stream): fallback mean + two-step Bayesian filter, accumulated into acc
-int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+// stage 3: fallback mean + two-step Bayesian filter, accumulated into acc.
+// Whole-frame runs (st = main stream, private = false): the host has read the level's work counters (levelMarkWait), the
+// chunks of the full list go through the scratch shared by all levels. Row-tile peer mode (private = true): the level
+// runs on its own stream with its own scratch and the list length stays on the device.
+int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStream_t st, bool deviceCounts)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
-	cudaStream_t st = h->stream;
 	const DeviceCounters c = L.counters;
+	DeviceCounters* dc = L.ctr.as<DeviceCounters>();
 	CU(cudaStreamWaitEvent(st, L.evMark, 0));
-	STAGE(h, BCD_B200_STAGE_FALLBACK, {
-		if(c.nFallback > 0)
+	STAGE_ON(h, st, BCD_B200_STAGE_FALLBACK, {
+		if(deviceCounts || c.nFallback > 0)
 			CU(launchFallback(L.color, L.smask.as<uint32_t>(), L.counts.as<int>(), g, L.fallbackList.as<int>(),
-					&L.ctr.as<DeviceCounters>()->nFallback, L.acc.as<float4>(), st, &h->launches));
+					&dc->nFallback, L.acc.as<float4>(), st, &h->launches));
 	});
-	if(c.nFull > 0)
+	FilterBuffers fb;
+	fb.A = (deviceCounts ? L.fA : h->fA).as<float>();
+	fb.Minv = (deviceCounts ? L.fMinv : h->fMinv).as<float>();
+	fb.mean = (deviceCounts ? L.fMean : h->fMean).as<float>();
+	fb.noise = (deviceCounts ? L.fNoise : h->fNoise).as<float>();
+	fb.xScratch = h->fX.as<float>();
+	fb.smCount = h->smCount;
+	fb.gridCap = h->smCount * 2;
+	const int chunk = deviceCounts ? L.filterChunk : h->filterChunk;
+	// upper bound of the list length the host knows without a read-back: the owned patch centres
+	const long long bound = deviceCounts ? (long long)std::max(0, g.rowEnd - g.rowBeg) * std::max(0, g.W - 2 * g.w) : c.nFull;
+	for(long long first = 0; first < bound; first += chunk)
 	{
-		FilterBuffers fb;
-		fb.A = h->fA.as<float>();
-		fb.Minv = h->fMinv.as<float>();
-		fb.mean = h->fMean.as<float>();
-		fb.noise = h->fNoise.as<float>();
-		fb.xScratch = h->fX.as<float>();
-		fb.gridCap = 148 * 2;
-		float ms[3] = {0.f, 0.f, 0.f};
-		for(int first = 0; first < c.nFull; first += h->filterChunk)
+		const int count = (int)std::min<long long>(chunk, bound - first);
+		int ei[6];
+		for(int i = 0; i < 6; ++i)
 		{
-			const int count = std::min(h->filterChunk, c.nFull - first);
-			cudaError_t e = launchFilterChunk(L.color, L.pixcov.as<float>(), L.smask.as<uint32_t>(), L.counts.as<int>(), g,
-					p.min_eig, L.fullList.as<int>(), first, count, fb, L.acc.as<float4>(), st, &h->launches, ms, h->fev);
-			if(e != cudaSuccess)
-				return fail(e == cudaErrorInvalidConfiguration ? BCD_B200_ERR_UNSUPPORTED : BCD_B200_ERR_CUDA,
-						"filter chunk failed: %s", cudaGetErrorString(e));
-			if(getenv("BCD_B200_TRACE"))
-			{
-				float t0 = 0.f, dt = 0.f;
-				cudaEventElapsedTime(&t0, h->evTotal[0], h->fev[0]);
-				cudaEventElapsedTime(&dt, h->fev[0], h->fev[5]);
-				fprintf(stderr, "[bcd_b200 trace] filter L%d    start %8.3f  dur %7.3f (%d matrices)\n", k, t0, dt, count);
-			}
+			int rc = takeEvent(h, &ei[i]);
+			if(rc) return rc;
 		}
-		h->timings.stage_ms[BCD_B200_STAGE_FILTER_STATS] += ms[0];
-		h->timings.stage_ms[BCD_B200_STAGE_FILTER_EIG] += ms[1];
-		h->timings.stage_ms[BCD_B200_STAGE_FILTER_APPLY] += ms[2];
+		cudaEvent_t ev[6];
+		for(int i = 0; i < 6; ++i) ev[i] = h->events[ei[i]];
+		cudaError_t e = launchFilterChunk(L.color, L.pixcov.as<float>(), L.smask.as<uint32_t>(), L.counts.as<int>(), g,
+				p.min_eig, L.fullList.as<int>(), (int)first, count, deviceCounts ? &dc->nFull : nullptr, fb, L.acc.as<float4>(), st,
+				&h->launches, ev);
+		if(e != cudaSuccess)
+			return fail(e == cudaErrorInvalidConfiguration ? BCD_B200_ERR_UNSUPPORTED : BCD_B200_ERR_CUDA,
+					"filter chunk failed: %s", cudaGetErrorString(e));
+		static const int stageOf[5] = {BCD_B200_STAGE_FILTER_STATS, BCD_B200_STAGE_FILTER_EIG, BCD_B200_STAGE_FILTER_APPLY,
+				BCD_B200_STAGE_FILTER_EIG, BCD_B200_STAGE_FILTER_APPLY};
+		for(int i = 0; i < 5; ++i)
+			h->spans.push_back({ei[i], ei[i + 1], stageOf[i]});
 	}
 	return 0;
+}
+
+int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	return levelFilterOn(h, k, p, h->stream, false);
 }
 
 // row-tile entry: filters of level k; colour / covariance part of the pyramid and the per-pixel covariances on demand
@@ -606,27 +530,25 @@ int levelMerge(bcd_b200_handle* h, int k)
 
 int collectTimings(bcd_b200_handle* h)
 {
-	for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
+	static const char* names[] = {"prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
+			"finalize", "pyramid", "exchange"};
+	for(const bcd_b200_handle::Span& sp : h->spans)
 	{
+		if(sp.e < 0) continue;
 		float ms = 0.f;
-		CU(cudaEventElapsedTime(&ms, h->events[i], h->events[i + 1]));
-		h->timings.stage_ms[h->eventStage[i / 2]] += ms;
+		CU(cudaEventElapsedTime(&ms, h->events[sp.b], h->events[sp.e]));
+		h->timings.stage_ms[sp.stage] += ms;
+		if(h->trace) // stage timeline (ms since the start of the run) on stderr: which stages overlap
+		{
+			float t0 = 0.f;
+			cudaEventElapsedTime(&t0, h->evTotal[0], h->events[sp.b]);
+			fprintf(stderr, "[bcd_b200 trace] dev %d %-12s start %8.3f  dur %7.3f\n", h->device,
+					sp.stage >= 0 && sp.stage < BCD_B200_STAGE_COUNT ? names[sp.stage] : "?", t0, ms);
+		}
 	}
 	CU(cudaEventElapsedTime(&h->timings.total_ms, h->evTotal[0], h->evTotal[1]));
-	if(getenv("BCD_B200_TRACE")) // stage timeline (ms since the start of the run) on stderr: which stages overlap
-	{
-		static const char* names[] = {"prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
-				"finalize", "pyramid"};
-		for(size_t i = 0; i + 1 < h->eventsUsed; i += 2)
-		{
-			float t0 = 0.f, dt = 0.f;
-			cudaEventElapsedTime(&t0, h->evTotal[0], h->events[i]);
-			cudaEventElapsedTime(&dt, h->events[i], h->events[i + 1]);
-			const int sgi = h->eventStage[i / 2];
-			fprintf(stderr, "[bcd_b200 trace] %-12s start %8.3f  dur %7.3f\n", sgi >= 0 && sgi < 10 ? names[sgi] : "?", t0, dt);
-		}
-		fprintf(stderr, "[bcd_b200 trace] total %8.3f\n", h->timings.total_ms);
-	}
+	if(h->trace)
+		fprintf(stderr, "[bcd_b200 trace] dev %d total %8.3f\n", h->device, h->timings.total_ms);
 	h->stats.kernel_launches = h->launches;
 	return 0;
 }
@@ -706,7 +628,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 	// global X scratch only when n_max x d does not fit shared memory next to the d x d inverse
 	const size_t xBytes = (size_t)g.Ns * g.d * 4;
 	if(xBytes + (size_t)g.d * g.d * 4 + 8 * 1024 > 190 * 1024)
-		CU(h->fX.reserve(xBytes * 148 * 2));
+		CU(h->fX.reserve(xBytes * h->smCount * 2));
 	while((int)h->ownAuxLevel.size() < nl - 1)
 	{
 		int lo = 0, hi = 0;
@@ -715,8 +637,6 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 		CU(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, hi));
 		h->ownAuxLevel.push_back(a);
 	}
-	for(int i = 0; i < 6; ++i)
-		if(!h->fev[i]) CU(cudaEventCreate(&h->fev[i]));
 	for(int i = 0; i < 2; ++i)
 		if(!h->evTotal[i]) CU(cudaEventCreate(&h->evTotal[i]));
 	return 0;
@@ -763,7 +683,7 @@ int checkImages(const bcd_b200_images* in)
 	return 0;
 }
 
-} // namespace
+} // namespace bcdeng
 
 extern "C"
 {
@@ -838,6 +758,11 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		e = getenv("BCD_B200_EIG_GROUP");
 		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
 			g_eigGroup = atoi(e);
+		e = getenv("BCD_B200_TRACE");
+		h->trace = e && e[0] == '1';
+		int sms = 0;
+		if(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+			h->smCount = sms;
 	}
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));
@@ -883,16 +808,21 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	for(auto& L : h->levels)
 	{
 		DevBuf* lb[] = {&L.ownColor, &L.ownNs, &L.ownHist, &L.ownCov, &L.altColor, &L.altNs, &L.altHist, &L.altCov, &L.out, &L.smask, &L.counts, &L.pre, &L.active, &L.asBits,
-				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr, &L.sPl, &L.cPl, &L.mplusl};
+				&L.progress, &L.fullList, &L.fallbackList, &L.acc, &L.pixcov, &L.ctr, &L.sPl, &L.cPl, &L.mplusl, &L.fA, &L.fMinv, &L.fMean, &L.fNoise};
 		for(DevBuf* b : lb) b->release();
 		if(L.hostCtr) cudaFreeHost(L.hostCtr);
 		if(L.evSel) cudaEventDestroy(L.evSel);
 		if(L.evMark) cudaEventDestroy(L.evMark);
 	}
-	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX};
+	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX, &h->peer.tickets};
 	for(DevBuf* b : bufs) b->release();
+	for(int side = 0; side < 2; ++side)
+		if(h->peer.nb[side] && h->peer.nbIpc[side]) cudaIpcCloseMemHandle(h->peer.nb[side]);
+	h->peer.arena.release();
+	if(h->peer.hostTimeouts) cudaFreeHost(h->peer.hostTimeouts);
+	if(h->peer.evColor) cudaEventDestroy(h->peer.evColor);
+	for(cudaEvent_t e : h->peer.evOut) cudaEventDestroy(e);
 	for(cudaEvent_t e : h->events) cudaEventDestroy(e);
-	for(int i = 0; i < 6; ++i) if(h->fev[i]) cudaEventDestroy(h->fev[i]);
 	for(int i = 0; i < 2; ++i) if(h->evTotal[i]) cudaEventDestroy(h->evTotal[i]);
 	if(h->ownAux) cudaStreamDestroy(h->ownAux);
 	if(h->ownStream) cudaStreamDestroy(h->ownStream);
@@ -1070,6 +1000,7 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));
 	h->eventsUsed = 0;
+	h->spans.clear();
 	h->launches = 0;
 	cudaStream_t st = h->stream;
 	const int s = p->nb_scales;
@@ -1250,11 +1181,13 @@ int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	memset(&h->stats, 0, sizeof(h->stats));
 	memset(&h->timings, 0, sizeof(h->timings));
 	h->eventsUsed = 0;
+	h->spans.clear();
 	h->launches = 0;
 	h->tiled = t->tile_count > 1;
 	h->imageH = t->image_height;
 	h->subRow0 = t->sub_row0; h->subRow1 = t->sub_row1;
 	h->ownRow0 = t->own_row0; h->ownRow1 = t->own_row1;
+	h->tileIndex = t->tile_index; h->tileCount = t->tile_count;
 	h->runParams = *p;
 	h->ran = false;
 	CU(cudaEventRecord(h->evTotal[0], h->stream));

@@ -1,0 +1,798 @@
+// Multi-GPU side of the C ABI (include/bcd_b200.h): peer mode of the row-tile path and the group API.
+//
+// The reference has no multi-GPU path; what is split here is its single-image loop nest
+//   Denoiser::denoise            /root/reference/src/core/Denoiser.cpp:84-212
+//   MultiscaleDenoiser::denoise  /root/reference/src/core/MultiscaleDenoiser.cpp:31-136
+// into horizontal bands, one per GPU. Design:
+//   * one handle (bcd_b200_capi.cu) per GPU holds the band plus its halo rows and runs the ordinary stage kernels on it;
+//   * the strips the bands owe each other — AS bits of the raster-order marking chain, accumulator halos, output rows
+//     for the pyramid merge — are pushed by kernels of the SENDING GPU into an arena of the RECEIVING GPU over NVLink
+//     and consumed behind an epoch flag (k_peer.cu); the systolic marking kernel chains neighbouring GPUs word by word;
+//   * every pyramid level is a pipeline of its own (marking -> filter -> halo exchange -> finalize -> row exchange) on
+//     its own stream, the list lengths stay on the device, so the host enqueues a whole frame without waiting once;
+//   * a group = the N handles of a box + one host thread each, alive across frames, behind one host-buffer call.
+#include "engine.h"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <unistd.h>
+
+using namespace bcdk;
+using namespace bcdeng;
+
+namespace
+{
+
+constexpr int ARENA_FLAG_WORDS = 16;
+// flag / ticket slots of a level: kind + side (the side of the RECEIVER the strip comes from)
+enum { SLOT_ACC = 0, SLOT_OUT_A = 2, SLOT_OUT_B = 4, SLOT_AS = 6, SLOTS_PER_LEVEL = 8 };
+constexpr int MAX_LEVELS = 16;
+constexpr int TIMEOUT_WORD = MAX_LEVELS * SLOTS_PER_LEVEL; // index of the time-out counter in the ticket buffer
+
+struct Token
+{
+	cudaIpcMemHandle_t ipc; // 64 bytes
+	uint64_t ptr;           // arena address in the exporting process
+	uint64_t bytes;
+	int64_t pid;
+	int32_t device;
+	int32_t magic;
+};
+static_assert(sizeof(Token) <= sizeof(bcd_b200_peer_token), "token layout");
+constexpr int32_t TOKEN_MAGIC = 0x42434432; // "BCD2"
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline int opposite(int side) { return side == BCD_B200_SIDE_UP ? BCD_B200_SIDE_DOWN : BCD_B200_SIDE_UP; }
+
+// arena layout of the current geometry (identical on every tile of the frame: it depends on the level widths only)
+size_t layoutArena(bcd_b200_handle* h, const bcd_b200_params& p)
+{
+	const int s = p.nb_scales, bw = p.search_radius + p.patch_radius;
+	h->peer.layout.assign(s, bcd_b200_handle::ArenaLevel());
+	size_t off = 0;
+	for(int k = 0; k < s; ++k)
+	{
+		bcd_b200_handle::ArenaLevel& a = h->peer.layout[k];
+		const int W = h->levels[k].W;
+		a.flags = off; off = alignUp(off + ARENA_FLAG_WORDS * 4, 256);
+		a.inbox = off; off = alignUp(off + (size_t)6 * markingRingPitch(W) * 4, 256);
+		a.asStrip = off; off = alignUp(off + (size_t)p.search_radius * markingRowWords(W) * 4, 256);
+		for(int side = 0; side < 2; ++side) { a.accHalo[side] = off; off = alignUp(off + (size_t)bw * W * sizeof(float4), 256); }
+		for(int use = 0; use < 2; ++use)
+			for(int side = 0; side < 2; ++side) { a.outRows[use][side] = off; off = alignUp(off + (size_t)2 * W * 3 * sizeof(float), 256); }
+	}
+	return off;
+}
+
+void applyTile(bcd_b200_handle* h, const bcd_b200_params& p, const bcd_b200_tile& t)
+{
+	h->tiled = t.tile_count > 1;
+	h->imageH = t.image_height;
+	h->subRow0 = t.sub_row0; h->subRow1 = t.sub_row1;
+	h->ownRow0 = t.own_row0; h->ownRow1 = t.own_row1;
+	h->tileIndex = t.tile_index; h->tileCount = t.tile_count;
+	h->runParams = p;
+}
+
+void closeNeighbour(bcd_b200_handle* h, int side)
+{
+	if(h->peer.nb[side] && h->peer.nbIpc[side])
+		cudaIpcCloseMemHandle(h->peer.nb[side]);
+	h->peer.nb[side] = nullptr;
+	h->peer.nbIpc[side] = false;
+}
+
+struct Ctx // what the strip helpers need
+{
+	bcd_b200_handle* h;
+	int level;
+	bcd_b200_handle::ArenaLevel a;
+	uint32_t epoch;
+	bool has[2];
+	unsigned int* tickets;
+	uint32_t* myFlags;
+	char* arena;
+};
+
+Ctx ctxOf(bcd_b200_handle* h, int k)
+{
+	Ctx c;
+	c.h = h; c.level = k; c.a = h->peer.layout[k]; c.epoch = h->peer.epoch;
+	c.has[BCD_B200_SIDE_UP] = h->tileIndex > 0;
+	c.has[BCD_B200_SIDE_DOWN] = h->tileIndex < h->tileCount - 1;
+	c.tickets = h->peer.tickets.as<unsigned int>();
+	c.arena = h->peer.arena.as<char>();
+	c.myFlags = reinterpret_cast<uint32_t*>(c.arena + c.a.flags);
+	return c;
+}
+
+// rows [row, row + rows) of a local image go to the neighbour on `side`, into `slotOff` of its arena; flag slot `slot`
+int pushRows(const Ctx& c, int side, const char* base, size_t rowBytes, int row, int rows, size_t slotOff, int slot, cudaStream_t st)
+{
+	if(!c.has[side]) return 0;
+	bcd_b200_handle* h = c.h;
+	char* nb = h->peer.nb[side];
+	// the receiver sees this strip arrive from its opposite side
+	uint32_t* flag = reinterpret_cast<uint32_t*>(nb + c.a.flags) + slot + opposite(side);
+	CU(launchPeerPush(base + (size_t)row * rowBytes, nb + slotOff, rowBytes * rows, flag, c.epoch,
+			c.tickets + c.level * SLOTS_PER_LEVEL + slot + side, st, &h->launches));
+	return 0;
+}
+
+// the strip the neighbour on `side` pushed into `slotOff` of my arena lands in rows [row, row + rows) (added when `add`)
+int recvRows(const Ctx& c, int side, char* base, size_t rowBytes, int row, int rows, size_t slotOff, int slot, bool add, cudaStream_t st)
+{
+	if(!c.has[side]) return 0;
+	bcd_b200_handle* h = c.h;
+	CU(launchPeerRecv(base + (size_t)row * rowBytes, c.arena + slotOff, rowBytes * rows, add, c.myFlags + slot + side, c.epoch,
+			c.tickets + TIMEOUT_WORD, st, &h->launches));
+	return 0;
+}
+
+// marking chain of level k in peer mode, on the level's stream
+int markPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	const Ctx c = ctxOf(h, k);
+	cudaStream_t st = auxOf(h, k);
+	const int Wp = markingRowWords(g.W), b = p.search_radius;
+	int own0, own1;
+	tileOwnedRows(h, k, own0, own1);
+	CU(cudaStreamWaitEvent(st, L.evSel, 0));
+	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
+		if(p.skip_prob > 0.f)
+		{
+			const bool ring = markingUsesRing(g);
+			const size_t rowBytes = (size_t)Wp * 4;
+			if(!ring)
+			{
+				int rc = recvRows(c, BCD_B200_SIDE_UP, (char*)L.asBits.p, rowBytes, own0 - b, b, c.a.asStrip, SLOT_AS, false, st);
+				if(rc) return rc;
+			}
+			const uint32_t* ringIn = ring && c.has[BCD_B200_SIDE_UP] ? reinterpret_cast<const uint32_t*>(c.arena + c.a.inbox) : nullptr;
+			uint32_t* ringOut = ring && c.has[BCD_B200_SIDE_DOWN] ? reinterpret_cast<uint32_t*>(h->peer.nb[BCD_B200_SIDE_DOWN] + c.a.inbox) : nullptr;
+			CU(launchMarking(L.pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, L.active.as<uint32_t>(),
+					L.asBits.as<uint32_t>(), Wp, L.progress.as<unsigned int>(), st, &h->launches,
+					&L.ctr.as<DeviceCounters>()->markTimeouts, c.epoch, ringIn, ringOut));
+			if(!ring)
+			{
+				int rc = pushRows(c, BCD_B200_SIDE_DOWN, (const char*)L.asBits.p, rowBytes, own1 - b, b, c.a.asStrip, SLOT_AS, st);
+				if(rc) return rc;
+			}
+		}
+		else
+			CU(launchAllActive(g, L.active.as<uint32_t>(), Wp, st, &h->launches));
+		CU(launchBuildLists(L.counts.as<int>(), L.active.as<uint32_t>(), Wp, g, L.fullList.as<int>(),
+				L.fallbackList.as<int>(), L.ctr.as<DeviceCounters>(), st, &h->launches));
+	});
+	CU(cudaEventRecord(L.evMark, st));
+	return 0;
+}
+
+// filter -> accumulator halos -> finalize -> output rows of level k, on the level's stream
+int filterPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const LevelGeom g = levelGeom(h, k, p);
+	const Ctx c = ctxOf(h, k);
+	cudaStream_t st = auxOf(h, k);
+	const int bw = p.search_radius + p.patch_radius;
+	int own0, own1;
+	tileOwnedRows(h, k, own0, own1);
+	CU(cudaStreamWaitEvent(st, h->peer.evColor, 0));
+	int rc = levelFilterOn(h, k, p, st, true);
+	if(rc) return rc;
+	// work counters of the level for the statistics (read after the final synchronisation)
+	CU(cudaMemcpyAsync(L.hostCtr, L.ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
+	const size_t accRow = (size_t)g.W * sizeof(float4), outRow = (size_t)g.W * 3 * sizeof(float);
+	STAGE_ON(h, st, BCD_B200_STAGE_EXCHANGE, {
+		// partial sums accumulated outside my band go to their owner and are ADDED there
+		if((rc = pushRows(c, BCD_B200_SIDE_UP, (const char*)L.acc.p, accRow, own0 - bw, bw, c.a.accHalo[BCD_B200_SIDE_DOWN], SLOT_ACC, st))) return rc;
+		if((rc = pushRows(c, BCD_B200_SIDE_DOWN, (const char*)L.acc.p, accRow, own1, bw, c.a.accHalo[BCD_B200_SIDE_UP], SLOT_ACC, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_UP, (char*)L.acc.p, accRow, own0, bw, c.a.accHalo[BCD_B200_SIDE_UP], SLOT_ACC, true, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_DOWN, (char*)L.acc.p, accRow, own1 - bw, bw, c.a.accHalo[BCD_B200_SIDE_DOWN], SLOT_ACC, true, st))) return rc;
+	});
+	STAGE_ON(h, st, BCD_B200_STAGE_FINALIZE, {
+		CU(launchFinalize(L.acc.as<float4>(), (size_t)g.W * g.H, L.out.as<float>(), st, &h->launches));
+	});
+	STAGE_ON(h, st, BCD_B200_STAGE_EXCHANGE, {
+		// 2 output rows each way: downscale + interpolate of the merge reach 2 rows into the neighbouring band
+		if((rc = pushRows(c, BCD_B200_SIDE_UP, (const char*)L.out.p, outRow, own0, 2, c.a.outRows[0][BCD_B200_SIDE_DOWN], SLOT_OUT_A, st))) return rc;
+		if((rc = pushRows(c, BCD_B200_SIDE_DOWN, (const char*)L.out.p, outRow, own1 - 2, 2, c.a.outRows[0][BCD_B200_SIDE_UP], SLOT_OUT_A, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_UP, (char*)L.out.p, outRow, own0 - 2, 2, c.a.outRows[0][BCD_B200_SIDE_UP], SLOT_OUT_A, false, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_DOWN, (char*)L.out.p, outRow, own1, 2, c.a.outRows[0][BCD_B200_SIDE_DOWN], SLOT_OUT_A, false, st))) return rc;
+	});
+	CU(cudaEventRecord(h->peer.evOut[k], st));
+	return 0;
+}
+
+// merged rows of level k (>= 1) feed the merge of level k - 1 on the neighbouring tiles
+int mergedRowsPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
+{
+	LevelBufs& L = h->levels[k];
+	const Ctx c = ctxOf(h, k);
+	cudaStream_t st = h->stream;
+	int own0, own1, rc;
+	tileOwnedRows(h, k, own0, own1);
+	const size_t outRow = (size_t)L.W * 3 * sizeof(float);
+	(void)p;
+	STAGE_ON(h, st, BCD_B200_STAGE_EXCHANGE, {
+		if((rc = pushRows(c, BCD_B200_SIDE_UP, (const char*)L.out.p, outRow, own0, 2, c.a.outRows[1][BCD_B200_SIDE_DOWN], SLOT_OUT_B, st))) return rc;
+		if((rc = pushRows(c, BCD_B200_SIDE_DOWN, (const char*)L.out.p, outRow, own1 - 2, 2, c.a.outRows[1][BCD_B200_SIDE_UP], SLOT_OUT_B, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_UP, (char*)L.out.p, outRow, own0 - 2, 2, c.a.outRows[1][BCD_B200_SIDE_UP], SLOT_OUT_B, false, st))) return rc;
+		if((rc = recvRows(c, BCD_B200_SIDE_DOWN, (char*)L.out.p, outRow, own1, 2, c.a.outRows[1][BCD_B200_SIDE_DOWN], SLOT_OUT_B, false, st))) return rc;
+	});
+	return 0;
+}
+
+int tileRun(bcd_b200_handle* h, const bcd_b200_params& p)
+{
+	if(!h->peer.enabled) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before bcd_b200_tile_setup");
+	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before upload/bind_device");
+	const bcd_b200_params& q = h->runParams;
+	if(p.patch_radius != q.patch_radius || p.search_radius != q.search_radius || p.nb_scales != q.nb_scales)
+		return fail(BCD_B200_ERR_STATE, "radii / scales differ from bcd_b200_tile_setup (w=%d b=%d s=%d)", q.patch_radius, q.search_radius, q.nb_scales);
+	if(h->H != h->subRow1 - h->subRow0 || h->W != h->peer.geomW)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "resident inputs are %dx%d but the tile was set up for %dx%d", h->W, h->H,
+				h->peer.geomW, h->subRow1 - h->subRow0);
+	for(int side = 0; side < 2; ++side)
+	{
+		const bool has = side == BCD_B200_SIDE_UP ? h->tileIndex > 0 : h->tileIndex < h->tileCount - 1;
+		if(has && !h->peer.nb[side])
+			return fail(BCD_B200_ERR_STATE, "tile %d of %d is not connected to its %s neighbour (bcd_b200_tile_connect)", h->tileIndex,
+					h->tileCount, side == BCD_B200_SIDE_UP ? "upper" : "lower");
+	}
+	CU(cudaSetDevice(h->device));
+	h->runParams = p;
+	memset(&h->stats, 0, sizeof(h->stats));
+	memset(&h->timings, 0, sizeof(h->timings));
+	h->eventsUsed = 0;
+	h->spans.clear();
+	h->launches = 0;
+	h->ran = false;
+	h->peer.epoch += 1;
+	cudaStream_t st = h->stream;
+	const int s = p.nb_scales;
+	int rc;
+	CU(cudaEventRecord(h->evTotal[0], st));
+	h->pyrHistDone = h->pyrColorDone = 0;
+	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));
+	// selection of every level on the main stream, finest first (its marking chain is the longest); each level's chain
+	// follows on the level's own stream as soon as its selection is there
+	for(int k = 0; k < s; ++k)
+	{
+		if((rc = levelSelect(h, k, p))) return rc;
+		if((rc = markPeer(h, k, p))) return rc;
+	}
+	// colour / covariance side of the pyramid, per-pixel covariances
+	if((rc = finishUpload(h))) return rc;
+	for(int k = 1; k < s; ++k)
+		if((rc = pyramidLevel(h, k, 2))) return rc;
+	for(int k = 0; k < s; ++k)
+		if((rc = levelPixelCov(h, k, p))) return rc;
+	CU(cudaEventRecord(h->peer.evColor, st));
+	// the levels' filter pipelines run side by side; coarsest first in issue order (its chain through the ranks is the
+	// shortest, so on the lower tiles it is ready first)
+	for(int k = s - 1; k >= 0; --k)
+		if((rc = filterPeer(h, k, p))) return rc;
+	// merges coarsest to finest on the main stream (MultiscaleDenoiser.cpp:79-134)
+	CU(cudaStreamWaitEvent(st, h->peer.evOut[s - 1], 0));
+	for(int k = s - 2; k >= 0; --k)
+	{
+		CU(cudaStreamWaitEvent(st, h->peer.evOut[k], 0));
+		if((rc = levelMerge(h, k))) return rc;
+		if(k > 0 && (rc = mergedRowsPeer(h, k, p))) return rc;
+	}
+	CU(cudaMemcpyAsync(h->peer.hostTimeouts, h->peer.tickets.as<unsigned int>() + TIMEOUT_WORD, sizeof(unsigned int),
+			cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(h->evTotal[1], st));
+	CU(cudaStreamSynchronize(st));
+	unsigned int markTimeouts = 0;
+	for(int k = 0; k < s; ++k)
+	{
+		const DeviceCounters c = *h->levels[k].hostCtr;
+		h->levels[k].counters = c;
+		markTimeouts += c.markTimeouts;
+		addCounters(h, c);
+	}
+	if(*h->peer.hostTimeouts || markTimeouts)
+	{
+		const unsigned int t = *h->peer.hostTimeouts;
+		CU(cudaMemsetAsync(h->peer.tickets.as<unsigned int>() + TIMEOUT_WORD, 0, sizeof(unsigned int), st));
+		CU(cudaStreamSynchronize(st));
+		return fail(BCD_B200_ERR_CUDA, "tile %d of %d: %u strip waits and %u marking hand-offs timed out (neighbouring tile lost or out of step)",
+				h->tileIndex, h->tileCount, t, markTimeouts);
+	}
+	if((rc = collectTimings(h))) return rc;
+	h->ran = true;
+	return 0;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth,
+		bcd_b200_peer_token* token_out)
+{
+	if(!h || !t || !token_out) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / tile / token");
+	int rc = checkParams(p);
+	if(rc) return rc;
+	if(hist_depth <= 0 || hist_depth > 255 || t->image_width <= 0 || t->sub_row1 <= t->sub_row0 || t->tile_count < 1 ||
+			t->tile_index < 0 || t->tile_index >= t->tile_count)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad tile (%d of %d, rows [%d,%d), %d channels)", t->tile_index, t->tile_count,
+				t->sub_row0, t->sub_row1, hist_depth);
+	if(p->nb_scales > MAX_LEVELS)
+		return fail(BCD_B200_ERR_UNSUPPORTED, "too many scales");
+	CU(cudaSetDevice(h->device));
+	CU(cudaStreamSynchronize(h->stream));
+	const int rows = t->sub_row1 - t->sub_row0;
+	if(h->haveInputs && (h->W != t->image_width || h->H != rows || h->B != hist_depth))
+		h->haveInputs = false; // resident inputs of another geometry
+	h->W = t->image_width; h->H = rows; h->B = hist_depth;
+	if(h->levels.empty()) h->levels.resize(1);
+	applyTile(h, *p, *t);
+	rc = ensureBuffers(h, *p);
+	if(rc) return rc;
+	// per-level filter scratch: the levels are filtered side by side
+	const LevelGeom g0 = makeGeom(h->W, h->H, h->B, p->patch_radius, p->search_radius);
+	const size_t perSlot = (size_t)2 * g0.d * g0.d * 4;
+	for(int k = 0; k < p->nb_scales; ++k)
+	{
+		LevelBufs& L = h->levels[k];
+		const LevelGeom g = levelGeom(h, k, *p);
+		const size_t bound = std::max<size_t>((size_t)std::max(0, g.rowEnd - g.rowBeg) * std::max(0, g.W - 2 * g.w), 1);
+		size_t chunk = ((size_t)1536 << 20 >> std::min(2 * k, 8)) / perSlot;
+		chunk = std::min(std::max<size_t>(chunk, 1024), bound);
+		L.filterChunk = (int)chunk;
+		CU(L.fA.reserve(chunk * g.d * g.d * 4));
+		CU(L.fMinv.reserve(chunk * g.d * g.d * 4));
+		CU(L.fMean.reserve(chunk * g.d * 4));
+		CU(L.fNoise.reserve(chunk * g.np * 6 * 4));
+	}
+	bcd_b200_handle::Peer& P = h->peer;
+	const size_t bytes = layoutArena(h, *p);
+	closeNeighbour(h, BCD_B200_SIDE_UP);
+	closeNeighbour(h, BCD_B200_SIDE_DOWN);
+	CU(P.arena.reserve(bytes));
+	P.arenaBytes = bytes;
+	CU(cudaMemset(P.arena.p, 0, P.arena.cap)); // flags and ring tags start from a defined state: epoch 0
+	P.epoch = 0;
+	CU(P.tickets.reserve((TIMEOUT_WORD + 4) * sizeof(unsigned int)));
+	CU(cudaMemset(P.tickets.p, 0, P.tickets.cap));
+	if(!P.hostTimeouts) CU(cudaMallocHost(&P.hostTimeouts, sizeof(unsigned int)));
+	*P.hostTimeouts = 0;
+	if(!P.evColor) CU(cudaEventCreateWithFlags(&P.evColor, cudaEventDisableTiming));
+	while((int)P.evOut.size() < p->nb_scales)
+	{
+		cudaEvent_t e;
+		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		P.evOut.push_back(e);
+	}
+	P.geomW = h->W; P.geomB = p->search_radius; P.geomWr = p->patch_radius; P.geomScales = p->nb_scales;
+	P.enabled = true;
+	CU(cudaDeviceSynchronize());
+	Token tok;
+	memset(&tok, 0, sizeof(tok));
+	if(cudaIpcGetMemHandle(&tok.ipc, P.arena.p) != cudaSuccess)
+		cudaGetLastError(); // same-process groups do not need it
+	tok.ptr = (uint64_t)(uintptr_t)P.arena.p;
+	tok.bytes = bytes;
+	tok.pid = (int64_t)getpid();
+	tok.device = h->device;
+	tok.magic = TOKEN_MAGIC;
+	memset(token_out, 0, sizeof(*token_out));
+	memcpy(token_out->bytes, &tok, sizeof(tok));
+	return 0;
+}
+
+int bcd_b200_tile_connect(bcd_b200_handle* h, int side, const bcd_b200_peer_token* neighbour)
+{
+	if(!h || side < 0 || side > 1) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / bad side");
+	if(!h->peer.enabled) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_connect called before bcd_b200_tile_setup");
+	CU(cudaSetDevice(h->device));
+	closeNeighbour(h, side);
+	if(!neighbour)
+		return 0;
+	Token tok;
+	memcpy(&tok, neighbour->bytes, sizeof(tok));
+	if(tok.magic != TOKEN_MAGIC || tok.bytes != h->peer.arenaBytes)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "neighbour token does not match this tile's geometry (arena %llu vs %llu bytes)",
+				(unsigned long long)tok.bytes, (unsigned long long)h->peer.arenaBytes);
+	if(tok.pid == (int64_t)getpid())
+	{
+		if(tok.device != h->device)
+		{
+			int can = 0;
+			CU(cudaDeviceCanAccessPeer(&can, h->device, tok.device));
+			if(!can)
+				return fail(BCD_B200_ERR_UNSUPPORTED, "device %d cannot access device %d (no peer path)", h->device, tok.device);
+			cudaError_t e = cudaDeviceEnablePeerAccess(tok.device, 0);
+			if(e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+			else if(e != cudaSuccess) return fail(BCD_B200_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", tok.device, cudaGetErrorString(e));
+		}
+		h->peer.nb[side] = reinterpret_cast<char*>((uintptr_t)tok.ptr);
+		h->peer.nbIpc[side] = false;
+	}
+	else
+	{
+		void* ptr = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&ptr, tok.ipc, cudaIpcMemLazyEnablePeerAccess);
+		if(e != cudaSuccess)
+		{
+			cudaGetLastError();
+			return fail(BCD_B200_ERR_CUDA, "cudaIpcOpenMemHandle (arena of device %d, pid %lld) failed: %s", tok.device, (long long)tok.pid,
+					cudaGetErrorString(e));
+		}
+		h->peer.nb[side] = static_cast<char*>(ptr);
+		h->peer.nbIpc[side] = true;
+	}
+	return 0;
+}
+
+int bcd_b200_tile_run(bcd_b200_handle* h, const bcd_b200_params* p)
+{
+	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");
+	if(p)
+	{
+		int rc = checkParams(p);
+		if(rc) return rc;
+	}
+	const bcd_b200_params q = p ? *p : h->runParams;
+	return tileRun(h, q);
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// group: N GPUs of one box behind one host-buffer call
+// ---------------------------------------------------------------------------------------------------------------------
+struct bcd_b200_group
+{
+	int n = 0;
+	std::vector<int> dev;
+	std::vector<bcd_b200_handle*> h;
+	bool pin = true;
+	std::vector<std::pair<const void*, size_t>> pinned;
+	// worker pool (one thread per GPU, alive across frames)
+	std::vector<std::thread> th;
+	std::mutex mu;
+	std::condition_variable cvGo, cvDone;
+	uint64_t gen = 0;
+	int pending = 0;
+	bool quit = false;
+	// barrier among the workers of a frame
+	std::mutex bmu;
+	std::condition_variable bcv;
+	int bcount = 0;
+	uint64_t bgen = 0;
+	// job
+	const bcd_b200_images* in = nullptr;
+	bcd_b200_params p;
+	float* out = nullptr;
+	int tiles = 0;
+	bool needSetup = true;
+	std::vector<int> rc;
+	std::vector<std::string> err;
+	std::vector<bcd_b200_tile> plan;
+	std::vector<bcd_b200_peer_token> tokens;
+	// geometry the tiles are connected for
+	int conW = 0, conH = 0, conB = 0, conTiles = 0, conW_ = 0, conB_ = 0, conS = 0;
+	bcd_b200_stats stats;
+	bcd_b200_timings timings;
+};
+
+namespace
+{
+
+void groupBarrier(bcd_b200_group* g, int parties)
+{
+	std::unique_lock<std::mutex> lk(g->bmu);
+	const uint64_t my = g->bgen;
+	if(++g->bcount == parties)
+	{
+		g->bcount = 0;
+		++g->bgen;
+		g->bcv.notify_all();
+	}
+	else
+		g->bcv.wait(lk, [&] { return g->bgen != my; });
+}
+
+bool anyFailed(bcd_b200_group* g)
+{
+	for(int i = 0; i < g->tiles; ++i)
+		if(g->rc[i]) return true;
+	return false;
+}
+
+void tileJob(bcd_b200_group* g, int r)
+{
+	bcd_b200_handle* h = g->h[r];
+	const bcd_b200_tile& t = g->plan[r];
+	const bcd_b200_images& in = *g->in;
+	auto note = [&](int rc) { if(rc && !g->rc[r]) { g->rc[r] = rc; g->err[r] = bcd_b200_last_error(); } };
+	if(g->needSetup)
+	{
+		note(bcd_b200_tile_setup(h, &g->p, &t, in.hist_depth, &g->tokens[r]));
+		groupBarrier(g, g->tiles);
+		if(!anyFailed(g))
+		{
+			note(bcd_b200_tile_connect(h, BCD_B200_SIDE_UP, r > 0 ? &g->tokens[r - 1] : nullptr));
+			note(bcd_b200_tile_connect(h, BCD_B200_SIDE_DOWN, r < g->tiles - 1 ? &g->tokens[r + 1] : nullptr));
+		}
+		groupBarrier(g, g->tiles);
+	}
+	if(anyFailed(g))
+		return;
+	const size_t W = (size_t)in.width;
+	bcd_b200_images sub = in;
+	sub.color = in.color + (size_t)t.sub_row0 * W * 3;
+	sub.nsamples = in.nsamples + (size_t)t.sub_row0 * W;
+	sub.hist = in.hist + (size_t)t.sub_row0 * W * in.hist_depth;
+	sub.cov = in.cov + (size_t)t.sub_row0 * W * 6;
+	sub.height = t.sub_row1 - t.sub_row0;
+	int rc = bcd_b200_upload_async(h, &sub);
+	// every tile must reach the run (its neighbours wait for its strips), so a local failure is only noted
+	if(!rc) rc = bcd_b200_tile_run(h, &g->p);
+	if(!rc) rc = bcd_b200_tile_download(h, g->out + (size_t)t.own_row0 * W * 3);
+	note(rc);
+}
+
+void workerLoop(bcd_b200_group* g, int r)
+{
+	cudaSetDevice(g->dev[r]);
+	uint64_t seen = 0;
+	for(;;)
+	{
+		{
+			std::unique_lock<std::mutex> lk(g->mu);
+			g->cvGo.wait(lk, [&] { return g->quit || g->gen != seen; });
+			if(g->quit) return;
+			seen = g->gen;
+		}
+		if(r < g->tiles)
+			tileJob(g, r);
+		{
+			std::lock_guard<std::mutex> lk(g->mu);
+			if(--g->pending == 0)
+				g->cvDone.notify_all();
+		}
+	}
+}
+
+// page-lock a host range the first time it is seen (a renderer reuses its image storage frame after frame)
+void pinRange(bcd_b200_group* g, const void* ptr, size_t bytes)
+{
+	if(!g->pin || !ptr || !bytes) return;
+	const char* a = static_cast<const char*>(ptr);
+	for(size_t i = 0; i < g->pinned.size();)
+	{
+		const char* b = static_cast<const char*>(g->pinned[i].first);
+		if(b == a && g->pinned[i].second == bytes)
+			return;
+		if(a < b + g->pinned[i].second && b < a + bytes) // overlaps a stale registration (storage was reallocated)
+		{
+			if(cudaHostUnregister(const_cast<char*>(b)) != cudaSuccess) cudaGetLastError();
+			g->pinned.erase(g->pinned.begin() + i);
+		}
+		else
+			++i;
+	}
+	if(g->pinned.size() >= 16)
+	{
+		if(cudaHostUnregister(const_cast<void*>(g->pinned.front().first)) != cudaSuccess) cudaGetLastError();
+		g->pinned.erase(g->pinned.begin());
+	}
+	cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable);
+	if(e == cudaSuccess)
+		g->pinned.push_back({ptr, bytes});
+	else
+		cudaGetLastError(); // already registered by the caller, or not registrable: the copies still work (pageable)
+}
+
+} // namespace
+
+extern "C"
+{
+
+int bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus)
+{
+	if(!out) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group pointer");
+	*out = nullptr;
+	const int ndev = bcd_b200_device_count();
+	if(ndev == 0)
+		return fail(BCD_B200_ERR_NO_DEVICE, "no CUDA device available; bcd_b200 has no CPU path");
+	if(nb_gpus <= 0) nb_gpus = device_ids ? 1 : ndev; // "all"
+	if(nb_gpus > 64) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "too many GPUs (%d)", nb_gpus);
+	bcd_b200_group* g = new bcd_b200_group();
+	g->n = nb_gpus;
+	memset(&g->stats, 0, sizeof(g->stats));
+	memset(&g->timings, 0, sizeof(g->timings));
+	{
+		const char* e = getenv("BCD_B200_PIN");
+		g->pin = !(e && e[0] == '0');
+	}
+	for(int i = 0; i < nb_gpus; ++i)
+	{
+		const int d = device_ids ? device_ids[i] : i;
+		if(d < 0 || d >= ndev)
+		{
+			bcd_b200_group_destroy(g);
+			return fail(BCD_B200_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", d, ndev);
+		}
+		bcd_b200_handle* h = nullptr;
+		int rc = bcd_b200_create(&h, d);
+		if(rc)
+		{
+			bcd_b200_group_destroy(g);
+			return rc;
+		}
+		g->dev.push_back(d);
+		g->h.push_back(h);
+	}
+	g->rc.assign(nb_gpus, 0);
+	g->err.assign(nb_gpus, std::string());
+	g->plan.resize(nb_gpus);
+	g->tokens.resize(nb_gpus);
+	if(nb_gpus > 1)
+		for(int r = 0; r < nb_gpus; ++r)
+			g->th.emplace_back(workerLoop, g, r);
+	*out = g;
+	return 0;
+}
+
+void bcd_b200_group_destroy(bcd_b200_group* g)
+{
+	if(!g) return;
+	{
+		std::lock_guard<std::mutex> lk(g->mu);
+		g->quit = true;
+	}
+	g->cvGo.notify_all();
+	for(std::thread& t : g->th) t.join();
+	// the neighbours' arenas must be unmapped before anyone frees them
+	for(bcd_b200_handle* h : g->h)
+		if(h && h->peer.enabled)
+		{
+			cudaSetDevice(h->device);
+			bcd_b200_tile_connect(h, BCD_B200_SIDE_UP, nullptr);
+			bcd_b200_tile_connect(h, BCD_B200_SIDE_DOWN, nullptr);
+		}
+	for(bcd_b200_handle* h : g->h) bcd_b200_destroy(h);
+	for(auto& r : g->pinned)
+		if(cudaHostUnregister(const_cast<void*>(r.first)) != cudaSuccess) cudaGetLastError();
+	delete g;
+}
+
+int bcd_b200_group_set_pinning(bcd_b200_group* g, int pin_host)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	g->pin = pin_host != 0;
+	return 0;
+}
+
+int bcd_b200_group_tiles(bcd_b200_group* g) { return g ? g->tiles : 0; }
+
+int bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb,
+		bcd_b200_progress_fn progress, void* user)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	if(!out_rgb) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for output image");
+	int rc = checkImages(in);
+	if(rc) return rc;
+	rc = checkParams(p);
+	if(rc) return rc;
+	const size_t np = (size_t)in->width * in->height;
+	CU(cudaSetDevice(g->dev[0]));
+	pinRange(g, in->color, np * 3 * sizeof(float));
+	pinRange(g, in->nsamples, np * sizeof(float));
+	pinRange(g, in->hist, np * in->hist_depth * sizeof(float));
+	pinRange(g, in->cov, np * 6 * sizeof(float));
+	pinRange(g, out_rgb, np * 3 * sizeof(float));
+	// as many tiles as GPUs, fewer when the frame is too small for that many bands
+	int tiles = g->n;
+	while(tiles > 1)
+	{
+		bool ok = true;
+		for(int r = 0; r < tiles && ok; ++r)
+			ok = bcd_b200_tile_plan(in->width, in->height, r, tiles, p, &g->plan[r]) == 0;
+		if(ok) break;
+		--tiles;
+	}
+	g->tiles = tiles;
+	if(tiles == 1)
+	{
+		bcd_b200_handle* h = g->h[0];
+		rc = bcd_b200_upload_async(h, in); // the host buffers outlive the call, so the transfer can stream under the run
+		if(!rc) rc = bcd_b200_run(h, p, progress, user);
+		if(!rc) rc = bcd_b200_download(h, out_rgb);
+		if(!rc)
+		{
+			g->stats = h->stats;
+			g->timings = h->timings;
+		}
+		return rc;
+	}
+	g->needSetup = !(g->conW == in->width && g->conH == in->height && g->conB == in->hist_depth && g->conTiles == tiles &&
+			g->conW_ == p->patch_radius && g->conB_ == p->search_radius && g->conS == p->nb_scales);
+	if(g->needSetup) g->conTiles = 0;
+	g->in = in;
+	g->p = *p;
+	g->out = out_rgb;
+	for(int r = 0; r < g->n; ++r) { g->rc[r] = 0; g->err[r].clear(); }
+	if(progress) progress(0.f, user);
+	{
+		std::unique_lock<std::mutex> lk(g->mu);
+		g->pending = g->n;
+		++g->gen;
+		g->cvGo.notify_all();
+		g->cvDone.wait(lk, [&] { return g->pending == 0; });
+	}
+	for(int r = 0; r < tiles; ++r)
+		if(g->rc[r])
+			return fail(g->rc[r], "tile %d of %d (device %d): %s", r, tiles, g->dev[r], g->err[r].c_str());
+	if(g->needSetup)
+	{
+		g->conW = in->width; g->conH = in->height; g->conB = in->hist_depth; g->conTiles = tiles;
+		g->conW_ = p->patch_radius; g->conB_ = p->search_radius; g->conS = p->nb_scales;
+	}
+	memset(&g->stats, 0, sizeof(g->stats));
+	memset(&g->timings, 0, sizeof(g->timings));
+	for(int r = 0; r < tiles; ++r)
+	{
+		const bcd_b200_stats& s = g->h[r]->stats;
+		g->stats.interior += s.interior; g->stats.strong += s.strong; g->stats.active += s.active; g->stats.full += s.full;
+		g->stats.fallback += s.fallback; g->stats.sum_n_full += s.sum_n_full; g->stats.kernel_launches += s.kernel_launches;
+		const bcd_b200_timings& t = g->h[r]->timings;
+		for(int i = 0; i < BCD_B200_STAGE_COUNT; ++i) g->timings.stage_ms[i] += t.stage_ms[i];
+		g->timings.total_ms = std::max(g->timings.total_ms, t.total_ms);
+	}
+	if(progress) progress(1.f, user);
+	return 0;
+}
+
+int bcd_b200_group_get_stats(bcd_b200_group* g, bcd_b200_stats* s)
+{
+	if(!g || !s) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group / output");
+	*s = g->stats;
+	return 0;
+}
+
+int bcd_b200_group_get_timings(bcd_b200_group* g, bcd_b200_timings* t)
+{
+	if(!g || !t) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group / output");
+	*t = g->timings;
+	return 0;
+}
+
+int bcd_b200_denoise_multi(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, const int32_t* device_ids,
+		int nb_gpus, bcd_b200_progress_fn progress, void* user)
+{
+	if(!out_rgb)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for output image");
+	int rc = checkImages(in);
+	if(rc) return rc;
+	rc = checkParams(p);
+	if(rc) return rc;
+	bcd_b200_group* g = nullptr;
+	rc = bcd_b200_group_create(&g, device_ids, nb_gpus);
+	if(rc) return rc;
+	bcd_b200_group_set_pinning(g, 0); // one frame: page-locking the buffers costs more than it saves
+	rc = bcd_b200_group_denoise(g, in, p, out_rgb, progress, user);
+	std::string msg = rc ? bcd_b200_last_error() : "";
+	bcd_b200_group_destroy(g);
+	if(rc) return fail(rc, "%s", msg.c_str());
+	return 0;
+}
+
+} // extern "C"

@@ -88,6 +88,15 @@ __host__ __device__ inline size_t sysPreIndex(int band, int t, int i, int lane, 
 inline size_t sysPreBytes(int W, int rows) { return (size_t)((rows > 0 ? rows : 1) + 31) / 32 * sysTEnd(W) * 128 * 16; }
 // `pre` rows are pitched to a multiple of 4 pixels so that 4-pixel groups are 16-byte aligned (cp.async 16)
 __host__ __device__ inline int prePitchOf(int W) { return (W + 3) & ~3; }
+// slots of a filter chunk [first, first + cap): the host passes the capacity, the device the list length when the host
+// never read it back (row-tile peer mode: no host hop between marking and filter)
+__device__ __forceinline__ int chunkCount(int cap, const int* countDev, int first)
+{
+	if(!countDev)
+		return cap;
+	const int left = *countDev - first;
+	return left < cap ? (left > 0 ? left : 0) : cap;
+}
 __device__ __forceinline__ bool testRowBit(const uint32_t* bits, int Wp, int y, int x)
 {
 	const int pos = x + MARK_PAD;

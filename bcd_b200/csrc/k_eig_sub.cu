@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 #include <cfloat>
 
 namespace bcdk
@@ -461,9 +462,10 @@ __device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps, float* __
 template <int G>
 __global__ void __launch_bounds__(32, G == 16 ? 24 : 14)
 k_eig_chain_sub(float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
-		int n, int np, float eps, int doClamp)
+		const int* __restrict__ countDev, int first, int n, int np, float eps, int doClamp)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
+	count = chunkCount(count, countDev, first);
 	constexpr int NM = 32 / G; // matrices per warp
 	const int sub = threadIdx.x / G, lid = threadIdx.x & (G - 1);
 	const int perMat = n * n + 7 * n + np * 6;
@@ -521,22 +523,24 @@ k_eig_chain_sub(float* __restrict__ A, float* __restrict__ MinvG, const float* _
 
 int g_eigGroup = 16; // lanes per matrix for d <= 32 (BCD_B200_EIG_GROUP = 32 selects the one-warp-per-matrix kernel)
 
-cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
-		int group, cudaStream_t st)
+cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, const int* countDev, int first,
+		int n, int np, float eps, int doClamp, int group, int smCount, cudaStream_t st)
 {
 	const int nm = 32 / group;
 	const size_t smem = (size_t)nm * (n * n + 7 * n + np * 6) * 4;
-	const int grid = (count + nm - 1) / nm;
+	// persistent warps (slot loop): two waves of the resident CTAs at most
+	const int resident = (group == 16 ? 24 : 14) * (smCount > 0 ? smCount : 148);
+	const int grid = std::min((count + nm - 1) / nm, 2 * resident);
 	cudaError_t err;
 	if(group == 16)
 	{
 		if((err = cudaFuncSetAttribute(k_eig_chain_sub<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-		k_eig_chain_sub<16><<<grid, 32, smem, st>>>(A, Minv, noise, count, n, np, eps, doClamp);
+		k_eig_chain_sub<16><<<grid, 32, smem, st>>>(A, Minv, noise, count, countDev, first, n, np, eps, doClamp);
 	}
 	else
 	{
 		if((err = cudaFuncSetAttribute(k_eig_chain_sub<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-		k_eig_chain_sub<8><<<grid, 32, smem, st>>>(A, Minv, noise, count, n, np, eps, doClamp);
+		k_eig_chain_sub<8><<<grid, 32, smem, st>>>(A, Minv, noise, count, countDev, first, n, np, eps, doClamp);
 	}
 	return cudaGetLastError();
 }

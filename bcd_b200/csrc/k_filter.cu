@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cfloat>
+#include <algorithm>
 
 namespace bcdk
 {
@@ -371,11 +372,12 @@ __device__ void meanCenterCov(float* X, int n, const LevelGeom& g, float* mean, 
 template <int NT, int DT>
 __global__ void __launch_bounds__(NT)
 k_filter_stats(const float* __restrict__ color, const float* __restrict__ pixcov, const uint32_t* __restrict__ smask,
-		LevelGeom g, const int* __restrict__ list, int first, int count,
+		LevelGeom g, const int* __restrict__ list, int first, int count, const int* __restrict__ countDev,
 		float* __restrict__ A, float* __restrict__ meanG, float* __restrict__ noiseG, float* xScratch)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	const int d = g.d, np = g.np, pw = 2 * g.w + 1, tid = threadIdx.x;
+	count = chunkCount(count, countDev, first);
 	FilterSmem s = carveFilterSmem(smemRaw, g, xScratch ? xScratch + (size_t)blockIdx.x * g.Ns * d : nullptr, false, 0);
 	for(int slot = blockIdx.x; slot < count; slot += gridDim.x)
 	{
@@ -422,11 +424,12 @@ template <int NT, int GS, int STEP, int DT>
 // d = 27: 72 registers (7 CTAs of 128 threads per SM; without the bound step 1 takes 96 and only 5 fit)
 __global__ void __launch_bounds__(NT, DT > 0 ? 7 : 1)
 k_filter_apply(const float* __restrict__ color, const uint32_t* __restrict__ smask, LevelGeom g,
-		const int* __restrict__ list, int first, int count,
+		const int* __restrict__ list, int first, int count, const int* __restrict__ countDev,
 		float* __restrict__ A, const float* __restrict__ MinvG, float* __restrict__ meanG,
 		const float* __restrict__ noiseG, float4* __restrict__ acc, float* xScratch)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
+	count = chunkCount(count, countDev, first);
 	constexpr int NG = NT / GS;
 	constexpr int PB = 4; // similar patches per group iteration: one Minv load feeds 4 FMAs (register blocking)
 	const int d = g.d, np = g.np, pw = 2 * g.w + 1, tid = threadIdx.x;
@@ -947,9 +950,10 @@ __device__ bool choleskyInverse(const EigSmem& S, int n, float eps)
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
-		int n, int np, float eps, int doClamp)
+		const int* __restrict__ countDev, int first, int n, int np, float eps, int doClamp)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
+	count = chunkCount(count, countDev, first);
 	float* f = reinterpret_cast<float*>(smemRaw);
 	EigSmem S;
 	S.M = f; f += n * n;
@@ -995,17 +999,22 @@ k_eig_chain(const float* __restrict__ A, float* __restrict__ MinvG, const float*
 // ---------------------------------------------------------------------------------------------------------------
 // launcher of the chain for one chunk of the full list
 // ---------------------------------------------------------------------------------------------------------------
+// `count` = capacity of the chunk (slots [first, first + count) of the list); countDev != nullptr: the list length lives
+// on the device (the kernels clip the chunk to it and idle CTAs leave at once), so no host read-back sits between the
+// marking stage and the filter. Grids are persistent (slot loops), capped at a few CTAs per SM.
+// ev: six events recorded around the five launches (resolved by the caller after its final synchronisation).
 template <int NT, int GS, int DT>
 static cudaError_t runFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const LevelGeom& g,
-		float minEig, const int* fullList, int first, int count, const FilterBuffers& fb, float4* acc,
-		cudaStream_t st, int* launches, float* stageMs, cudaEvent_t* ev, int eigNT)
+		float minEig, const int* fullList, int first, int count, const int* countDev, const FilterBuffers& fb, float4* acc,
+		cudaStream_t st, int* launches, cudaEvent_t* ev, int eigNT)
 {
 	const size_t smemLimit = 200 * 1024;
 	bool xInSmem = filterSmemBytes(g, true, true, NT / GS) <= smemLimit;
 	if(!xInSmem && !fb.xScratch)
 		return cudaErrorInvalidConfiguration;
 	float* xs = xInSmem ? nullptr : fb.xScratch;
-	const int grid = xInSmem ? count : (count < fb.gridCap ? count : fb.gridCap);
+	const int sms = fb.smCount > 0 ? fb.smCount : 148;
+	const int grid = std::min(count, xInSmem ? sms * 16 : fb.gridCap);
 	const size_t smStats = filterSmemBytes(g, xInSmem, false, 0);
 	const size_t smApply = filterSmemBytes(g, xInSmem, true, NT / GS);
 	const size_t smEig = ((size_t)2 * g.d * g.d + 6 * g.d + 32 + g.np * 6) * 4;
@@ -1018,73 +1027,60 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 	if((err = cudaFuncSetAttribute(kA2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
 
 	auto launchEig = [&](int doClamp) -> cudaError_t {
-		const int eg = count;
 		if(eigNT == 32 && g.d <= 32 && (g_eigGroup == 16 || g_eigGroup == 8))
-			return launchEigChainSub(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp, g_eigGroup, st);
+			return launchEigChainSub(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp, g_eigGroup, sms, st);
+		const int eg = std::min(count, sms * 8);
 		if(eigNT == 32)
 		{
 			cudaFuncSetAttribute(k_eig_chain<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
-			k_eig_chain<32><<<eg, 32, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+			k_eig_chain<32><<<eg, 32, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		else if(eigNT == 96)
 		{
 			cudaFuncSetAttribute(k_eig_chain<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
-			k_eig_chain<96><<<eg, 96, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+			k_eig_chain<96><<<eg, 96, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		else
 		{
 			cudaFuncSetAttribute(k_eig_chain<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
-			k_eig_chain<160><<<eg, 160, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, g.d, g.np, minEig, doClamp);
+			k_eig_chain<160><<<eg, 160, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		return cudaGetLastError();
 	};
 
 	if(ev) cudaEventRecord(ev[0], st);
-	kStats<<<grid, NT, smStats, st>>>(color, pixcov, smask, g, fullList, first, count, fb.A, fb.mean, fb.noise, xs);
+	kStats<<<grid, NT, smStats, st>>>(color, pixcov, smask, g, fullList, first, count, countDev, fb.A, fb.mean, fb.noise, xs);
 	if((err = cudaGetLastError()) != cudaSuccess) return err;
 	if(ev) cudaEventRecord(ev[1], st);
 	if((err = launchEig(1)) != cudaSuccess) return err;
 	if(ev) cudaEventRecord(ev[2], st);
-	kA1<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
+	kA1<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, countDev, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
 	if((err = cudaGetLastError()) != cudaSuccess) return err;
 	if(ev) cudaEventRecord(ev[3], st);
 	if((err = launchEig(0)) != cudaSuccess) return err;
 	if(ev) cudaEventRecord(ev[4], st);
-	kA2<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
+	kA2<<<grid, NT, smApply, st>>>(color, smask, g, fullList, first, count, countDev, fb.A, fb.Minv, fb.mean, fb.noise, acc, xs);
 	if((err = cudaGetLastError()) != cudaSuccess) return err;
 	if(ev) cudaEventRecord(ev[5], st);
 	*launches += 5;
-	if(ev && stageMs)
-	{
-		if((err = cudaEventSynchronize(ev[5])) != cudaSuccess) return err;
-		float t01, t12, t23, t34, t45;
-		cudaEventElapsedTime(&t01, ev[0], ev[1]);
-		cudaEventElapsedTime(&t12, ev[1], ev[2]);
-		cudaEventElapsedTime(&t23, ev[2], ev[3]);
-		cudaEventElapsedTime(&t34, ev[3], ev[4]);
-		cudaEventElapsedTime(&t45, ev[4], ev[5]);
-		stageMs[0] += t01;
-		stageMs[1] += t12 + t34;
-		stageMs[2] += t23 + t45;
-	}
 	return cudaSuccess;
 }
 
 cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const int* counts,
-		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const FilterBuffers& fb,
-		float4* acc, cudaStream_t st, int* launches, float* stageMs, cudaEvent_t* ev)
+		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const int* countDev, const FilterBuffers& fb,
+		float4* acc, cudaStream_t st, int* launches, cudaEvent_t* ev)
 {
 	(void)counts;
 	if(count <= 0)
 		return cudaSuccess;
 	if(g.d == 27) // the default patch radius: compile-time d
-		return runFilterChunk<128, 32, 27>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
+		return runFilterChunk<128, 32, 27>(color, pixcov, smask, g, minEig, fullList, first, count, countDev, fb, acc, st, launches, ev, 32);
 	if(g.d <= 32)
-		return runFilterChunk<128, 32, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 32);
+		return runFilterChunk<128, 32, 0>(color, pixcov, smask, g, minEig, fullList, first, count, countDev, fb, acc, st, launches, ev, 32);
 	if(g.d <= 96)
-		return runFilterChunk<192, 96, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 96);
+		return runFilterChunk<192, 96, 0>(color, pixcov, smask, g, minEig, fullList, first, count, countDev, fb, acc, st, launches, ev, 96);
 	if(g.d <= 160)
-		return runFilterChunk<160, 160, 0>(color, pixcov, smask, g, minEig, fullList, first, count, fb, acc, st, launches, stageMs, ev, 160);
+		return runFilterChunk<160, 160, 0>(color, pixcov, smask, g, minEig, fullList, first, count, countDev, fb, acc, st, launches, ev, 160);
 	return cudaErrorInvalidValue;
 }
 

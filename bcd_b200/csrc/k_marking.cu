@@ -801,6 +801,26 @@ k_active_from_as(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, f
 		actBits[(size_t)r * Wp + ((C + MARK_PAD) >> 5)] = v;
 }
 
+// Row tiles, systolic kernel: the AS bits of the upper tile's last six rows arrived as ring words (4 bits per block of 4
+// columns) in this tile's inbox; k_active_from_as wants them as bit-rows above the first owned row.
+__global__ void k_ring_to_asbits(const uint32_t* __restrict__ inbox, int ringPitch, int W, uint32_t* __restrict__ asBits, int Wp, int rowBeg)
+{
+	const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+	const int k = blockIdx.y;          // ring row k = image row rowBeg - 1 - k
+	const int row = rowBeg - 1 - k;
+	if(wi >= Wp || row < 0)
+		return;
+	const uint32_t* src = inbox + (size_t)k * ringPitch + SYS_PAD;
+	uint32_t v = 0u;
+	for(int bit = 0; bit < 32; ++bit)
+	{
+		const int x = wi * 32 + bit - MARK_PAD;
+		if(x >= 0 && x < W)
+			v |= ((src[x >> 2] >> (x & 3)) & 1u) << bit;
+	}
+	asBits[(size_t)row * Wp + wi] = v;
+}
+
 // m = 0: every interior pixel is processed (the mask is never consulted, DenoisingUnit.cpp:165-166)
 __global__ void k_all_active_bits(LevelGeom g, uint32_t* __restrict__ actBits, int Wp)
 {
@@ -855,6 +875,29 @@ size_t markingPreBytes(int W, int H, int b, int Pw)
 	return rowMajor > bandMajor ? rowMajor : bandMajor;
 }
 
+// true when launchMarking runs the systolic kernel for this geometry: row tiles then chain their launches through ring
+// words in peer memory (ringIn / ringOut) instead of exchanging AS bit-row strips
+static int sysBandsPerCta(const LevelGeom& g)
+{
+	const int rows = g.rowEnd - g.rowBeg;
+	if(rows <= 0 || g.b != 6 || g_forceGenericMarking || g_markingKernel != 1)
+		return 0;
+	const int bands = divUp(rows, 32);
+	const int tEnd = sysTEnd(g.W);
+	static const int cand[4] = {8, 4, 2, 1};
+	for(int i = 0; i < 4; ++i)
+	{
+		const int nw = cand[i];
+		if(nw > 1 && g_markingBandsPerCta < nw)
+			continue;
+		const size_t smem = (size_t)(nw + 1) * sysPktStride(tEnd) * 16 + 16;
+		if(smem <= 112 * 1024 && divUp(bands, nw) <= 2 * 148)
+			return nw;
+	}
+	return 0;
+}
+bool markingUsesRing(const LevelGeom& g) { return sysBandsPerCta(g) > 0; }
+
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
 		unsigned int* timeouts, uint32_t epoch, const uint32_t* ringIn, uint32_t* ringOut)
@@ -888,6 +931,10 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 				if((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
 				kern<<<divUp(bands, NWV), 32 * ((NWV) + 1), smem, st>>>(a); \
 				if((err = cudaGetLastError()) != cudaSuccess) return err; \
+				if(ringIn) { \
+					k_ring_to_asbits<<<dim3(divUp(Wp, 64), 6), 64, 0, st>>>(ringIn, a.ringPitch, g.W, asBits, Wp, g.rowBeg); \
+					*launches += 1; \
+				} \
 				dim3 ablock(32, 8), agrid(divUp(divUp(prePitch, 4), 32), divUp(rows, 8)); \
 				if(always) k_active_from_as<true><<<agrid, ablock, 0, st>>>(pre, prePitch, g, skipProb, seed, asBits, actBits, Wp); \
 				else k_active_from_as<false><<<agrid, ablock, 0, st>>>(pre, prePitch, g, skipProb, seed, asBits, actBits, Wp); \

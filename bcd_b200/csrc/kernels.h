@@ -33,8 +33,8 @@ extern int g_markingKernel; // b = 6: 1 = systolic kernel (default), 0 = shared-
 // K3e for d <= 32: lanes per matrix (16 or 8: several matrices per warp, k_eig_sub.cu; 32: one warp per matrix). Test hook
 // BCD_B200_EIG_GROUP.
 extern int g_eigGroup;
-cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, int n, int np, float eps, int doClamp,
-		int group, cudaStream_t st);
+cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, const int* countDev, int first,
+		int n, int np, float eps, int doClamp, int group, int smCount, cudaStream_t st);
 int markingPreLayout(int b); // what k_symmetrize must write: 0 generic, 1 `pre2` row-major, 2 `pre2` band-major (systolic kernel)
 size_t markingPreBytes(int W, int H, int b, int Pw); // capacity of the marking input for any kernel choice
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
@@ -42,6 +42,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 		unsigned int* timeouts = nullptr, uint32_t epoch = 1, const uint32_t* ringIn = nullptr, uint32_t* ringOut = nullptr);
 // (systolic kernel, b = 6) epoch: tag of the hand-off ring words of this launch, different from the previous launches that
 // used the same scratch; ringIn / ringOut: inbox fed by the upper row tile / inbox of the lower row tile (markingRingWords)
+bool markingUsesRing(const LevelGeom& g); // the systolic kernel serves this geometry (ringIn / ringOut are honoured)
 cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
 // work lists
 cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,
@@ -58,12 +59,21 @@ struct FilterBuffers
 	float* noise;  // chunk x np*6
 	float* xScratch; // optional global scratch for X when it does not fit shared memory (gridCap x nsmax*d)
 	int gridCap;
+	int smCount;     // multiprocessors of the device (persistent grids are sized from it)
 };
+// count: capacity of the chunk; countDev (optional): device-resident list length that clips it (no host read-back);
+// ev (optional): 6 events recorded around the 5 launches (stats | eig | apply 1 | eig | apply 2)
 cudaError_t launchFilterChunk(const float* color, const float* pixcov, const uint32_t* smask, const int* counts,
-		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const FilterBuffers& fb,
-		float4* acc, cudaStream_t st, int* launches, float* stageMs /*3: stats, eig, apply*/, cudaEvent_t* ev);
+		const LevelGeom& g, float minEig, const int* fullList, int first, int count, const int* countDev, const FilterBuffers& fb,
+		float4* acc, cudaStream_t st, int* launches, cudaEvent_t* ev);
 // halo strip added into the accumulator (row tiles)
 cudaError_t launchAddStrip(float4* acc, const float4* strip, size_t n, cudaStream_t st, int* launches);
+// peer-memory strips of the row-tile path (k_peer.cu): push = copy into the receiving GPU's arena + epoch flag there;
+// recv = wait for the local flag (bounded), then copy (or add float4) the slot into the image
+cudaError_t launchPeerPush(const void* src, void* dstPeer, size_t bytes, uint32_t* flagPeer, uint32_t epoch, unsigned int* ticket,
+		cudaStream_t st, int* launches);
+cudaError_t launchPeerRecv(void* dst, const void* slot, size_t bytes, bool addFloat4, const uint32_t* flag, uint32_t epoch,
+		unsigned int* timeouts, cudaStream_t st, int* launches);
 // K4 finalAggregation
 cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches);
 // (row f1) SpikeRemovalFilter: out-of-place; src = W*H ints of scratch

@@ -10,8 +10,25 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbcdcore_b200.so")
 SYMBOLS = ["bcd_synth_generate", "bcd_host_accumulate", "bcd_host_cxx_denoise", "bcd_host_exr_load", "bcd_host_exr_fetch",
            "bcd_host_exr_write", "bcd_host_exr_write_ex", "bcd_host_exr_last_error", "bcd_host_params_load", "bcd_host_params_write"]
+SYMBOLS += ["bcd_host_session_create", "bcd_host_session_destroy", "bcd_host_session_load", "bcd_host_session_denoise",
+            "bcd_host_session_fetch", "bcd_host_session_nb_devices_used"]
+SYNTH_LIB_PATH = os.path.join(_HERE, "libbcdsynth.so")
 DEFAULT_SEED = 20170627
 _lib = None
+_synth_lib = None
+
+
+def synth_lib():
+    """The generator alone (libbcdsynth.so: no CUDA library behind it) — what bench.py's reference arm loads."""
+    global _synth_lib
+    if _synth_lib is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `make`" % SYNTH_LIB_PATH)
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.bcd_synth_generate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int, C.c_float, C.c_float,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _synth_lib = L
+    return _synth_lib
 
 
 def lib():
@@ -33,6 +50,14 @@ def lib():
         L.bcd_host_exr_last_error.restype = C.c_char_p
         L.bcd_host_params_load.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         L.bcd_host_params_write.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_char_p, C.c_char_p, C.c_char_p]
+        L.bcd_host_session_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+        L.bcd_host_session_create.restype = C.c_void_p
+        L.bcd_host_session_destroy.argtypes = [C.c_void_p]
+        L.bcd_host_session_destroy.restype = None
+        L.bcd_host_session_load.argtypes = [C.c_void_p, fp, fp, fp, fp, C.c_int, C.c_int, C.c_int]
+        L.bcd_host_session_denoise.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float]
+        L.bcd_host_session_fetch.argtypes = [C.c_void_p, fp]
+        L.bcd_host_session_nb_devices_used.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -44,10 +69,56 @@ def synth(W, H, spp=64, seed=DEFAULT_SEED, sigma=0.6, nb_bins=20, gamma=2.2, max
     if out is None:
         out = dict(color=np.empty((rows, W, 3), np.float32), nsamples=np.empty((rows, W, 1), np.float32),
                    hist=np.empty((rows, W, 3 * nb_bins), np.float32), cov=np.empty((rows, W, 6), np.float32))
-    lib().bcd_synth_generate(W, H, spp, seed, sigma, nb_bins, gamma, max_value, row0, rows,
-                             out["color"].ctypes.data, out["nsamples"].ctypes.data, out["hist"].ctypes.data,
-                             out["cov"].ctypes.data)
+    synth_lib().bcd_synth_generate(W, H, spp, seed, sigma, nb_bins, gamma, max_value, row0, rows,
+                                   out["color"].ctypes.data, out["nsamples"].ctypes.data, out["hist"].ctypes.data,
+                                   out["cov"].ctypes.data)
     return out
+
+
+class CxxSession:
+    """A host renderer's view of the drop-in across frames: ONE bcd::Denoiser / bcd::MultiscaleDenoiser object and one
+    set of DeepImages in pageable std::vector storage (bcd_host_session_*)."""
+
+    def __init__(self, scales=1, devices=None, pin=True):
+        if devices is None:
+            ids, n = None, 0
+        elif devices == "all":
+            ids, n = None, -1
+        else:
+            ids, n = (C.c_int * len(devices))(*devices), len(devices)
+        self._s = lib().bcd_host_session_create(int(scales), ids, n, int(bool(pin)))
+        self.shape = None
+
+    def load(self, color, nsamples, hist, cov):
+        color = np.ascontiguousarray(color, np.float32)
+        H, W, _ = color.shape
+        ns = np.ascontiguousarray(nsamples, np.float32)
+        hist = np.ascontiguousarray(hist, np.float32)
+        cov = np.ascontiguousarray(cov, np.float32)
+        lib().bcd_host_session_load(self._s, color.ctypes.data, ns.ctypes.data, hist.ctypes.data, cov.ctypes.data, W, H, hist.shape[2])
+        self.shape = (H, W)
+
+    def denoise(self, tau=1.0, w=1, b=6, eps=1e-8, random_order=False, m=1.0):
+        return bool(lib().bcd_host_session_denoise(self._s, tau, w, b, eps, int(random_order), m))
+
+    def fetch(self):
+        out = np.empty(self.shape + (3,), np.float32)
+        lib().bcd_host_session_fetch(self._s, out.ctypes.data)
+        return out
+
+    def devices_used(self):
+        return int(lib().bcd_host_session_nb_devices_used(self._s))
+
+    def close(self):
+        if self._s:
+            lib().bcd_host_session_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def accumulate(samples, nb_bins=20, gamma=2.2, max_value=2.5):

@@ -7,6 +7,9 @@
 #include "MultiscaleDenoiser.h"
 #include "bcd_b200.h"
 
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <iostream>
 
 namespace bcd
@@ -26,6 +29,68 @@ namespace bcd
 			std::cerr << "Aborting denoising: input " << i_pName << " image is " << i_rImage.getWidth() << "x" << i_rImage.getHeight()
 					<< "but input color image is " << i_rColors.getWidth() << "x" << i_rColors.getHeight() << std::endl;
 		}
+	}
+
+	Denoiser::Denoiser() : IDenoiser(), m_devices(1, 0), m_allDevices(false), m_pinHostBuffers(true), m_pSession(nullptr)
+	{
+		const char* pPin = std::getenv("BCD_B200_PIN"); // "0": never page-lock the caller's image storage
+		if(pPin && pPin[0] == '0')
+			m_pinHostBuffers = false;
+		// BCD_B200_DEVICES: "all", or a comma-separated list of CUDA device ordinals
+		const char* pEnv = std::getenv("BCD_B200_DEVICES");
+		if(pEnv && *pEnv)
+		{
+			if(std::strcmp(pEnv, "all") == 0)
+			{
+				m_devices.clear();
+				m_allDevices = true;
+			}
+			else
+			{
+				std::vector<int> ids;
+				for(const char* p = pEnv; *p;)
+				{
+					char* pEnd = nullptr;
+					const long v = std::strtol(p, &pEnd, 10);
+					if(pEnd == p)
+						break;
+					ids.push_back(int(v));
+					p = (*pEnd == ',') ? pEnd + 1 : pEnd;
+				}
+				if(!ids.empty())
+					m_devices = ids;
+			}
+		}
+	}
+
+	Denoiser::~Denoiser()
+	{
+		releaseDeviceResources();
+	}
+
+	void Denoiser::releaseDeviceResources()
+	{
+		if(m_pSession)
+			bcd_b200_group_destroy(static_cast<bcd_b200_group*>(m_pSession));
+		m_pSession = nullptr;
+	}
+
+	void Denoiser::setDevice(int i_device)
+	{
+		if(m_devices.size() == 1 && m_devices[0] == i_device && !m_allDevices)
+			return;
+		releaseDeviceResources();
+		m_devices.assign(1, i_device);
+		m_allDevices = false;
+	}
+
+	void Denoiser::setDevices(const int* i_pDeviceIds, int i_nbOfDevices)
+	{
+		releaseDeviceResources();
+		m_devices.clear();
+		m_allDevices = i_nbOfDevices <= 0;
+		for(int i = 0; i < i_nbOfDevices; ++i)
+			m_devices.push_back(i_pDeviceIds ? i_pDeviceIds[i] : i);
 	}
 
 	bool Denoiser::inputsOutputsAreOk()
@@ -96,13 +161,29 @@ namespace bcd
 		params.skip_prob = m_parameters.m_markedPixelsSkippingProbability;
 		params.nb_scales = i_nbOfScales;
 
-		// the reference overwrites m_nbOfCores with the real team size (Denoiser.cpp:121); one GPU plays that role here
-		m_parameters.m_nbOfCores = 1;
+		// the device session lives as long as the object: handles, buffers, streams, peer links, page-locked ranges
+		if(!m_pSession)
+		{
+			bcd_b200_group* pGroup = nullptr;
+			const int rcCreate = bcd_b200_group_create(&pGroup, m_allDevices ? nullptr : m_devices.data(),
+					m_allDevices ? 0 : int(m_devices.size()));
+			if(rcCreate != BCD_B200_OK)
+			{
+				std::cerr << "Aborting denoising: " << bcd_b200_last_error() << std::endl;
+				return false;
+			}
+			m_pSession = pGroup;
+		}
+		bcd_b200_group* pGroup = static_cast<bcd_b200_group*>(m_pSession);
+		bcd_b200_group_set_pinning(pGroup, m_pinHostBuffers ? 1 : 0);
 
 		// the output is resized to W x H x 3 and overwritten (Denoiser.cpp:207-208)
 		m_outputs.m_pDenoisedColors->resize(images.width, images.height, 3);
-		const int rc = bcd_b200_denoise(&images, &params, m_outputs.m_pDenoisedColors->getDataPtr(), m_device,
+		const int rc = bcd_b200_group_denoise(pGroup, &images, &params, m_outputs.m_pDenoisedColors->getDataPtr(),
 				&forwardProgress, &m_progressCallback);
+		// the reference overwrites m_nbOfCores with the real team size (Denoiser.cpp:121); the GPUs that worked on the
+		// frame play that role here
+		m_parameters.m_nbOfCores = std::max(1, bcd_b200_group_tiles(pGroup));
 		if(rc != BCD_B200_OK)
 		{
 			std::cerr << "Aborting denoising: " << bcd_b200_last_error() << std::endl;

@@ -2,8 +2,10 @@
 // (include/bcd_b200_host.h). Host code only; nothing here is on the denoising hot path.
 #include "bcd_b200_host.h"
 #include "SamplesAccumulator.h"
+#ifndef BCD_SYNTH_ONLY
 #include "Denoiser.h"
 #include "MultiscaleDenoiser.h"
+#endif
 
 #include <cmath>
 #include <cstring>
@@ -119,6 +121,7 @@ extern "C" int bcd_host_accumulate(const float* samples, int width, int height, 
 	return 0;
 }
 
+#ifndef BCD_SYNTH_ONLY
 extern "C" int bcd_host_cxx_denoise(const float* color, const float* nsamples, const float* hist, const float* cov,
 		int width, int height, int hist_depth,
 		float tau, int patch_radius, int search_radius, float min_eig, int random_order, float skip_prob,
@@ -161,3 +164,81 @@ extern "C" int bcd_host_cxx_denoise(const float* color, const float* nsamples, c
 		outImg.copyDataTo(out_rgb);
 	return ok ? 1 : 0;
 }
+
+// ---- a host renderer's view of the drop-in, kept across frames (bench.py's e2e_plugin leg, tests): one Denoiser object,
+// one set of DeepImages in ordinary pageable std::vector storage, denoise() called frame after frame on them
+struct bcd_host_session
+{
+	std::unique_ptr<bcd::Denoiser> denoiser;
+	bcd::Deepimf color, nsamples, hist, cov, out;
+};
+
+extern "C" bcd_host_session* bcd_host_session_create(int nb_scales, const int* devices, int nb_devices, int pin_host)
+{
+	bcd_host_session* s = new bcd_host_session();
+	s->denoiser.reset(nb_scales > 1 ? new bcd::MultiscaleDenoiser(nb_scales) : new bcd::Denoiser());
+	if(nb_devices != 0 || devices)
+		s->denoiser->setDevices(devices, nb_devices);
+	s->denoiser->setPinHostBuffers(pin_host != 0);
+	return s;
+}
+
+extern "C" void bcd_host_session_destroy(bcd_host_session* s) { delete s; }
+
+extern "C" int bcd_host_session_load(bcd_host_session* s, const float* color, const float* nsamples, const float* hist,
+		const float* cov, int width, int height, int hist_depth)
+{
+	if(!s) return 0;
+	// resize() keeps the storage when the size is unchanged: the renderer overwrites its images in place
+	if(s->color.getWidth() != width || s->color.getHeight() != height || s->hist.getDepth() != hist_depth)
+	{
+		s->color.resize(width, height, 3);
+		s->nsamples.resize(width, height, 1);
+		s->hist.resize(width, height, hist_depth);
+		s->cov.resize(width, height, 6);
+		s->out.resize(width, height, 3);
+	}
+	s->color.copyDataFrom(color);
+	s->nsamples.copyDataFrom(nsamples);
+	s->hist.copyDataFrom(hist);
+	s->cov.copyDataFrom(cov);
+	return 1;
+}
+
+extern "C" int bcd_host_session_denoise(bcd_host_session* s, float tau, int patch_radius, int search_radius, float min_eig,
+		int random_order, float skip_prob)
+{
+	if(!s) return 0;
+	bcd::DenoiserInputs inputs;
+	inputs.m_pColors = &s->color;
+	inputs.m_pNbOfSamples = &s->nsamples;
+	inputs.m_pHistograms = &s->hist;
+	inputs.m_pSampleCovariances = &s->cov;
+	bcd::DenoiserOutputs outputs;
+	outputs.m_pDenoisedColors = &s->out;
+	bcd::DenoiserParameters parameters;
+	parameters.m_histogramDistanceThreshold = tau;
+	parameters.m_patchRadius = patch_radius;
+	parameters.m_searchWindowRadius = search_radius;
+	parameters.m_minEigenValue = min_eig;
+	parameters.m_useRandomPixelOrder = random_order != 0;
+	parameters.m_markedPixelsSkippingProbability = skip_prob;
+	bcd::IDenoiser& rDenoiser = *s->denoiser;
+	rDenoiser.setInputs(inputs);
+	rDenoiser.setOutputs(outputs);
+	rDenoiser.setParameters(parameters);
+	return rDenoiser.denoise() ? 1 : 0;
+}
+
+extern "C" int bcd_host_session_fetch(bcd_host_session* s, float* out_rgb)
+{
+	if(!s || s->out.isEmpty()) return 0;
+	s->out.copyDataTo(out_rgb);
+	return 1;
+}
+
+extern "C" int bcd_host_session_nb_devices_used(bcd_host_session* s)
+{
+	return s ? s->denoiser->getParameters().m_nbOfCores : 0;
+}
+#endif // BCD_SYNTH_ONLY

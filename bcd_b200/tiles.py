@@ -47,6 +47,9 @@ def _lib():
         L.bcd_b200_tile_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.bcd_b200_tile_end.argtypes = [C.c_void_p]
         L.bcd_b200_tile_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.bcd_b200_tile_setup.argtypes = [C.c_void_p, C.POINTER(capi.Params), C.POINTER(Tile), C.c_int, C.c_void_p]
+        L.bcd_b200_tile_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.bcd_b200_tile_run.argtypes = [C.c_void_p, C.POINTER(capi.Params)]
         L._tiles_ready = True
     return L
 
@@ -115,6 +118,41 @@ class TileWorker:
             out = np.empty((rows, self.tile.image_width, 3), np.float32)
         capi._check(_lib().bcd_b200_tile_download(self.h._h, C.c_void_p(out.ctypes.data if isinstance(out, np.ndarray) else out)))
         return out
+
+
+# ------------------------------------------------------------------------------------------ peer mode (no host hop)
+TOKEN_BYTES = 96
+
+
+def peer_setup(handle, params, tile, hist_depth=60):
+    """bcd_b200_tile_setup: sizes the tile's buffers and returns the 96-byte token of its arena."""
+    tok = C.create_string_buffer(TOKEN_BYTES)
+    capi._check(_lib().bcd_b200_tile_setup(handle._h, C.byref(params), C.byref(tile), hist_depth, tok))
+    return tok.raw
+
+
+def peer_connect(handle, side, token):
+    """bcd_b200_tile_connect: token = the neighbour's arena token (bytes), or None to disconnect."""
+    buf = C.create_string_buffer(token, TOKEN_BYTES) if token is not None else None
+    capi._check(_lib().bcd_b200_tile_connect(handle._h, side, buf))
+
+
+def peer_run(handle, params=None):
+    """bcd_b200_tile_run: the whole tile schedule; strips travel through peer memory, the host never waits in between."""
+    capi._check(_lib().bcd_b200_tile_run(handle._h, C.byref(params) if params is not None else None))
+
+
+def peer_connect_dist(handle, params, tile, dist, rank, world, hist_depth=60):
+    """One tile per rank: setup, all_gather of the arena tokens (which is also the barrier tile_run needs: every rank
+    has finished its setup), connect to the two neighbours (CUDA IPC)."""
+    tok = peer_setup(handle, params, tile, hist_depth)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, tok)
+    if rank > 0:
+        peer_connect(handle, UP, gathered[rank - 1])
+    if rank < world - 1:
+        peer_connect(handle, DOWN, gathered[rank + 1])
+    dist.barrier()
 
 
 # ------------------------------------------------------------------------------------------------------ exchanges
@@ -254,8 +292,12 @@ def make_worker(inputs_full, params, index, count, device_index=0, main_stream=N
 
 # ---------------------------------------------------------------------------------------------------------- bench
 def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_stdout_fd=None):
-    """bench.py's N > 1 arm: one row tile per rank; barrier + synchronize on both sides, max over ranks."""
+    """bench.py's N > 1 arm: one row tile per rank (one process per GPU), the tiles linked through peer memory (CUDA IPC
+    arenas over NVLink: bcd_b200_tile_setup / _connect / _run); barrier + synchronize on both sides, max over ranks.
+    BCD_B200_EXCHANGE=nccl selects the previous exchange (torch.distributed send/recv per strip) for A/B runs."""
     import json
+    import os
+    import sys
     import time
     import torch
     from . import host
@@ -266,6 +308,7 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
     t = plan(W, H, rank, world, params)
     rows = t.sub_row1 - t.sub_row0
     Bd = 60
+    use_nccl = os.environ.get("BCD_B200_EXCHANGE", "peer") == "nccl"
     pin = dict(color=torch.empty((rows, W, 3), dtype=torch.float32).pin_memory(),
                nsamples=torch.empty((rows, W, 1), dtype=torch.float32).pin_memory(),
                hist=torch.empty((rows, W, Bd), dtype=torch.float32).pin_memory(),
@@ -277,21 +320,33 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
     out_pin = torch.empty((own_rows, W, 3), dtype=torch.float32).pin_memory()
     devt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
     torch.cuda.synchronize()
-    # an explicit (non-default) stream shared by torch/NCCL and the handle: the legacy default stream has handle 0,
-    # which bcd_b200_set_stream reads as "use the handle's own stream" and would leave the strips unordered
+    # an explicit (non-default) stream shared by the torch events (and NCCL in the A/B mode) and the handle: the legacy
+    # default stream has handle 0, which bcd_b200_set_stream reads as "use the handle's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     h = capi.Handle(local_rank)
-    worker = TileWorker(h, params, t, dev, stream, None)  # one marking stream per level
-    ex = DistExchange(dist, rank, world)
+    if use_nccl:
+        worker = TileWorker(h, params, t, dev, stream, None)  # one marking stream per level
+        ex = DistExchange(dist, rank, world)
+    else:
+        h.set_streams(stream.cuda_stream, 0)
+        peer_connect_dist(h, params, t, dist, rank, world, Bd)
+        worker = TileWorker.__new__(TileWorker)
+        worker.h, worker.tile = h, t
+
+    def run_once():
+        if use_nccl:
+            run_tile(worker, ex)
+        else:
+            peer_run(h, params)
 
     def step_resident():
-        run_tile(worker, ex)
+        run_once()
 
     def step_e2e():
         h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd,
                       streamed=True)
-        run_tile(worker, ex)
+        run_once()
         worker.download(out_pin.data_ptr())
 
     def timed(fn, bind):
@@ -325,12 +380,41 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
     ms_res, stages, launches, clocks = timed(step_resident, True)
     stats = h.stats()
     ms_e2e, _, _, _ = timed(step_e2e, False)
+    # ---- parity of the N-GPU frame against the SAME frame denoised by one GPU (rank 0 gathers the bands)
+    mine = torch.from_numpy(out_pin.numpy().copy()).to(dev)
+    sizes = [None] * world
+    dist.all_gather_object(sizes, own_rows)
+    parity = None
+    if rank == 0:
+        bands = [torch.empty((r, W, 3), dtype=torch.float32, device=dev) for r in sizes]
+        bands[0].copy_(mine)
+        for r in range(1, world):
+            dist.recv(bands[r], src=r)
+        frame_n = torch.cat(bands, 0).cpu().numpy()
+        full = host.synth(W, H, spp=a.spp)
+        h1 = capi.Handle(local_rank)
+        h1.upload(**full)
+        h1.run(params)
+        frame_1 = h1.download()
+        st1 = h1.stats()
+        h1.close()
+        del full
+        import numpy as np
+        inner = (slice(2, -2), slice(2, -2))
+        den = float(np.abs(frame_1[inner]).max())
+        parity = {"rel_linf_vs_1gpu": float(np.abs(frame_n[inner] - frame_1[inner]).max() / den),
+                  "what": "the N-GPU frame of this run against the same frame denoised by one GPU (bcd_b200_run); "
+                          "only the order of the float atomics differs", "counters_1gpu": st1}
+    else:
+        dist.send(mine, dst=0)
     st = torch.tensor([float(stats[k]) for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full")], device=dev, dtype=torch.float64)
     dist.all_reduce(st, op=dist.ReduceOp.SUM)
     pair = torch.tensor([stages["pair"] / a.steps], device=dev)
     dist.all_reduce(pair, op=dist.ReduceOp.MAX)
     h2d = torch.tensor([float(sum(v.numel() * 4 for v in pin.values())), float(out_pin.numel() * 4)], device=dev)
     dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {k: round(v / a.steps, 4) for k, v in stages.items()})
     if rank == 0:
         value = W * H * a.steps / (ms_res * 1e-3) / 1e6
         e2e_val = W * H * a.steps / (ms_e2e * 1e-3) / 1e6
@@ -338,24 +422,33 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         npix_all = sum((W >> k) * (H >> k) for k in range(a.scales))
         alg_bytes = npix_all * (Bd + 1) * 4 / world          # per GPU
         achieved = alg_bytes / (float(pair.item()) * 1e-3) / 1e9
+        counters = dict(zip(("interior", "strong", "active", "full", "fallback", "sum_n_full"), [int(v) for v in st.tolist()]))
+        if parity is not None:
+            parity["counters_equal"] = all(counters[k] == parity["counters_1gpu"][k] for k in counters)
         line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": B.UNIT, "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
-                        "ms_per_step": ms_e2e / a.steps, "api": "per rank: bcd_b200_upload(tile rows) + tile stages + bcd_b200_tile_download"},
+                        "ms_per_step": ms_e2e / a.steps,
+                        "api": "per rank: bcd_b200_upload_async(tile rows, pinned) + bcd_b200_tile_run + bcd_b200_tile_download"},
                 "gpu_launches": launches,
+                "exchange": "nccl send/recv per strip (A/B mode)" if use_nccl else
+                            "peer memory: strips pushed into the neighbour's arena over NVLink (CUDA IPC), epoch flags, marking ring chained GPU to GPU; no NCCL call and no host hop inside a frame",
                 "roofline": {"kernel": "k_pair_terms_sparse (per GPU, slowest rank)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
                              "note": "FP32-issue-bound kernel; see the N=1 line for the FP32 figure"},
                 "stage_ms_per_step_rank0": {k: v / a.steps for k, v in stages.items()},
-                "work_counters": dict(zip(("interior", "strong", "active", "full", "fallback", "sum_n_full"), [int(v) for v in st.tolist()])),
+                "stage_ms_per_step_by_rank": per_rank,
+                "work_counters": counters, "parity": parity,
                 "input_generation_s": gen_s}
-        import os
-        import sys
         sys.stdout.flush()
         if saved_stdout_fd is not None:
             os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
+    if not use_nccl:  # unmap the neighbours' arenas before anyone frees its own
+        peer_connect(h, UP, None)
+        peer_connect(h, DOWN, None)
+    dist.barrier()
     h.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -27,6 +27,9 @@ import sys
 import threading
 import time
 
+# every stream of a handle gets its own hardware queue (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -49,6 +52,9 @@ def parse():
     ap.add_argument("--b", type=int, default=6)
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the e2e_plugin leg (bcd::MultiscaleDenoiser::denoise() on pageable buffers)")
+    ap.add_argument("--alt-spp", type=int, default=48, help="second resident measurement with this sample count (not a power of two); 0 = skip")
+    ap.add_argument("--parity-crop", type=int, default=256, help="window of the single-thread reference run the frame's parity is checked on (m > 0)")
     ap.add_argument("--cpu-crop", type=int, default=768, help="side of the square crop the CPU reference is timed on (768: about 5 s of CPU work on 16 threads, 25 s on 8)")
     return ap.parse_args()
 
@@ -187,26 +193,40 @@ def gpu_uuid(local_rank):
 
 
 # ------------------------------------------------------------------------------------------------------ CPU reference
-def cpu_reference_sample(inputs, crop, scales, m, w, b, cores=0):
-    """Times the unmodified reference (oracle/_ref) on a crop x crop window of the frame, all host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracles as O
+def host_threads():
+    """Host threads the CPU reference may use: the affinity mask of this process (torchrun exports OMP_NUM_THREADS=1
+    for nproc > 1, which an explicit m_nbOfCores overrides — reference Denoiser.cpp:112-115)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def centre_crop(inputs, crop):
     H, W, _ = inputs["color"].shape
     c = min(crop, H, W)
     y0, x0 = (H - c) // 2, (W - c) // 2  # centred: straddles the albedo-texture boundary at x = W/2
-    sub = {k: np.ascontiguousarray(v[y0:y0 + c, x0:x0 + c]) for k, v in inputs.items()}
+    return {k: np.ascontiguousarray(v[y0:y0 + c, x0:x0 + c]) for k, v in inputs.items()}, c
+
+
+def cpu_reference_sample(inputs, crop, scales, m, w, b, cores=None):
+    """Times the unmodified reference (oracle/_ref) on a crop x crop window of the frame, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles as O
+    sub, c = centre_crop(inputs, crop)
     kind = "reference" if O.have_ref() else "port"
+    cores = host_threads() if cores is None else cores
     t = time.perf_counter()
     if kind == "reference":
-        O.ref_denoise(**sub, cores=cores, m=m, scales=scales, w=w, b=b, random_order=False)
-        ncores = O.ref_lib().bcdref_max_threads()
+        out = O.ref_denoise(**sub, cores=cores, m=m, scales=scales, w=w, b=b, random_order=False)
+        ncores = cores
     else:
-        O.port_denoise(**sub, m=m, scales=scales, w=w, b=b)
+        out = O.port_denoise(**sub, m=m, scales=scales, w=w, b=b)
         ncores = 1
     dt = time.perf_counter() - t
-    return {"value": c * c / dt / 1e6, "unit": UNIT, "cores": int(ncores), "kind": kind, "seconds": dt,
+    return {"value": c * c / dt / 1e6, "unit": UNIT, "cores": int(ncores), "kind": kind, "seconds": dt, "crop": c, "out": out,
             "sample": "%dx%d centre crop of the same synthetic frame, s=%d m=%g b=%d w=%d, raster order, %s" % (
-                c, c, scales, m, b, w, "OpenMP all cores" if kind == "reference" else "scalar C port")}
+                c, c, scales, m, b, w, "OpenMP, %d threads (m_nbOfCores set explicitly)" % ncores if kind == "reference" else "scalar C port")}
 
 
 def peaks():
@@ -235,24 +255,39 @@ def main():
               "l2_policy": "inputs (%.0f MB) exceed the 126 MB L2; no explicit flush" % (W * H * 280 / 1e6),
               "parallelism": "1 GPU" if n_gpus == 1 else "row tiles x%d (one rank per GPU)" % n_gpus}
 
+    # torchrun exports OMP_NUM_THREADS=1 for nproc > 1: the synthetic-input generator (OpenMP) would crawl. Give every
+    # rank its share of the host threads before any OpenMP runtime is loaded.
+    if world > 1 or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // (1 if a.impl == "reference" else world)))
+
     from bcd_b200 import host
 
     # ---------------------------------------------------------------------------------------------- reference arm
     if a.impl == "reference":
         if rank != 0:
             return 0
+        # nothing of the product path is mapped here: the generator comes from libbcdsynth.so (no CUDA library behind
+        # it), the timed call is bcdref_denoise of oracle/_ref/libbcd_ref.so (the reference compiled in place)
         inp = host.synth(W, H, spp=a.spp)
-        times = []
-        info = None
+        crop = min(a.cpu_crop, W, H)
+        budget_s = 200.0  # the whole --steps K --warmup W run must end within a few minutes
+        times, info = [], None
         for i in range(a.warmup + a.steps):
-            info = cpu_reference_sample(inp, a.cpu_crop, a.scales, a.m, a.w, a.b)
+            info = cpu_reference_sample(inp, crop, a.scales, a.m, a.w, a.b)
+            if i == 0 and info["seconds"] * (a.warmup + a.steps) > budget_s:
+                # first sample too slow for K + W repeats on this host: shrink the window (Mpix/s is size-independent
+                # to first order: the clipped-window border is a few percent of these crops)
+                scale = (budget_s / (info["seconds"] * (a.warmup + a.steps))) ** 0.5
+                crop = max(192, int(crop * scale) // 64 * 64)
             if i >= a.warmup:
-                times.append(info["seconds"])
-        c = min(a.cpu_crop, W, H)
-        val = c * c * len(times) / sum(times) / 1e6
+                times.append((info["crop"], info["seconds"]))
+        pix = sum(c * c for c, _ in times)
+        secs = sum(t for _, t in times)
+        val = pix / secs / 1e6
         info["value"] = val
+        config["workload"] = workload + " — reference arm: each step denoises a %dx%d centre crop of that frame" % (times[-1][0], times[-1][0])
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                "warmup": a.warmup, "ms_per_step": 1e3 * secs / len(times), "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -345,6 +380,54 @@ def main():
     ms_e2e_serial, _, _, _ = timed(step_e2e_serial, False)
     result_ok = bool(np.isfinite(out_pin.numpy()[2:-2, 2:-2]).all())
 
+    # ---- the plugin call itself: ONE bcd::MultiscaleDenoiser object and pageable std::vector DeepImages, denoise() per
+    #      frame (what a host renderer / the reference's GUI does, src/gui/GuiWindow.cpp:345-376). First call = device
+    #      session created, buffers allocated, image storage page-locked; steady state = every call after it.
+    e2e_plugin = None
+    if not a.no_plugin:
+        sess = host.CxxSession(scales=a.scales, devices=[local_rank])
+        sess.load(**{k: v.numpy() for k, v in pin.items()})
+        t0 = time.perf_counter()
+        ok_first = sess.denoise(m=a.m, w=a.w, b=a.b)
+        first_ms = (time.perf_counter() - t0) * 1e3
+        for _ in range(max(0, a.warmup - 1)):
+            sess.denoise(m=a.m, w=a.w, b=a.b)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            ok_first = sess.denoise(m=a.m, w=a.w, b=a.b) and ok_first
+        steady_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+        plug = sess.fetch()
+        sess.close()
+        ref_img = out_pin.numpy()
+        e2e_plugin = {"value": W * H / (steady_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": steady_ms, "first_call_ms": first_ms,
+                      "ok": bool(ok_first), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "rel_linf_vs_handle_api": float(np.abs(plug[2:-2, 2:-2] - ref_img[2:-2, 2:-2]).max() / np.abs(ref_img[2:-2, 2:-2]).max()),
+                      "api": "bcd::MultiscaleDenoiser::denoise() on one persistent object, DeepImage storage in pageable std::vector "
+                             "(page-locked by the object on first sight), host wall clock around denoise()"}
+
+    # ---- the path a renderer with a non-power-of-two / adaptive sample count takes (K1a's uniform-2^k shortcut is off)
+    nonuniform = None
+    if a.alt_spp > 0 and a.alt_spp != a.spp:
+        alt = host.synth(W, H, spp=a.alt_spp)
+        h.upload(**alt)
+        del alt
+        for _ in range(a.warmup):
+            h.run(params)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc_pair = 0.0
+        e0.record(stream)
+        for _ in range(a.steps):
+            h.run(params)
+            acc_pair += h.timings()["pair"]
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_alt = e0.elapsed_time(e1) / a.steps
+        nonuniform = {"spp": a.alt_spp, "value": W * H / (ms_alt * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_alt,
+                      "pair_ms_per_step": acc_pair / a.steps, "work_counters": h.stats(),
+                      "what": "same workload with %d samples per pixel: n is not a power of two, so the pair-term kernel evaluates the "
+                              "reference's full term (13 packed operations per visited bin instead of 9)" % a.alt_spp}
+
     value = W * H * a.steps / (ms_res * 1e-3) / 1e6
     e2e_val = W * H * a.steps / (ms_e2e * 1e-3) / 1e6
 
@@ -391,9 +474,28 @@ def main():
             "stage_ms_per_step": {k: v / a.steps for k, v in stages.items()},
             "stage_ms_per_step_e2e": {k: v / a.steps for k, v in stages_e2e.items()},
             "work_counters": stats, "input_generation_s": gen_s, "output_finite": result_ok}
+    if e2e_plugin is not None:
+        line["e2e_plugin"] = e2e_plugin
+    if nonuniform is not None:
+        line["nonuniform_n"] = nonuniform
     if not a.no_cpu_baseline:
-        cb = cpu_reference_sample({k: v.numpy() for k, v in pin.items()}, a.cpu_crop, a.scales, a.m, a.w, a.b)
+        frame = {k: v.numpy() for k, v in pin.items()}
+        cb = cpu_reference_sample(frame, a.cpu_crop, a.scales, a.m, a.w, a.b)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # parity of this very frame: the CUDA path against the reference on the same window. With the marking strategy
+        # (m = 1) the reference is only deterministic on ONE thread in raster order (SURVEY finding 2), so that case
+        # pays a second, smaller single-thread run; for m = 0 the timed multi-thread run above is the checker.
+        if a.m > 0:
+            chk = cpu_reference_sample(frame, a.parity_crop, a.scales, a.m, a.w, a.b, cores=1)
+        else:
+            chk = cb
+        sub, c = centre_crop(frame, chk["crop"])
+        h.upload(**sub)
+        h.run(params)
+        ours = h.download(np.empty((c, c, 3), np.float32))
+        line["parity"] = {"rel_linf": float(np.abs(ours - chk["out"]).max() / np.abs(chk["out"]).max()), "tolerance": 1e-4,
+                          "sample": chk["sample"], "checker": chk["kind"],
+                          "what": "bcd_b200_run on that window vs the CPU reference on the same window (max|a-b| / max|ref|)"}
     print(json.dumps(line))
     h.close()
     return 0

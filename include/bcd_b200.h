@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCD_B200_ABI_VERSION 1
+#define BCD_B200_ABI_VERSION 2
 
 typedef enum bcd_b200_status {
 	BCD_B200_OK = 0,
@@ -79,7 +79,8 @@ typedef struct bcd_b200_stats {
 enum { BCD_B200_STAGE_PREPASS = 0, BCD_B200_STAGE_PAIR = 1, BCD_B200_STAGE_SELECT = 2, BCD_B200_STAGE_MARKING = 3,
        BCD_B200_STAGE_FALLBACK = 4, BCD_B200_STAGE_FILTER_STATS = 5, BCD_B200_STAGE_FILTER_EIG = 6,
        BCD_B200_STAGE_FILTER_APPLY = 7, BCD_B200_STAGE_FINALIZE = 8, BCD_B200_STAGE_PYRAMID = 9,
-       BCD_B200_STAGE_COUNT = 10 };
+       BCD_B200_STAGE_EXCHANGE = 10, /* row tiles: strips pushed to / awaited from the neighbouring GPUs */
+       BCD_B200_STAGE_COUNT = 11 };
 typedef struct bcd_b200_timings {
 	float stage_ms[BCD_B200_STAGE_COUNT];
 	float total_ms;
@@ -207,6 +208,47 @@ int  bcd_b200_tile_export(bcd_b200_handle* h, int level, int what, int side, voi
 int  bcd_b200_tile_import(bcd_b200_handle* h, int level, int what, int side, const void* dev_buf);
 int  bcd_b200_tile_end(bcd_b200_handle* h);                 /* synchronises, collects stats/timings */
 int  bcd_b200_tile_download(bcd_b200_handle* h, float* out_rows /* (own_row1-own_row0) * W * 3 */);
+
+/* ---- peer mode of the row-tile API: the tiles exchange their strips through peer memory (NVLink) -----------------------
+ * The strips of the table above travel without any host or NCCL hop: every tile owns an "arena" (one device allocation)
+ * into which its neighbours' kernels push their rows, followed by an epoch flag; the consuming kernels wait for the flag
+ * on the device. The systolic marking kernel (b = 6) even chains its launches on neighbouring GPUs word by word — the
+ * raster-order dependency crosses the tile boundary at the pace of the wavefront instead of tile by tile.
+ *   tile_setup    sizes the buffers for tile t of a W x H frame (hist_depth channels) and returns the token of the arena;
+ *   tile_connect  makes the arena of the neighbour on `side` writable from this GPU: same process -> peer access,
+ *                 other process -> CUDA IPC (the 96 token bytes travel by any means, e.g. an all_gather at start-up);
+ *   tile_run      the whole schedule of the table above on the resident rows of the tile (upload / bind them first), all
+ *                 tiles of the frame concurrently (one thread or process each, every tile the same number of runs since
+ *                 its setup; all tiles must have finished tile_setup before the first one runs). Returns after this
+ *                 tile's rows are done; tile_download fetches them.
+ * Every wait is bounded (~4 s): a lost neighbour makes tile_run fail with BCD_B200_ERR_CUDA, it never hangs the GPU. */
+typedef struct bcd_b200_peer_token { unsigned char bytes[96]; } bcd_b200_peer_token;
+int  bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth,
+                         bcd_b200_peer_token* token_out);
+int  bcd_b200_tile_connect(bcd_b200_handle* h, int side, const bcd_b200_peer_token* neighbour /* NULL: disconnect */);
+int  bcd_b200_tile_run(bcd_b200_handle* h, const bcd_b200_params* p /* NULL: the parameters of tile_setup; same radii / scales */);
+
+/* ---- group API: N GPUs of one box behind one call (what bcd::Denoiser / bcd::MultiscaleDenoiser hold) -----------------
+ * A group owns one handle and one host thread per GPU, keeps every device allocation, stream and peer link across
+ * frames and page-locks the caller's buffers the first time it sees them (a renderer hands over the same DeepImage
+ * storage frame after frame; reference call sites src/cli/main.cpp:457-468, src/gui/GuiWindow.cpp:345-376).
+ * group_denoise: host buffers in, host buffer out, like bcd_b200_denoise. With nb_gpus > 1 the frame is cut into row
+ * tiles (bcd_b200_tile_plan), every GPU streams its rows from the host buffers and the tiles run in peer mode; the
+ * number of tiles is reduced when the frame is too small for nb_gpus bands. device_ids may repeat a device (tests on a
+ * one-GPU box). pin_host: 1 = cudaHostRegister the five host ranges (cached per pointer), 0 = leave them pageable. */
+typedef struct bcd_b200_group bcd_b200_group;
+int  bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus);
+void bcd_b200_group_destroy(bcd_b200_group* g);
+int  bcd_b200_group_set_pinning(bcd_b200_group* g, int pin_host);
+int  bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb,
+                            bcd_b200_progress_fn progress, void* user);
+/* counters summed over the tiles; timings: per-stage sums over the tiles, total_ms = the slowest tile */
+int  bcd_b200_group_get_stats(bcd_b200_group* g, bcd_b200_stats* s);
+int  bcd_b200_group_get_timings(bcd_b200_group* g, bcd_b200_timings* t);
+int  bcd_b200_group_tiles(bcd_b200_group* g); /* tiles the last frame was cut into */
+/* one-shot multi-GPU variant of bcd_b200_denoise (creates and destroys a group) */
+int  bcd_b200_denoise_multi(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, const int32_t* device_ids,
+                            int nb_gpus, bcd_b200_progress_fn progress, void* user);
 
 /* ---- stage-level read-backs used by the parity tests (level 0 of the last run) ---------------------------------
  * masks: W*H*words uint32, bit index (dy+b)*(2b+1)+(dx+b) — the ordered similar set S(p) of

@@ -33,6 +33,21 @@ int bcd_host_cxx_denoise(const float* color, const float* nsamples, const float*
                          float tau, int patch_radius, int search_radius, float min_eig, int random_order, float skip_prob,
                          int nb_scales, int device, float* out_rgb, int* progress_calls);
 
+/* The same drop-in seen by a host renderer that keeps its objects: ONE bcd::Denoiser / bcd::MultiscaleDenoiser and one
+ * set of DeepImages in pageable std::vector storage, denoise() called frame after frame (reference call site
+ * src/gui/GuiWindow.cpp:345-376). devices == NULL && nb_devices == 0: the object's default (device 0 or BCD_B200_DEVICES);
+ * nb_devices < 0: every visible GPU. load = the renderer writing a frame into its images (not part of denoise());
+ * denoise returns 1 when denoise() returned true; fetch copies the output image. */
+typedef struct bcd_host_session bcd_host_session;
+bcd_host_session* bcd_host_session_create(int nb_scales, const int* devices, int nb_devices, int pin_host);
+void bcd_host_session_destroy(bcd_host_session* s);
+int bcd_host_session_load(bcd_host_session* s, const float* color, const float* nsamples, const float* hist, const float* cov,
+                          int width, int height, int hist_depth);
+int bcd_host_session_denoise(bcd_host_session* s, float tau, int patch_radius, int search_radius, float min_eig,
+                             int random_order, float skip_prob);
+int bcd_host_session_fetch(bcd_host_session* s, float* out_rgb);
+int bcd_host_session_nb_devices_used(bcd_host_session* s); /* m_nbOfCores after denoise(): GPUs that worked on the frame */
+
 /* bcd::ImageIO from C (tests): load returns 1 and the image size (HWC float32; multi_channel = 0: R,G,B file -> depth 3,
  * or 1 for a grey file; 1: Bin_%04d file), fetch copies the pixels of the image loaded last by this thread; write
  * returns 1 on success. bcd_host_exr_last_error: message of the last failure. */

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the multi-tile tests run several handles (7 streams each) on one device, some of them with kernels that wait for a
+# neighbouring tile: every stream needs its own hardware queue (the library asks for the same when it is loaded first)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 

@@ -20,7 +20,7 @@ def test_bcd_b200_h_symbols_exported():
     for n in names:
         assert hasattr(L, n), "symbol %s declared in include/bcd_b200.h is not exported" % n
     assert sorted(capi.SYMBOLS) == names
-    assert L.bcd_b200_abi_version() == 1
+    assert L.bcd_b200_abi_version() == 2
 
 
 def test_host_header_symbols_exported():

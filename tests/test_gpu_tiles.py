@@ -76,3 +76,102 @@ def test_too_small_tiles_are_rejected():
     from bcd_b200 import capi, tiles
     with pytest.raises(capi.BcdError):
         tiles.plan(64, 96, 0, 8, capi.make_params(scales=3))
+
+
+# ------------------------------------------------------------------------------------------- peer mode / group API
+def _counters_equal(a, b):
+    for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full"):
+        assert a[k] == b[k], (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("count,kw", [
+    (2, dict(m=1.0, scales=1)),
+    (2, dict(m=0.0, scales=2)),
+    (3, dict(m=1.0, scales=3)),
+    (4, dict(m=1.0, scales=2)),
+    (2, dict(m=1.0, scales=2, b=4)),          # marking kernel without a ring: the AS rows travel as a strip
+    (2, dict(m=1.0, scales=1, w=2, b=5)),
+])
+def test_group_tiles_on_one_device_equal_full_frame(count, kw):
+    """The group API in peer mode (bcd_b200_group_denoise: one host thread per tile, strips pushed into the neighbour's
+    arena and awaited on the device, marking ring chained from tile to tile) with every tile on device 0."""
+    from bcd_b200 import capi, host
+    inp = host.synth(120, 208, spp=24)
+    ref, st_ref = _full(capi, inp, **kw)
+    g = capi.Group([0] * count)
+    try:
+        out = g.denoise(**inp, **kw)
+        assert g.tiles() == count
+        _counters_equal(g.stats(), st_ref)
+        assert O.rel_linf(out, ref) <= 2e-6  # only the order of the float atomics differs
+        # a second, different frame through the same group: epochs advance, buffers / links / pinned ranges are reused
+        inp2 = host.synth(120, 208, spp=16, seed=7)
+        ref2, st_ref2 = _full(capi, inp2, **kw)
+        out2 = g.denoise(**inp2, **kw)
+        _counters_equal(g.stats(), st_ref2)
+        assert O.rel_linf(out2, ref2) <= 2e-6
+        # another geometry: the tiles are set up and connected again
+        inp3 = host.synth(96, 160, spp=16, seed=11)
+        ref3, _ = _full(capi, inp3, **kw)
+        assert O.rel_linf(g.denoise(**inp3, **kw), ref3) <= 2e-6
+    finally:
+        g.close()
+
+
+def test_group_reduces_the_tile_count_for_small_frames():
+    from bcd_b200 import capi, host
+    inp = host.synth(64, 96, spp=16)
+    ref, _ = _full(capi, inp, m=1.0, scales=3)
+    g = capi.Group([0] * 8)
+    try:
+        out = g.denoise(**inp, m=1.0, scales=3)
+        assert 1 <= g.tiles() < 8
+        assert O.rel_linf(out, ref) <= 2e-6
+    finally:
+        g.close()
+
+
+def test_group_matches_reference_golden(crop_a):
+    from conftest import inputs_of
+    from bcd_b200 import capi
+    out = capi.denoise_multi(**inputs_of(crop_a), devices=[0, 0], m=1.0, scales=1)
+    assert O.rel_linf(out, crop_a["ref_s1_m1"]) <= 1e-4
+
+
+def test_group_on_several_gpus_equals_one_gpu():
+    """Real peer memory: one tile per GPU over NVLink. Skipped on a one-GPU box."""
+    from bcd_b200 import capi, host
+    n = capi.lib().bcd_b200_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = min(n, 8)
+    inp = host.synth(640, 64 * n + 40, spp=16)
+    for kw in (dict(m=1.0, scales=3), dict(m=0.0, scales=1), dict(m=1.0, scales=2, b=4)):
+        ref, st_ref = _full(capi, inp, **kw)
+        g = capi.Group(list(range(n)))
+        try:
+            for _ in range(3):
+                out = g.denoise(**inp, **kw)
+                assert g.tiles() == n
+                _counters_equal(g.stats(), st_ref)
+                assert O.rel_linf(out, ref) <= 2e-6
+        finally:
+            g.close()
+
+
+def test_cxx_session_keeps_its_device_session_across_frames():
+    """bcd::MultiscaleDenoiser as a renderer holds it: one object, pageable DeepImage storage, denoise() per frame. The
+    second frame reuses handle, buffers and page-locked ranges and must give the same pixels as the C ABI."""
+    from bcd_b200 import capi, host
+    kw = dict(m=1.0, scales=3)
+    s = host.CxxSession(scales=3, devices=[0, 0])
+    try:
+        for seed in (3, 5, 3):
+            inp = host.synth(160, 176, spp=16, seed=seed)
+            ref, _ = _full(capi, inp, **kw)
+            s.load(**inp)
+            assert s.denoise(m=1.0)
+            assert s.devices_used() == 2
+            assert O.rel_linf(s.fetch(), ref) <= 2e-6
+    finally:
+        s.close()
