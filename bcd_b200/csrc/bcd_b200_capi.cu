@@ -28,7 +28,13 @@ thread_local std::string g_lastError;
 // this only has an effect when the library is loaded before the CUDA context exists.
 struct ConnectionsDefault
 {
-	ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+	ConnectionsDefault()
+	{
+		setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+		// kernels are loaded with the context instead of at their first launch: a lazy load waits for the device to go
+		// idle, which a tile whose kernels wait for a neighbour never is (bcd_b200_tile_setup warms up as well)
+		setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+	}
 } g_connectionsDefault;
 }
 
@@ -64,6 +70,17 @@ int takeEvent(bcd_b200_handle* h, int* idx)
 		h->events.push_back(e);
 	}
 	*idx = (int)h->eventsUsed++;
+	return 0;
+}
+
+int reserveEvents(bcd_b200_handle* h, size_t count)
+{
+	while(h->events.size() < count)
+	{
+		cudaEvent_t e;
+		CU(cudaEventCreate(&e));
+		h->events.push_back(e);
+	}
 	return 0;
 }
 
@@ -683,6 +700,42 @@ int checkImages(const bcd_b200_images* in)
 	return 0;
 }
 
+// streams / events of the streamed upload and the storage of the level-0 inputs. Device allocations and stream creation
+// synchronise with running kernels, so row tiles do this in bcd_b200_tile_setup — never while a neighbouring tile's
+// kernel may already be waiting for this one.
+int prepareUpload(bcd_b200_handle* h, int width, int height, int histDepth)
+{
+	if(h->levels.empty()) h->levels.resize(1);
+	LevelBufs& L = h->levels[0];
+	bcd_b200_handle::Upload& up = h->up;
+	if(!up.copy)
+	{
+		CU(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&up.evAll, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&up.evOrder, cudaEventDisableTiming));
+		{
+			// high priority: the short selection kernels of band i-1 take the SMs the pair kernel of band i+1 frees, so
+			// the selection never lags more than one band behind
+			int lo = 0, hi = 0;
+			cudaDeviceGetStreamPriorityRange(&lo, &hi);
+			CU(cudaStreamCreateWithPriority(&up.sel, cudaStreamNonBlocking, hi));
+		}
+		CU(cudaEventCreateWithFlags(&up.evSelDone, cudaEventDisableTiming));
+		CU(cudaStreamCreateWithFlags(&up.coarse, cudaStreamNonBlocking));
+		for(int i = 0; i < 16; ++i)
+		{
+			CU(cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&up.evPair[i], cudaEventDisableTiming));
+		}
+	}
+	const size_t np = (size_t)width * height;
+	CU(L.ownColor.reserve(np * 3 * sizeof(float)));
+	CU(L.ownNs.reserve(np * sizeof(float)));
+	CU(L.ownHist.reserve(np * histDepth * sizeof(float)));
+	CU(L.ownCov.reserve(np * 6 * sizeof(float)));
+	return 0;
+}
+
 } // namespace bcdeng
 
 extern "C"
@@ -876,34 +929,11 @@ int bcd_b200_upload_async(bcd_b200_handle* h, const bcd_b200_images* in)
 	int rc = checkImages(in);
 	if(rc) return rc;
 	CU(cudaSetDevice(h->device));
-	if(h->levels.empty()) h->levels.resize(1);
+	rc = prepareUpload(h, in->width, in->height, in->hist_depth);
+	if(rc) return rc;
 	LevelBufs& L = h->levels[0];
 	bcd_b200_handle::Upload& up = h->up;
-	if(!up.copy)
-	{
-		CU(cudaStreamCreateWithFlags(&up.copy, cudaStreamNonBlocking));
-		CU(cudaEventCreateWithFlags(&up.evAll, cudaEventDisableTiming));
-		CU(cudaEventCreateWithFlags(&up.evOrder, cudaEventDisableTiming));
-		{
-			// high priority: the short selection kernels of band i-1 take the SMs the pair kernel of band i+1 frees, so
-			// the selection never lags more than one band behind
-			int lo = 0, hi = 0;
-			cudaDeviceGetStreamPriorityRange(&lo, &hi);
-			CU(cudaStreamCreateWithPriority(&up.sel, cudaStreamNonBlocking, hi));
-		}
-		CU(cudaEventCreateWithFlags(&up.evSelDone, cudaEventDisableTiming));
-		CU(cudaStreamCreateWithFlags(&up.coarse, cudaStreamNonBlocking));
-		for(int i = 0; i < 16; ++i)
-		{
-			CU(cudaEventCreateWithFlags(&up.ev[i], cudaEventDisableTiming));
-			CU(cudaEventCreateWithFlags(&up.evPair[i], cudaEventDisableTiming));
-		}
-	}
 	const size_t np = (size_t)in->width * in->height;
-	CU(L.ownColor.reserve(np * 3 * sizeof(float)));
-	CU(L.ownNs.reserve(np * sizeof(float)));
-	CU(L.ownHist.reserve(np * in->hist_depth * sizeof(float)));
-	CU(L.ownCov.reserve(np * 6 * sizeof(float)));
 	// the copies may not overtake work of the main stream that still reads the resident inputs
 	CU(cudaEventRecord(up.evOrder, h->stream));
 	CU(cudaStreamWaitEvent(up.copy, up.evOrder, 0));

@@ -105,8 +105,8 @@ Ctx ctxOf(bcd_b200_handle* h, int k)
 {
 	Ctx c;
 	c.h = h; c.level = k; c.a = h->peer.layout[k]; c.epoch = h->peer.epoch;
-	c.has[BCD_B200_SIDE_UP] = h->tileIndex > 0;
-	c.has[BCD_B200_SIDE_DOWN] = h->tileIndex < h->tileCount - 1;
+	c.has[BCD_B200_SIDE_UP] = !h->peer.solo && h->tileIndex > 0;
+	c.has[BCD_B200_SIDE_DOWN] = !h->peer.solo && h->tileIndex < h->tileCount - 1;
 	c.tickets = h->peer.tickets.as<unsigned int>();
 	c.arena = h->peer.arena.as<char>();
 	c.myFlags = reinterpret_cast<uint32_t*>(c.arena + c.a.flags);
@@ -136,6 +136,37 @@ int recvRows(const Ctx& c, int side, char* base, size_t rowBytes, int row, int r
 	return 0;
 }
 
+// owned patch-centre rows of tile `index` at level k, like levelGeom() computes them for the handle's own tile
+bool tileLevelGeom(const bcd_b200_handle* h, int index, int k, const bcd_b200_params& p, LevelGeom& g)
+{
+	bcd_b200_tile t;
+	if(bcd_b200_tile_plan(h->W, h->imageH, index, h->tileCount, &p, &t) != 0)
+		return false;
+	int W = h->W, H = t.sub_row1 - t.sub_row0;
+	for(int l = 0; l < k; ++l) { W /= 2; H /= 2; }
+	g = makeGeom(W, H, h->B, p.patch_radius, p.search_radius);
+	const int own0 = (t.own_row0 - t.sub_row0) >> k;
+	const int own1 = t.own_row1 >= h->imageH ? H : (t.own_row1 - t.sub_row0) >> k;
+	g.rowBeg = std::max(g.w, own0);
+	g.rowEnd = std::min(H - g.w, own1);
+	return true;
+}
+
+// Can the marking chain cross the boundary below tile `upper` word by word (ring of the systolic kernel)? Both tiles
+// must run that kernel at this level, and the last band of the upper tile must hold the six hand-off rows. Both sides
+// of the boundary evaluate this identically; otherwise the AS rows travel as a strip after the upper tile's kernel.
+bool ringAcross(const bcd_b200_handle* h, int upper, int k, const bcd_b200_params& p)
+{
+	LevelGeom gu, gl;
+	if(!tileLevelGeom(h, upper, k, p, gu) || !tileLevelGeom(h, upper + 1, k, p, gl))
+		return false;
+	if(!markingUsesRing(gu) || !markingUsesRing(gl))
+		return false;
+	const int rows = gu.rowEnd - gu.rowBeg;
+	const int lastBand = rows - (divUp(rows, 32) - 1) * 32;
+	return lastBand >= 6;
+}
+
 // marking chain of level k in peer mode, on the level's stream
 int markPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
@@ -150,19 +181,20 @@ int markPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
 		{
-			const bool ring = markingUsesRing(g);
+			const bool ringUp = c.has[BCD_B200_SIDE_UP] && ringAcross(h, h->tileIndex - 1, k, p);
+			const bool ringDown = c.has[BCD_B200_SIDE_DOWN] && ringAcross(h, h->tileIndex, k, p);
 			const size_t rowBytes = (size_t)Wp * 4;
-			if(!ring)
+			if(c.has[BCD_B200_SIDE_UP] && !ringUp)
 			{
 				int rc = recvRows(c, BCD_B200_SIDE_UP, (char*)L.asBits.p, rowBytes, own0 - b, b, c.a.asStrip, SLOT_AS, false, st);
 				if(rc) return rc;
 			}
-			const uint32_t* ringIn = ring && c.has[BCD_B200_SIDE_UP] ? reinterpret_cast<const uint32_t*>(c.arena + c.a.inbox) : nullptr;
-			uint32_t* ringOut = ring && c.has[BCD_B200_SIDE_DOWN] ? reinterpret_cast<uint32_t*>(h->peer.nb[BCD_B200_SIDE_DOWN] + c.a.inbox) : nullptr;
+			const uint32_t* ringIn = ringUp ? reinterpret_cast<const uint32_t*>(c.arena + c.a.inbox) : nullptr;
+			uint32_t* ringOut = ringDown ? reinterpret_cast<uint32_t*>(h->peer.nb[BCD_B200_SIDE_DOWN] + c.a.inbox) : nullptr;
 			CU(launchMarking(L.pre.as<uint32_t>(), prePitchOf(g.W), g, p.skip_prob, 0x9E3779B9u + (uint32_t)k, L.active.as<uint32_t>(),
 					L.asBits.as<uint32_t>(), Wp, L.progress.as<unsigned int>(), st, &h->launches,
 					&L.ctr.as<DeviceCounters>()->markTimeouts, c.epoch, ringIn, ringOut));
-			if(!ring)
+			if(c.has[BCD_B200_SIDE_DOWN] && !ringDown)
 			{
 				int rc = pushRows(c, BCD_B200_SIDE_DOWN, (const char*)L.asBits.p, rowBytes, own1 - b, b, c.a.asStrip, SLOT_AS, st);
 				if(rc) return rc;
@@ -233,7 +265,8 @@ int mergedRowsPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	return 0;
 }
 
-int tileRun(bcd_b200_handle* h, const bcd_b200_params& p)
+// solo = the warm-up pass of bcd_b200_tile_setup: the same launches without any neighbour (see there)
+int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
 {
 	if(!h->peer.enabled) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before bcd_b200_tile_setup");
 	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before upload/bind_device");
@@ -243,7 +276,8 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p)
 	if(h->H != h->subRow1 - h->subRow0 || h->W != h->peer.geomW)
 		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "resident inputs are %dx%d but the tile was set up for %dx%d", h->W, h->H,
 				h->peer.geomW, h->subRow1 - h->subRow0);
-	for(int side = 0; side < 2; ++side)
+	h->peer.solo = solo;
+	for(int side = 0; side < 2 && !solo; ++side)
 	{
 		const bool has = side == BCD_B200_SIDE_UP ? h->tileIndex > 0 : h->tileIndex < h->tileCount - 1;
 		if(has && !h->peer.nb[side])
@@ -258,7 +292,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p)
 	h->spans.clear();
 	h->launches = 0;
 	h->ran = false;
-	h->peer.epoch += 1;
+	if(!solo) h->peer.epoch += 1;
 	cudaStream_t st = h->stream;
 	const int s = p.nb_scales;
 	int rc;
@@ -343,6 +377,10 @@ int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	applyTile(h, *p, *t);
 	rc = ensureBuffers(h, *p);
 	if(rc) return rc;
+	// everything a run may need is created now: allocations and stream creation synchronise with running kernels, and
+	// during a run a neighbouring tile's kernel may already be waiting for this tile
+	if((rc = prepareUpload(h, h->W, h->H, h->B))) return rc;
+	if((rc = reserveEvents(h, 1024))) return rc;
 	// per-level filter scratch: the levels are filtered side by side
 	const LevelGeom g0 = makeGeom(h->W, h->H, h->B, p->patch_radius, p->search_radius);
 	const size_t perSlot = (size_t)2 * g0.d * g0.d * 4;
@@ -380,6 +418,41 @@ int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	}
 	P.geomW = h->W; P.geomB = p->search_radius; P.geomWr = p->patch_radius; P.geomScales = p->nb_scales;
 	P.enabled = true;
+	// Warm-up: one pass over zeroed inputs without neighbours, plus empty launches of the exchange kernels. CUDA loads a
+	// kernel the first time it is used and that load waits for the device to go idle — in a real frame it would wait for
+	// this tile's kernels that are waiting for a neighbour whose host thread is stuck in the same way. After this pass
+	// every kernel the geometry needs is resident.
+	{
+		LevelBufs& L0 = h->levels[0];
+		const float *sc = L0.color, *sn = L0.ns, *sh = L0.hist, *sv = L0.cov;
+		const bool hadInputs = h->haveInputs, hadPending = h->up.pending;
+		const size_t np = (size_t)h->W * h->H;
+		CU(cudaMemsetAsync(L0.ownColor.p, 0, np * 3 * sizeof(float), h->stream));
+		CU(cudaMemsetAsync(L0.ownNs.p, 0, np * sizeof(float), h->stream));
+		CU(cudaMemsetAsync(L0.ownHist.p, 0, np * h->B * sizeof(float), h->stream));
+		CU(cudaMemsetAsync(L0.ownCov.p, 0, np * 6 * sizeof(float), h->stream));
+		L0.color = L0.ownColor.as<float>(); L0.ns = L0.ownNs.as<float>(); L0.hist = L0.ownHist.as<float>(); L0.cov = L0.ownCov.as<float>();
+		h->haveInputs = true;
+		h->up.pending = false;
+		rc = tileRun(h, *p, true);
+		if(!rc)
+		{
+			cudaError_t e = launchPeerWarmup(P.tickets.as<unsigned int>() + TIMEOUT_WORD + 1, h->stream);
+			if(e != cudaSuccess) rc = fail(BCD_B200_ERR_CUDA, "warm-up of the exchange kernels failed: %s", cudaGetErrorString(e));
+		}
+		if(!rc)
+		{
+			cudaError_t e = launchMarkingWarmup(h->stream);
+			if(e != cudaSuccess) rc = fail(BCD_B200_ERR_CUDA, "warm-up of the marking kernels failed: %s", cudaGetErrorString(e));
+		}
+		L0.color = sc; L0.ns = sn; L0.hist = sh; L0.cov = sv;
+		h->haveInputs = hadInputs && sc != L0.ownColor.as<float>(); // uploaded inputs were overwritten, bound ones are intact
+		h->up.pending = false;
+		(void)hadPending;
+		h->peer.solo = false;
+		h->ran = false;
+		if(rc) return rc;
+	}
 	CU(cudaDeviceSynchronize());
 	Token tok;
 	memset(&tok, 0, sizeof(tok));

@@ -145,6 +145,7 @@ struct bcd_b200_handle
 	struct Peer
 	{
 		bool enabled = false;        // tile_run uses the peer path
+		bool solo = false;           // warm-up pass of tile_setup: the tile runs without neighbours
 		DevBuf arena;
 		size_t arenaBytes = 0;
 		std::vector<ArenaLevel> layout;
@@ -173,6 +174,8 @@ int checkParams(const bcd_b200_params* p);
 int checkImages(const bcd_b200_images* in);
 int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p);
 int finishUpload(bcd_b200_handle* h);
+int prepareUpload(bcd_b200_handle* h, int width, int height, int histDepth);
+int reserveEvents(bcd_b200_handle* h, size_t count);
 int pyramidLevel(bcd_b200_handle* h, int k, int parts);
 int levelClear(bcd_b200_handle* h, int k, const bcd_b200_params& p);
 int levelPixelCov(bcd_b200_handle* h, int k, const bcd_b200_params& p);

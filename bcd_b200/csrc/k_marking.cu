@@ -898,6 +898,23 @@ static int sysBandsPerCta(const LevelGeom& g)
 }
 bool markingUsesRing(const LevelGeom& g) { return sysBandsPerCta(g) > 0; }
 
+// tile_setup: loads the kernels a frame may use although the warm-up pass did not launch them (the ring converter, and the
+// systolic kernels of the other skipping mode — the skipping probability may change from frame to frame)
+cudaError_t launchMarkingWarmup(cudaStream_t st)
+{
+	k_ring_to_asbits<<<dim3(1, 6), 64, 0, st>>>(nullptr, 0, 0, nullptr, 0, 0);
+	cudaError_t err = cudaGetLastError();
+	cudaFuncAttributes fa;
+#define TOUCH(NWV) \
+	if(err == cudaSuccess) err = cudaFuncGetAttributes(&fa, k_marking_sys6<NWV, true>); \
+	if(err == cudaSuccess) err = cudaFuncGetAttributes(&fa, k_marking_sys6<NWV, false>);
+	TOUCH(1) TOUCH(2) TOUCH(4) TOUCH(8)
+#undef TOUCH
+	if(err == cudaSuccess) err = cudaFuncGetAttributes(&fa, k_active_from_as<true>);
+	if(err == cudaSuccess) err = cudaFuncGetAttributes(&fa, k_active_from_as<false>);
+	return err;
+}
+
 cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g, float skipProb, uint32_t seed,
 		uint32_t* actBits, uint32_t* asBits, int Wp, unsigned int* progress, cudaStream_t st, int* launches,
 		unsigned int* timeouts, uint32_t epoch, const uint32_t* ringIn, uint32_t* ringOut)

@@ -116,4 +116,16 @@ cudaError_t launchPeerRecv(void* dst, const void* slot, size_t bytes, bool addFl
 	return cudaGetLastError();
 }
 
+// empty launches of every exchange kernel (tile_setup: loads them while no neighbour can be waiting); scratch = one word
+cudaError_t launchPeerWarmup(unsigned int* scratch, cudaStream_t st)
+{
+	uint32_t* w = reinterpret_cast<uint32_t*>(scratch);
+	k_push<float4><<<1, 256, 0, st>>>(nullptr, nullptr, 0, w + 1, 0u, scratch);
+	k_push<uint32_t><<<1, 256, 0, st>>>(nullptr, nullptr, 0, w + 1, 0u, scratch);
+	k_recv<float4, true><<<1, 256, 0, st>>>(nullptr, nullptr, 0, w + 1, 0u, scratch + 2);
+	k_recv<float4, false><<<1, 256, 0, st>>>(nullptr, nullptr, 0, w + 1, 0u, scratch + 2);
+	k_recv<uint32_t, false><<<1, 256, 0, st>>>(nullptr, nullptr, 0, w + 1, 0u, scratch + 2);
+	return cudaGetLastError();
+}
+
 } // namespace bcdk

@@ -43,6 +43,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 // (systolic kernel, b = 6) epoch: tag of the hand-off ring words of this launch, different from the previous launches that
 // used the same scratch; ringIn / ringOut: inbox fed by the upper row tile / inbox of the lower row tile (markingRingWords)
 bool markingUsesRing(const LevelGeom& g); // the systolic kernel serves this geometry (ringIn / ringOut are honoured)
+cudaError_t launchMarkingWarmup(cudaStream_t st); // loads the kernels a warm-up frame does not launch
 cudaError_t launchAllActive(const LevelGeom& g, uint32_t* actBits, int Wp, cudaStream_t st, int* launches);
 // work lists
 cudaError_t launchBuildLists(const int* counts, const uint32_t* actBits, int Wp, const LevelGeom& g,
@@ -74,6 +75,7 @@ cudaError_t launchPeerPush(const void* src, void* dstPeer, size_t bytes, uint32_
 		cudaStream_t st, int* launches);
 cudaError_t launchPeerRecv(void* dst, const void* slot, size_t bytes, bool addFloat4, const uint32_t* flag, uint32_t epoch,
 		unsigned int* timeouts, cudaStream_t st, int* launches);
+cudaError_t launchPeerWarmup(unsigned int* scratch /* 4 words */, cudaStream_t st);
 // K4 finalAggregation
 cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStream_t st, int* launches);
 // (row f1) SpikeRemovalFilter: out-of-place; src = W*H ints of scratch

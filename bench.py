@@ -29,6 +29,7 @@ import time
 
 # every stream of a handle gets its own hardware queue (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # a lazy kernel load waits for an idle device (see bcd_b200_tile_setup)
 
 import numpy as np
 

@@ -6,6 +6,7 @@ import pytest
 # the multi-tile tests run several handles (7 streams each) on one device, some of them with kernels that wait for a
 # neighbouring tile: every stream needs its own hardware queue (the library asks for the same when it is loaded first)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # a lazy kernel load waits for an idle device (see bcd_b200_tile_setup)
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
