@@ -32,6 +32,9 @@ SYMBOLS = [
     "bcd_b200_tile_setup", "bcd_b200_tile_connect", "bcd_b200_tile_run",
     "bcd_b200_group_create", "bcd_b200_group_destroy", "bcd_b200_group_set_pinning", "bcd_b200_group_denoise",
     "bcd_b200_group_get_stats", "bcd_b200_group_get_timings", "bcd_b200_group_tiles", "bcd_b200_denoise_multi",
+    "bcd_b200_group_set_tiles_per_gpu", "bcd_b200_group_local_tiles", "bcd_b200_group_create_ranked", "bcd_b200_group_setup",
+    "bcd_b200_group_connect", "bcd_b200_group_tile_info", "bcd_b200_group_set_tile_buffers", "bcd_b200_group_upload_tile",
+    "bcd_b200_group_run", "bcd_b200_group_download_tile",
 ]
 
 
@@ -108,6 +111,16 @@ def lib():
         L.bcd_b200_group_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.bcd_b200_group_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
         L.bcd_b200_group_tiles.argtypes = [C.c_void_p]
+        L.bcd_b200_group_local_tiles.argtypes = [C.c_void_p]
+        L.bcd_b200_group_set_tiles_per_gpu.argtypes = [C.c_void_p, C.c_int]
+        L.bcd_b200_group_create_ranked.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int]
+        L.bcd_b200_group_setup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(C.c_int32), C.c_int]
+        L.bcd_b200_group_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.bcd_b200_group_tile_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.bcd_b200_group_set_tile_buffers.argtypes = [C.c_void_p, C.c_int, C.POINTER(Images), C.c_void_p]
+        L.bcd_b200_group_upload_tile.argtypes = [C.c_void_p, C.c_int, C.POINTER(Images)]
+        L.bcd_b200_group_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int]
+        L.bcd_b200_group_download_tile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.bcd_b200_denoise_multi.argtypes = [C.POINTER(Images), C.POINTER(Params), C.c_void_p, C.POINTER(C.c_int32), C.c_int,
                                              C.c_void_p, C.c_void_p]
         _lib = L
@@ -158,12 +171,56 @@ def denoise_multi(color, nsamples, hist, cov, devices, params=None, **kw):
 class Group:
     """N GPUs behind one host-buffer call (bcd_b200_group_*): what bcd::Denoiser / bcd::MultiscaleDenoiser hold."""
 
-    def __init__(self, devices, pin=None):
+    def __init__(self, devices, pin=None, tiles_per_gpu=None, rank=0, world=1):
         self._g = C.c_void_p()
         ids = (C.c_int32 * len(devices))(*devices)
-        _check(lib().bcd_b200_group_create(C.byref(self._g), ids, len(devices)))
+        _check(lib().bcd_b200_group_create_ranked(C.byref(self._g), ids, len(devices), rank, world))
         if pin is not None:
             _check(lib().bcd_b200_group_set_pinning(self._g, int(bool(pin))))
+        if tiles_per_gpu is not None:
+            _check(lib().bcd_b200_group_set_tiles_per_gpu(self._g, int(tiles_per_gpu)))
+
+    # ---- ranked use (one process per GPU): see include/bcd_b200.h
+    TOKEN_BYTES = 96
+
+    def setup(self, W, H, B, params, capacity=64):
+        """-> [(tile index, token bytes)] of the local tiles."""
+        toks = C.create_string_buffer(self.TOKEN_BYTES * capacity)
+        idx = (C.c_int32 * capacity)()
+        _check(lib().bcd_b200_group_setup(self._g, W, H, B, C.byref(params), toks, idx, capacity))
+        n = self.local_tiles()
+        return [(int(idx[i]), toks.raw[i * self.TOKEN_BYTES:(i + 1) * self.TOKEN_BYTES]) for i in range(n)]
+
+    def connect(self, tokens_by_tile=None):
+        if tokens_by_tile is None:
+            _check(lib().bcd_b200_group_connect(self._g, None, 0))
+        else:
+            buf = C.create_string_buffer(b"".join(tokens_by_tile), self.TOKEN_BYTES * len(tokens_by_tile))
+            _check(lib().bcd_b200_group_connect(self._g, buf, len(tokens_by_tile)))
+
+    def local_tiles(self):
+        return int(lib().bcd_b200_group_local_tiles(self._g))
+
+    def tile_info(self, local_tile):
+        """-> dict(image_width, image_height, own_row0, own_row1, sub_row0, sub_row1, tile_index, tile_count)."""
+        v = (C.c_int32 * 8)()
+        _check(lib().bcd_b200_group_tile_info(self._g, local_tile, v))
+        return dict(zip(("image_width", "image_height", "own_row0", "own_row1", "sub_row0", "sub_row1", "tile_index", "tile_count"),
+                        [int(x) for x in v]))
+
+    def set_tile_buffers(self, local_tile, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, rows, B, out_ptr):
+        img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, rows, B)
+        _check(lib().bcd_b200_group_set_tile_buffers(self._g, local_tile, C.byref(img), C.c_void_p(out_ptr)))
+
+    def upload_tile(self, local_tile, color_ptr, ns_ptr, hist_ptr, cov_ptr, W, rows, B):
+        img = Images(color_ptr, ns_ptr, hist_ptr, cov_ptr, W, rows, B)
+        _check(lib().bcd_b200_group_upload_tile(self._g, local_tile, C.byref(img)))
+
+    def run(self, params=None, from_host=False):
+        _check(lib().bcd_b200_group_run(self._g, C.byref(params) if params is not None else None, int(bool(from_host))))
+
+    def download_tile(self, local_tile, out_ptr):
+        _check(lib().bcd_b200_group_download_tile(self._g, local_tile, C.c_void_p(out_ptr)))
 
     def close(self):
         if self._g:

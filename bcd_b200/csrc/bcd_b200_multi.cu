@@ -527,45 +527,76 @@ int bcd_b200_tile_run(bcd_b200_handle* h, const bcd_b200_params* p)
 } // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------------
-// group: N GPUs of one box behind one host-buffer call
+// group: the GPUs of one box (or this process' share of them) behind one call
+//
+// The frame is cut into `tiles` horizontal bands that are dealt out to the GPUs CYCLICALLY: tile j runs on GPU j mod G.
+// With several tiles per GPU the raster-order marking chain — the one dependency through all rows of the frame —
+// pipelines: while the GPUs select their second tiles the chain already runs through the first G tiles, and the filters
+// follow it band by band, instead of the chain starting only when whole eighths of the frame have been selected.
+// Every local tile has its own handle (streams, buffers, arena) and its own host thread, alive across frames.
 // ---------------------------------------------------------------------------------------------------------------------
 struct bcd_b200_group
 {
-	int n = 0;
-	std::vector<int> dev;
-	std::vector<bcd_b200_handle*> h;
+	int rank = 0, world = 1;       // this process' position when the GPUs of the box are spread over several processes
+	std::vector<int> dev;          // CUDA devices of this process
+	int tilesPerGpu = 0;           // 0: chosen from the frame height
 	bool pin = true;
 	std::vector<std::pair<const void*, size_t>> pinned;
-	// worker pool (one thread per GPU, alive across frames)
-	std::vector<std::thread> th;
+
+	struct Slot // one local tile
+	{
+		bcd_b200_group* g = nullptr;
+		int slot = 0, device = 0;
+		bcd_b200_handle* h = nullptr;
+		std::thread th;
+		bcd_b200_tile plan;
+		bcd_b200_peer_token token;
+		bcd_b200_images hostIn;    // this tile's rows in host memory (e2e jobs)
+		float* hostOut = nullptr;
+		int rc = 0;
+		std::string err;
+	};
+	std::vector<Slot*> slots;      // grow-only; the first nLocal are in use for the current frame geometry
+	int nLocal = 0;
+	int tiles = 0;                 // tiles of the whole frame (all processes)
+	std::vector<bcd_b200_peer_token> allTokens; // by tile index
+	// worker dispatch
 	std::mutex mu;
 	std::condition_variable cvGo, cvDone;
 	uint64_t gen = 0;
 	int pending = 0;
 	bool quit = false;
-	// barrier among the workers of a frame
+	int job = 0;
+	// barrier among the local workers
 	std::mutex bmu;
 	std::condition_variable bcv;
 	int bcount = 0;
 	uint64_t bgen = 0;
-	// job
-	const bcd_b200_images* in = nullptr;
+	// current job
 	bcd_b200_params p;
-	float* out = nullptr;
-	int tiles = 0;
-	bool needSetup = true;
-	std::vector<int> rc;
-	std::vector<std::string> err;
-	std::vector<bcd_b200_tile> plan;
-	std::vector<bcd_b200_peer_token> tokens;
-	// geometry the tiles are connected for
-	int conW = 0, conH = 0, conB = 0, conTiles = 0, conW_ = 0, conB_ = 0, conS = 0;
+	int W = 0, H = 0, B = 0;
+	bool ready = false;            // set up and connected for (W, H, B, radii, scales, tiles)
+	int conW = 0, conH = 0, conB = 0, conTiles = 0, conWr = 0, conBr = 0, conS = 0;
 	bcd_b200_stats stats;
 	bcd_b200_timings timings;
 };
 
 namespace
 {
+
+enum { JOB_SETUP = 1, JOB_CONNECT = 2, JOB_RUN = 3, JOB_E2E = 4 };
+
+typedef bcd_b200_group::Slot Slot;
+
+int gpusTotal(const bcd_b200_group* g) { return g->world * (int)g->dev.size(); }
+// tile j runs on global GPU j mod G; global GPU q belongs to process q / nLocalGpus
+bool tileIsLocal(const bcd_b200_group* g, int j, int* localGpu)
+{
+	const int q = j % gpusTotal(g), per = (int)g->dev.size();
+	if(q / per != g->rank) return false;
+	if(localGpu) *localGpu = q % per;
+	return true;
+}
 
 void groupBarrier(bcd_b200_group* g, int parties)
 {
@@ -581,50 +612,45 @@ void groupBarrier(bcd_b200_group* g, int parties)
 		g->bcv.wait(lk, [&] { return g->bgen != my; });
 }
 
-bool anyFailed(bcd_b200_group* g)
+void note(Slot& s, int rc)
 {
-	for(int i = 0; i < g->tiles; ++i)
-		if(g->rc[i]) return true;
-	return false;
+	if(rc && !s.rc) { s.rc = rc; s.err = bcd_b200_last_error(); }
 }
 
-void tileJob(bcd_b200_group* g, int r)
+void slotJob(Slot& s)
 {
-	bcd_b200_handle* h = g->h[r];
-	const bcd_b200_tile& t = g->plan[r];
-	const bcd_b200_images& in = *g->in;
-	auto note = [&](int rc) { if(rc && !g->rc[r]) { g->rc[r] = rc; g->err[r] = bcd_b200_last_error(); } };
-	if(g->needSetup)
+	bcd_b200_group* g = s.g;
+	const int idx = s.plan.tile_index;
+	switch(g->job)
 	{
-		note(bcd_b200_tile_setup(h, &g->p, &t, in.hist_depth, &g->tokens[r]));
-		groupBarrier(g, g->tiles);
-		if(!anyFailed(g))
-		{
-			note(bcd_b200_tile_connect(h, BCD_B200_SIDE_UP, r > 0 ? &g->tokens[r - 1] : nullptr));
-			note(bcd_b200_tile_connect(h, BCD_B200_SIDE_DOWN, r < g->tiles - 1 ? &g->tokens[r + 1] : nullptr));
-		}
-		groupBarrier(g, g->tiles);
+	case JOB_SETUP:
+		note(s, bcd_b200_tile_setup(s.h, &g->p, &s.plan, g->B, &s.token));
+		break;
+	case JOB_CONNECT:
+		note(s, bcd_b200_tile_connect(s.h, BCD_B200_SIDE_UP, idx > 0 ? &g->allTokens[idx - 1] : nullptr));
+		note(s, bcd_b200_tile_connect(s.h, BCD_B200_SIDE_DOWN, idx < g->tiles - 1 ? &g->allTokens[idx + 1] : nullptr));
+		break;
+	case JOB_RUN:
+		note(s, bcd_b200_tile_run(s.h, &g->p));
+		break;
+	case JOB_E2E:
+	{
+		// every tile must reach the run (its neighbours wait for its strips), so a local failure is only noted
+		int rc = bcd_b200_upload_async(s.h, &s.hostIn);
+		if(!rc) rc = bcd_b200_tile_run(s.h, &g->p);
+		if(!rc) rc = bcd_b200_tile_download(s.h, s.hostOut);
+		note(s, rc);
+		break;
 	}
-	if(anyFailed(g))
-		return;
-	const size_t W = (size_t)in.width;
-	bcd_b200_images sub = in;
-	sub.color = in.color + (size_t)t.sub_row0 * W * 3;
-	sub.nsamples = in.nsamples + (size_t)t.sub_row0 * W;
-	sub.hist = in.hist + (size_t)t.sub_row0 * W * in.hist_depth;
-	sub.cov = in.cov + (size_t)t.sub_row0 * W * 6;
-	sub.height = t.sub_row1 - t.sub_row0;
-	int rc = bcd_b200_upload_async(h, &sub);
-	// every tile must reach the run (its neighbours wait for its strips), so a local failure is only noted
-	if(!rc) rc = bcd_b200_tile_run(h, &g->p);
-	if(!rc) rc = bcd_b200_tile_download(h, g->out + (size_t)t.own_row0 * W * 3);
-	note(rc);
+	default:
+		break;
+	}
 }
 
-void workerLoop(bcd_b200_group* g, int r)
+void workerLoop(Slot* s, uint64_t seen)
 {
-	cudaSetDevice(g->dev[r]);
-	uint64_t seen = 0;
+	bcd_b200_group* g = s->g;
+	cudaSetDevice(s->device);
 	for(;;)
 	{
 		{
@@ -633,14 +659,45 @@ void workerLoop(bcd_b200_group* g, int r)
 			if(g->quit) return;
 			seen = g->gen;
 		}
-		if(r < g->tiles)
-			tileJob(g, r);
+		if(s->slot < g->nLocal)
+			slotJob(*s);
 		{
 			std::lock_guard<std::mutex> lk(g->mu);
 			if(--g->pending == 0)
 				g->cvDone.notify_all();
 		}
 	}
+}
+
+// runs `job` on every local tile (one thread each) and returns the first failure
+int dispatch(bcd_b200_group* g, int job)
+{
+	for(int i = 0; i < g->nLocal; ++i) { g->slots[i]->rc = 0; g->slots[i]->err.clear(); }
+	{
+		std::unique_lock<std::mutex> lk(g->mu);
+		g->job = job;
+		g->pending = (int)g->slots.size();
+		++g->gen;
+		g->cvGo.notify_all();
+		g->cvDone.wait(lk, [&] { return g->pending == 0; });
+	}
+	for(int i = 0; i < g->nLocal; ++i)
+		if(g->slots[i]->rc)
+			return fail(g->slots[i]->rc, "tile %d of %d (device %d): %s", g->slots[i]->plan.tile_index, g->tiles, g->slots[i]->device,
+					g->slots[i]->err.c_str());
+	return 0;
+}
+
+int ensureSlots(bcd_b200_group* g, int count)
+{
+	while((int)g->slots.size() < count)
+	{
+		Slot* s = new Slot();
+		s->g = g;
+		s->slot = (int)g->slots.size();
+		g->slots.push_back(s);
+	}
+	return 0;
 }
 
 // page-lock a host range the first time it is seen (a renderer reuses its image storage frame after frame)
@@ -673,12 +730,52 @@ void pinRange(bcd_b200_group* g, const void* ptr, size_t bytes)
 		cudaGetLastError(); // already registered by the caller, or not registrable: the copies still work (pageable)
 }
 
+// number of tiles for a frame: tilesPerGpu x GPUs, fewer when the bands would get too thin for the pyramid
+int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::vector<bcd_b200_tile>& plan)
+{
+	const int G = gpusTotal(g);
+	int T = g->tilesPerGpu;
+	if(T <= 0)
+	{
+		// default: bands of at least ~48 level-0 rows per scale step, at most 4 per GPU (measured: profiles/r02_scaling.md)
+		const int minRows = 48 << (p.nb_scales > 1 ? 1 : 0);
+		T = std::max(1, std::min(4, H / std::max(1, G * minRows)));
+		if(G == 1) T = 1;
+	}
+	for(int tiles = G * T; tiles > 1; tiles = tiles > G ? tiles - G : tiles - 1)
+	{
+		plan.resize(tiles);
+		bool ok = true;
+		for(int j = 0; j < tiles && ok; ++j)
+			ok = bcd_b200_tile_plan(W, H, j, tiles, &p, &plan[j]) == 0;
+		if(ok) return tiles;
+	}
+	plan.resize(1);
+	bcd_b200_tile_plan(W, H, 0, 1, &p, &plan[0]);
+	return 1;
+}
+
+void collectGroupStats(bcd_b200_group* g)
+{
+	memset(&g->stats, 0, sizeof(g->stats));
+	memset(&g->timings, 0, sizeof(g->timings));
+	for(int i = 0; i < g->nLocal; ++i)
+	{
+		const bcd_b200_stats& s = g->slots[i]->h->stats;
+		g->stats.interior += s.interior; g->stats.strong += s.strong; g->stats.active += s.active; g->stats.full += s.full;
+		g->stats.fallback += s.fallback; g->stats.sum_n_full += s.sum_n_full; g->stats.kernel_launches += s.kernel_launches;
+		const bcd_b200_timings& t = g->slots[i]->h->timings;
+		for(int k = 0; k < BCD_B200_STAGE_COUNT; ++k) g->timings.stage_ms[k] += t.stage_ms[k];
+		g->timings.total_ms = std::max(g->timings.total_ms, t.total_ms);
+	}
+}
+
 } // namespace
 
 extern "C"
 {
 
-int bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus)
+int bcd_b200_group_create_ranked(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus, int rank, int world)
 {
 	if(!out) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group pointer");
 	*out = nullptr;
@@ -686,42 +783,36 @@ int bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int n
 	if(ndev == 0)
 		return fail(BCD_B200_ERR_NO_DEVICE, "no CUDA device available; bcd_b200 has no CPU path");
 	if(nb_gpus <= 0) nb_gpus = device_ids ? 1 : ndev; // "all"
-	if(nb_gpus > 64) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "too many GPUs (%d)", nb_gpus);
+	if(nb_gpus > 64 || world < 1 || rank < 0 || rank >= world)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad group request (%d GPUs, rank %d of %d)", nb_gpus, rank, world);
 	bcd_b200_group* g = new bcd_b200_group();
-	g->n = nb_gpus;
+	g->rank = rank;
+	g->world = world;
 	memset(&g->stats, 0, sizeof(g->stats));
 	memset(&g->timings, 0, sizeof(g->timings));
 	{
 		const char* e = getenv("BCD_B200_PIN");
 		g->pin = !(e && e[0] == '0');
+		e = getenv("BCD_B200_TILES_PER_GPU");
+		if(e && atoi(e) > 0) g->tilesPerGpu = std::min(atoi(e), 16);
 	}
 	for(int i = 0; i < nb_gpus; ++i)
 	{
 		const int d = device_ids ? device_ids[i] : i;
 		if(d < 0 || d >= ndev)
 		{
-			bcd_b200_group_destroy(g);
+			delete g;
 			return fail(BCD_B200_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", d, ndev);
 		}
-		bcd_b200_handle* h = nullptr;
-		int rc = bcd_b200_create(&h, d);
-		if(rc)
-		{
-			bcd_b200_group_destroy(g);
-			return rc;
-		}
 		g->dev.push_back(d);
-		g->h.push_back(h);
 	}
-	g->rc.assign(nb_gpus, 0);
-	g->err.assign(nb_gpus, std::string());
-	g->plan.resize(nb_gpus);
-	g->tokens.resize(nb_gpus);
-	if(nb_gpus > 1)
-		for(int r = 0; r < nb_gpus; ++r)
-			g->th.emplace_back(workerLoop, g, r);
 	*out = g;
 	return 0;
+}
+
+int bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus)
+{
+	return bcd_b200_group_create_ranked(out, device_ids, nb_gpus, 0, 1);
 }
 
 void bcd_b200_group_destroy(bcd_b200_group* g)
@@ -732,16 +823,21 @@ void bcd_b200_group_destroy(bcd_b200_group* g)
 		g->quit = true;
 	}
 	g->cvGo.notify_all();
-	for(std::thread& t : g->th) t.join();
+	for(Slot* s : g->slots)
+		if(s->th.joinable()) s->th.join();
 	// the neighbours' arenas must be unmapped before anyone frees them
-	for(bcd_b200_handle* h : g->h)
-		if(h && h->peer.enabled)
+	for(Slot* s : g->slots)
+		if(s->h && s->h->peer.enabled)
 		{
-			cudaSetDevice(h->device);
-			bcd_b200_tile_connect(h, BCD_B200_SIDE_UP, nullptr);
-			bcd_b200_tile_connect(h, BCD_B200_SIDE_DOWN, nullptr);
+			cudaSetDevice(s->h->device);
+			bcd_b200_tile_connect(s->h, BCD_B200_SIDE_UP, nullptr);
+			bcd_b200_tile_connect(s->h, BCD_B200_SIDE_DOWN, nullptr);
 		}
-	for(bcd_b200_handle* h : g->h) bcd_b200_destroy(h);
+	for(Slot* s : g->slots)
+	{
+		bcd_b200_destroy(s->h);
+		delete s;
+	}
 	for(auto& r : g->pinned)
 		if(cudaHostUnregister(const_cast<void*>(r.first)) != cudaSuccess) cudaGetLastError();
 	delete g;
@@ -754,12 +850,169 @@ int bcd_b200_group_set_pinning(bcd_b200_group* g, int pin_host)
 	return 0;
 }
 
+int bcd_b200_group_set_tiles_per_gpu(bcd_b200_group* g, int tiles_per_gpu)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	if(tiles_per_gpu < 0 || tiles_per_gpu > 16) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "tiles per GPU must be 0 (automatic) .. 16");
+	if(tiles_per_gpu != g->tilesPerGpu) g->ready = false;
+	g->tilesPerGpu = tiles_per_gpu;
+	return 0;
+}
+
 int bcd_b200_group_tiles(bcd_b200_group* g) { return g ? g->tiles : 0; }
+int bcd_b200_group_local_tiles(bcd_b200_group* g) { return g ? g->nLocal : 0; }
+
+int bcd_b200_group_setup(bcd_b200_group* g, int width, int height, int hist_depth, const bcd_b200_params* p,
+		bcd_b200_peer_token* tokens_out, int32_t* tile_indices_out, int capacity)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	int rc = checkParams(p);
+	if(rc) return rc;
+	if(width <= 0 || height <= 0 || hist_depth <= 0)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad frame %dx%dx%d", width, height, hist_depth);
+	g->ready = false;
+	g->p = *p;
+	g->W = width; g->H = height; g->B = hist_depth;
+	std::vector<bcd_b200_tile> plan;
+	g->tiles = chooseTiles(g, width, height, *p, plan);
+	// local tiles, in frame order
+	int n = 0;
+	for(int j = 0; j < g->tiles; ++j)
+	{
+		int lg = 0;
+		if(!tileIsLocal(g, j, &lg)) continue;
+		ensureSlots(g, n + 1);
+		Slot& s = *g->slots[n];
+		const int device = g->dev[lg];
+		if(s.h && s.device != device) // cannot happen: slot i always maps to local GPU i mod (GPUs of this process)
+			return fail(BCD_B200_ERR_STATE, "tile slot %d moved from device %d to %d", n, s.device, device);
+		s.device = device;
+		if(!s.h)
+		{
+			rc = bcd_b200_create(&s.h, device);
+			if(rc) return rc;
+		}
+		s.plan = plan[j];
+		++n;
+	}
+	g->nLocal = n;
+	for(Slot* s : g->slots)
+		if(!s->th.joinable())
+			s->th = std::thread(workerLoop, s, g->gen); // no job is in flight: gen is stable
+	if(g->tiles == 1)
+	{
+		g->allTokens.clear();
+		return 0;
+	}
+	rc = dispatch(g, JOB_SETUP);
+	if(rc) return rc;
+	g->allTokens.assign(g->tiles, bcd_b200_peer_token());
+	for(int i = 0; i < n; ++i)
+		g->allTokens[g->slots[i]->plan.tile_index] = g->slots[i]->token;
+	if(tokens_out || tile_indices_out)
+	{
+		if(capacity < n) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "room for %d tokens, %d local tiles", capacity, n);
+		for(int i = 0; i < n; ++i)
+		{
+			if(tokens_out) tokens_out[i] = g->slots[i]->token;
+			if(tile_indices_out) tile_indices_out[i] = g->slots[i]->plan.tile_index;
+		}
+	}
+	return 0;
+}
+
+int bcd_b200_group_connect(bcd_b200_group* g, const bcd_b200_peer_token* tokens_by_tile, int nb_tiles)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	if(g->tiles > 1)
+	{
+		if(tokens_by_tile)
+		{
+			if(nb_tiles != g->tiles) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "%d tokens for %d tiles", nb_tiles, g->tiles);
+			g->allTokens.assign(tokens_by_tile, tokens_by_tile + nb_tiles);
+		}
+		int rc = dispatch(g, JOB_CONNECT);
+		if(rc) return rc;
+	}
+	g->ready = true;
+	g->conW = g->W; g->conH = g->H; g->conB = g->B; g->conTiles = g->tiles;
+	g->conWr = g->p.patch_radius; g->conBr = g->p.search_radius; g->conS = g->p.nb_scales;
+	return 0;
+}
+
+int bcd_b200_group_tile_info(bcd_b200_group* g, int local_tile, bcd_b200_tile* out)
+{
+	if(!g || !out || local_tile < 0 || local_tile >= g->nLocal) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad local tile %d", local_tile);
+	*out = g->slots[local_tile]->plan;
+	return 0;
+}
+
+int bcd_b200_group_set_tile_buffers(bcd_b200_group* g, int local_tile, const bcd_b200_images* rows_in, float* rows_out)
+{
+	if(!g || local_tile < 0 || local_tile >= g->nLocal) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad local tile %d", local_tile);
+	Slot& s = *g->slots[local_tile];
+	if(rows_in)
+	{
+		int rc = checkImages(rows_in);
+		if(rc) return rc;
+		if(rows_in->width != g->W || rows_in->height != s.plan.sub_row1 - s.plan.sub_row0 || rows_in->hist_depth != g->B)
+			return fail(BCD_B200_ERR_INVALID_ARGUMENT, "tile %d holds %dx%d rows, got %dx%d", s.plan.tile_index, g->W,
+					s.plan.sub_row1 - s.plan.sub_row0, rows_in->width, rows_in->height);
+		s.hostIn = *rows_in;
+	}
+	s.hostOut = rows_out;
+	return 0;
+}
+
+int bcd_b200_group_upload_tile(bcd_b200_group* g, int local_tile, const bcd_b200_images* rows_in)
+{
+	if(!g || local_tile < 0 || local_tile >= g->nLocal) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad local tile %d", local_tile);
+	return bcd_b200_upload(g->slots[local_tile]->h, rows_in);
+}
+
+int bcd_b200_group_run(bcd_b200_group* g, const bcd_b200_params* p, int from_host)
+{
+	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	if(!g->ready) return fail(BCD_B200_ERR_STATE, "bcd_b200_group_run called before bcd_b200_group_setup / _connect");
+	if(p)
+	{
+		int rc = checkParams(p);
+		if(rc) return rc;
+		if(p->patch_radius != g->conWr || p->search_radius != g->conBr || p->nb_scales != g->conS)
+			return fail(BCD_B200_ERR_STATE, "radii / scales differ from bcd_b200_group_setup");
+		g->p = *p;
+	}
+	int rc;
+	if(g->tiles == 1)
+	{
+		if(g->nLocal < 1) return 0; // the only tile lives in another process
+		Slot& s = *g->slots[0];
+		CU(cudaSetDevice(s.device));
+		rc = 0;
+		if(from_host) rc = bcd_b200_upload_async(s.h, &s.hostIn);
+		if(!rc) rc = bcd_b200_run(s.h, &g->p, nullptr, nullptr);
+		if(!rc && from_host) rc = bcd_b200_download(s.h, s.hostOut);
+	}
+	else
+		rc = dispatch(g, from_host ? JOB_E2E : JOB_RUN);
+	if(rc) return rc;
+	collectGroupStats(g);
+	return 0;
+}
+
+int bcd_b200_group_download_tile(bcd_b200_group* g, int local_tile, float* rows_out)
+{
+	if(!g || local_tile < 0 || local_tile >= g->nLocal) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad local tile %d", local_tile);
+	Slot& s = *g->slots[local_tile];
+	if(g->tiles == 1) return bcd_b200_download(s.h, rows_out);
+	return bcd_b200_tile_download(s.h, rows_out);
+}
 
 int bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb,
 		bcd_b200_progress_fn progress, void* user)
 {
 	if(!g) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group");
+	if(g->world != 1) return fail(BCD_B200_ERR_STATE, "bcd_b200_group_denoise needs the whole frame: use the per-tile calls in a ranked group");
 	if(!out_rgb) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "Aborting denoising: nullptr for output image");
 	int rc = checkImages(in);
 	if(rc) return rc;
@@ -772,64 +1025,40 @@ int bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const b
 	pinRange(g, in->hist, np * in->hist_depth * sizeof(float));
 	pinRange(g, in->cov, np * 6 * sizeof(float));
 	pinRange(g, out_rgb, np * 3 * sizeof(float));
-	// as many tiles as GPUs, fewer when the frame is too small for that many bands
-	int tiles = g->n;
-	while(tiles > 1)
+	const bool same = g->ready && g->conW == in->width && g->conH == in->height && g->conB == in->hist_depth &&
+			g->conWr == p->patch_radius && g->conBr == p->search_radius && g->conS == p->nb_scales;
+	if(!same)
 	{
-		bool ok = true;
-		for(int r = 0; r < tiles && ok; ++r)
-			ok = bcd_b200_tile_plan(in->width, in->height, r, tiles, p, &g->plan[r]) == 0;
-		if(ok) break;
-		--tiles;
+		rc = bcd_b200_group_setup(g, in->width, in->height, in->hist_depth, p, nullptr, nullptr, 0);
+		if(!rc) rc = bcd_b200_group_connect(g, nullptr, 0);
+		if(rc) return rc;
 	}
-	g->tiles = tiles;
-	if(tiles == 1)
+	if(g->tiles == 1)
 	{
-		bcd_b200_handle* h = g->h[0];
-		rc = bcd_b200_upload_async(h, in); // the host buffers outlive the call, so the transfer can stream under the run
-		if(!rc) rc = bcd_b200_run(h, p, progress, user);
-		if(!rc) rc = bcd_b200_download(h, out_rgb);
-		if(!rc)
-		{
-			g->stats = h->stats;
-			g->timings = h->timings;
-		}
+		Slot& s = *g->slots[0];
+		CU(cudaSetDevice(s.device));
+		rc = bcd_b200_upload_async(s.h, in); // the host buffers outlive the call, so the transfer can stream under the run
+		if(!rc) rc = bcd_b200_run(s.h, p, progress, user);
+		if(!rc) rc = bcd_b200_download(s.h, out_rgb);
+		if(!rc) collectGroupStats(g);
 		return rc;
 	}
-	g->needSetup = !(g->conW == in->width && g->conH == in->height && g->conB == in->hist_depth && g->conTiles == tiles &&
-			g->conW_ == p->patch_radius && g->conB_ == p->search_radius && g->conS == p->nb_scales);
-	if(g->needSetup) g->conTiles = 0;
-	g->in = in;
-	g->p = *p;
-	g->out = out_rgb;
-	for(int r = 0; r < g->n; ++r) { g->rc[r] = 0; g->err[r].clear(); }
+	const size_t W = (size_t)in->width;
+	for(int i = 0; i < g->nLocal; ++i)
+	{
+		Slot& s = *g->slots[i];
+		const bcd_b200_tile& t = s.plan;
+		s.hostIn = *in;
+		s.hostIn.color = in->color + (size_t)t.sub_row0 * W * 3;
+		s.hostIn.nsamples = in->nsamples + (size_t)t.sub_row0 * W;
+		s.hostIn.hist = in->hist + (size_t)t.sub_row0 * W * in->hist_depth;
+		s.hostIn.cov = in->cov + (size_t)t.sub_row0 * W * 6;
+		s.hostIn.height = t.sub_row1 - t.sub_row0;
+		s.hostOut = out_rgb + (size_t)t.own_row0 * W * 3;
+	}
 	if(progress) progress(0.f, user);
-	{
-		std::unique_lock<std::mutex> lk(g->mu);
-		g->pending = g->n;
-		++g->gen;
-		g->cvGo.notify_all();
-		g->cvDone.wait(lk, [&] { return g->pending == 0; });
-	}
-	for(int r = 0; r < tiles; ++r)
-		if(g->rc[r])
-			return fail(g->rc[r], "tile %d of %d (device %d): %s", r, tiles, g->dev[r], g->err[r].c_str());
-	if(g->needSetup)
-	{
-		g->conW = in->width; g->conH = in->height; g->conB = in->hist_depth; g->conTiles = tiles;
-		g->conW_ = p->patch_radius; g->conB_ = p->search_radius; g->conS = p->nb_scales;
-	}
-	memset(&g->stats, 0, sizeof(g->stats));
-	memset(&g->timings, 0, sizeof(g->timings));
-	for(int r = 0; r < tiles; ++r)
-	{
-		const bcd_b200_stats& s = g->h[r]->stats;
-		g->stats.interior += s.interior; g->stats.strong += s.strong; g->stats.active += s.active; g->stats.full += s.full;
-		g->stats.fallback += s.fallback; g->stats.sum_n_full += s.sum_n_full; g->stats.kernel_launches += s.kernel_launches;
-		const bcd_b200_timings& t = g->h[r]->timings;
-		for(int i = 0; i < BCD_B200_STAGE_COUNT; ++i) g->timings.stage_ms[i] += t.stage_ms[i];
-		g->timings.total_ms = std::max(g->timings.total_ms, t.total_ms);
-	}
+	rc = bcd_b200_group_run(g, p, 1);
+	if(rc) return rc;
 	if(progress) progress(1.f, user);
 	return 0;
 }

@@ -292,105 +292,149 @@ def make_worker(inputs_full, params, index, count, device_index=0, main_stream=N
 
 # ---------------------------------------------------------------------------------------------------------- bench
 def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_stdout_fd=None):
-    """bench.py's N > 1 arm: one row tile per rank (one process per GPU), the tiles linked through peer memory (CUDA IPC
-    arenas over NVLink: bcd_b200_tile_setup / _connect / _run); barrier + synchronize on both sides, max over ranks.
-    BCD_B200_EXCHANGE=nccl selects the previous exchange (torch.distributed send/recv per strip) for A/B runs."""
+    """bench.py's N > 1 arm: one process per GPU, each holding its share of the row tiles in a ranked group
+    (bcd_b200_group_*: tile j on GPU j mod N, linked through CUDA IPC arenas over NVLink); barrier + synchronize on both
+    sides, max over ranks. BCD_B200_EXCHANGE=nccl selects the round-1 exchange (one tile per rank, torch.distributed
+    send/recv per strip) for A/B runs."""
     import json
     import os
     import sys
     import time
+    import numpy as np
     import torch
     from . import host
     import bench as B  # clocks sampler / constants of the N=1 arm
 
     dev = torch.device("cuda", local_rank)
     params = capi.make_params(w=a.w, b=a.b, m=a.m, scales=a.scales)
-    t = plan(W, H, rank, world, params)
-    rows = t.sub_row1 - t.sub_row0
     Bd = 60
     use_nccl = os.environ.get("BCD_B200_EXCHANGE", "peer") == "nccl"
-    pin = dict(color=torch.empty((rows, W, 3), dtype=torch.float32).pin_memory(),
-               nsamples=torch.empty((rows, W, 1), dtype=torch.float32).pin_memory(),
-               hist=torch.empty((rows, W, Bd), dtype=torch.float32).pin_memory(),
-               cov=torch.empty((rows, W, 6), dtype=torch.float32).pin_memory())
-    t0 = time.time()
-    host.synth(W, H, spp=a.spp, row0=t.sub_row0, rows=rows, out={k: v.numpy() for k, v in pin.items()})
-    gen_s = time.time() - t0
-    own_rows = t.own_row1 - t.own_row0
-    out_pin = torch.empty((own_rows, W, 3), dtype=torch.float32).pin_memory()
-    devt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-    torch.cuda.synchronize()
-    # an explicit (non-default) stream shared by the torch events (and NCCL in the A/B mode) and the handle: the legacy
-    # default stream has handle 0, which bcd_b200_set_stream reads as "use the handle's own stream"
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    h = capi.Handle(local_rank)
+
     if use_nccl:
-        worker = TileWorker(h, params, t, dev, stream, None)  # one marking stream per level
-        ex = DistExchange(dist, rank, world)
+        infos = [plan(W, H, rank, world, params)]
+        infos = [dict(own_row0=t.own_row0, own_row1=t.own_row1, sub_row0=t.sub_row0, sub_row1=t.sub_row1, tile_index=rank) for t in infos]
+        g = None
     else:
-        h.set_streams(stream.cuda_stream, 0)
-        peer_connect_dist(h, params, t, dist, rank, world, Bd)
-        worker = TileWorker.__new__(TileWorker)
-        worker.h, worker.tile = h, t
+        g = capi.Group([local_rank], rank=rank, world=world, tiles_per_gpu=a.tiles_per_gpu)
+        mine = g.setup(W, H, Bd, params)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)  # also the barrier between every process' setup and the first run
+        tokens = {}
+        for part in gathered:
+            for idx, tok in part:
+                tokens[idx] = tok
+        g.connect([tokens[j] for j in range(len(tokens))])
+        infos = [g.tile_info(i) for i in range(g.local_tiles())]
+        dist.barrier()
 
-    def run_once():
-        if use_nccl:
-            run_tile(worker, ex)
-        else:
-            peer_run(h, params)
+    # ---- inputs of the local tiles, generated straight into pinned host memory
+    t0 = time.time()
+    pins, outs = [], []
+    for t in infos:
+        rows = t["sub_row1"] - t["sub_row0"]
+        pin = dict(color=torch.empty((rows, W, 3), dtype=torch.float32).pin_memory(),
+                   nsamples=torch.empty((rows, W, 1), dtype=torch.float32).pin_memory(),
+                   hist=torch.empty((rows, W, Bd), dtype=torch.float32).pin_memory(),
+                   cov=torch.empty((rows, W, 6), dtype=torch.float32).pin_memory())
+        host.synth(W, H, spp=a.spp, row0=t["sub_row0"], rows=rows, out={k: v.numpy() for k, v in pin.items()})
+        pins.append(pin)
+        outs.append(torch.empty((t["own_row1"] - t["own_row0"], W, 3), dtype=torch.float32).pin_memory())
+    gen_s = time.time() - t0
 
-    def step_resident():
-        run_once()
+    if use_nccl:
+        h = capi.Handle(local_rank)
+        tl = plan(W, H, rank, world, params)
+        worker = TileWorker(h, params, tl, dev, stream, None)  # one marking stream per level
+        ex = DistExchange(dist, rank, world)
+        pin, rows = pins[0], infos[0]["sub_row1"] - infos[0]["sub_row0"]
+        devt = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        torch.cuda.synchronize()
 
-    def step_e2e():
-        h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd,
-                      streamed=True)
-        run_once()
-        worker.download(out_pin.data_ptr())
-
-    def timed(fn, bind):
-        if bind:
+        def prepare_resident():
             h.bind_device(devt["color"].data_ptr(), devt["nsamples"].data_ptr(), devt["hist"].data_ptr(), devt["cov"].data_ptr(), W, rows, Bd)
+
+        def step_resident():
+            run_tile(worker, ex)
+
+        def step_e2e():
+            h.upload_ptrs(pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd,
+                          streamed=True)
+            run_tile(worker, ex)
+            worker.download(outs[0].data_ptr())
+
+        def stats_timings():
+            return h.stats(), h.timings()
+    else:
+        for i, (t, pin, out) in enumerate(zip(infos, pins, outs)):
+            rows = t["sub_row1"] - t["sub_row0"]
+            g.set_tile_buffers(i, pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(),
+                               W, rows, Bd, out.data_ptr())
+
+        def prepare_resident():
+            for i, (t, pin) in enumerate(zip(infos, pins)):
+                rows = t["sub_row1"] - t["sub_row0"]
+                g.upload_tile(i, pin["color"].data_ptr(), pin["nsamples"].data_ptr(), pin["hist"].data_ptr(), pin["cov"].data_ptr(), W, rows, Bd)
+
+        def step_resident():
+            g.run(params, from_host=False)
+
+        def step_e2e():
+            g.run(params, from_host=True)
+
+        def stats_timings():
+            return g.stats(), g.timings()
+
+    def timed(fn, resident):
+        if resident:
+            prepare_resident()
         for _ in range(a.warmup):
             fn()
         torch.cuda.synchronize()
         dist.barrier()
         sampler = B.ClockSampler(local_rank, B.gpu_uuid(local_rank))
         sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage_acc, launches = {}, 0
         torch.cuda.synchronize()
+        dist.barrier()
+        # a frame spans the streams of several tile handles, so the K steps are bracketed by two events on an otherwise
+        # idle stream, each recorded while the whole device is idle (synchronised just before): their distance is the
+        # device-clock time from "before the first kernel" to "after the last one" (every step ends with all local tile
+        # streams drained by bcd_b200_group_run)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(a.steps):
             fn()
-            for k, v in h.timings().items():
+            st, tm = stats_timings()
+            for k, v in tm.items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
-            launches += h.stats()["kernel_launches"]
+            launches += st["kernel_launches"]
+        torch.cuda.synchronize()
         e1.record(stream)
         torch.cuda.synchronize()
+        ms_local = e0.elapsed_time(e1)
         dist.barrier()
         clocks = sampler.stop()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([ms_local], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ln = torch.tensor([float(launches)], device=dev)
         dist.all_reduce(ln, op=dist.ReduceOp.SUM)
         return float(ms.item()), stage_acc, int(ln.item()), clocks
 
     ms_res, stages, launches, clocks = timed(step_resident, True)
-    stats = h.stats()
+    stats, _ = stats_timings()
     ms_e2e, _, _, _ = timed(step_e2e, False)
     # ---- parity of the N-GPU frame against the SAME frame denoised by one GPU (rank 0 gathers the bands)
-    mine = torch.from_numpy(out_pin.numpy().copy()).to(dev)
-    sizes = [None] * world
-    dist.all_gather_object(sizes, own_rows)
+    bands_local = [(t["own_row0"], torch.from_numpy(o.numpy().copy())) for t, o in zip(infos, outs)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [(r0, b.numpy()) for r0, b in bands_local])
     parity = None
     if rank == 0:
-        bands = [torch.empty((r, W, 3), dtype=torch.float32, device=dev) for r in sizes]
-        bands[0].copy_(mine)
-        for r in range(1, world):
-            dist.recv(bands[r], src=r)
-        frame_n = torch.cat(bands, 0).cpu().numpy()
+        frame_n = np.empty((H, W, 3), np.float32)
+        for part in gathered:
+            for r0, band in part:
+                frame_n[r0:r0 + band.shape[0]] = band
         full = host.synth(W, H, spp=a.spp)
         h1 = capi.Handle(local_rank)
         h1.upload(**full)
@@ -399,19 +443,16 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         st1 = h1.stats()
         h1.close()
         del full
-        import numpy as np
         inner = (slice(2, -2), slice(2, -2))
         den = float(np.abs(frame_1[inner]).max())
         parity = {"rel_linf_vs_1gpu": float(np.abs(frame_n[inner] - frame_1[inner]).max() / den),
                   "what": "the N-GPU frame of this run against the same frame denoised by one GPU (bcd_b200_run); "
                           "only the order of the float atomics differs", "counters_1gpu": st1}
-    else:
-        dist.send(mine, dst=0)
     st = torch.tensor([float(stats[k]) for k in ("interior", "strong", "active", "full", "fallback", "sum_n_full")], device=dev, dtype=torch.float64)
     dist.all_reduce(st, op=dist.ReduceOp.SUM)
     pair = torch.tensor([stages["pair"] / a.steps], device=dev)
     dist.all_reduce(pair, op=dist.ReduceOp.MAX)
-    h2d = torch.tensor([float(sum(v.numel() * 4 for v in pin.values())), float(out_pin.numel() * 4)], device=dev)
+    h2d = torch.tensor([float(sum(v.numel() * 4 for pin in pins for v in pin.values())), float(sum(o.numel() * 4 for o in outs))], device=dev)
     dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
     per_rank = [None] * world
     dist.all_gather_object(per_rank, {k: round(v / a.steps, 4) for k, v in stages.items()})
@@ -425,16 +466,20 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         counters = dict(zip(("interior", "strong", "active", "full", "fallback", "sum_n_full"), [int(v) for v in st.tolist()]))
         if parity is not None:
             parity["counters_equal"] = all(counters[k] == parity["counters_1gpu"][k] for k in counters)
+        ntiles = g.tiles() if g is not None else world
+        config = dict(config)
+        config["parallelism"] = "%d row tiles dealt out cyclically to %d GPUs (one process per GPU)" % (ntiles, world)
         line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+                "timing": "CUDA events recorded on an idle device right before the first and right after the last of the K steps (a frame spans the streams of several tile handles), max over ranks",
                 "e2e": {"value": e2e_val, "unit": B.UNIT, "h2d_bytes_per_step": int(h2d[0].item()), "d2h_bytes_per_step": int(h2d[1].item()),
                         "ms_per_step": ms_e2e / a.steps,
-                        "api": "per rank: bcd_b200_upload_async(tile rows, pinned) + bcd_b200_tile_run + bcd_b200_tile_download"},
-                "gpu_launches": launches,
+                        "api": "per tile: bcd_b200_upload_async(tile rows, pinned) + bcd_b200_tile_run + bcd_b200_tile_download (bcd_b200_group_run(from_host=1))"},
+                "gpu_launches": launches, "tiles": ntiles,
                 "exchange": "nccl send/recv per strip (A/B mode)" if use_nccl else
                             "peer memory: strips pushed into the neighbour's arena over NVLink (CUDA IPC), epoch flags, marking ring chained GPU to GPU; no NCCL call and no host hop inside a frame",
-                "roofline": {"kernel": "k_pair_terms_sparse (per GPU, slowest rank)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                "roofline": {"kernel": "k_pair_terms_sparse (per GPU, slowest rank; sum over its tiles)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
                              "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_src, "traffic": None,
                              "note": "FP32-issue-bound kernel; see the N=1 line for the FP32 figure"},
                 "stage_ms_per_step_rank0": {k: v / a.steps for k, v in stages.items()},
@@ -445,11 +490,11 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         if saved_stdout_fd is not None:
             os.dup2(saved_stdout_fd, 1)
         print(json.dumps(line), flush=True)
-    if not use_nccl:  # unmap the neighbours' arenas before anyone frees its own
-        peer_connect(h, UP, None)
-        peer_connect(h, DOWN, None)
     dist.barrier()
-    h.close()
+    if g is not None:
+        g.close()
+    else:
+        h.close()
     dist.barrier()
     dist.destroy_process_group()
     return 0

@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--w", type=int, default=1)
     ap.add_argument("--b", type=int, default=6)
     ap.add_argument("--spp", type=int, default=64)
+    ap.add_argument("--tiles-per-gpu", type=int, default=0, help="N > 1: row tiles per GPU, dealt out cyclically (0 = chosen from the frame height)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plugin", action="store_true", help="skip the e2e_plugin leg (bcd::MultiscaleDenoiser::denoise() on pageable buffers)")
     ap.add_argument("--alt-spp", type=int, default=48, help="second resident measurement with this sample count (not a power of two); 0 = skip")

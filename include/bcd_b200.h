@@ -228,27 +228,53 @@ int  bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd
 int  bcd_b200_tile_connect(bcd_b200_handle* h, int side, const bcd_b200_peer_token* neighbour /* NULL: disconnect */);
 int  bcd_b200_tile_run(bcd_b200_handle* h, const bcd_b200_params* p /* NULL: the parameters of tile_setup; same radii / scales */);
 
-/* ---- group API: N GPUs of one box behind one call (what bcd::Denoiser / bcd::MultiscaleDenoiser hold) -----------------
- * A group owns one handle and one host thread per GPU, keeps every device allocation, stream and peer link across
- * frames and page-locks the caller's buffers the first time it sees them (a renderer hands over the same DeepImage
+/* ---- group API: the GPUs of one box behind one call (what bcd::Denoiser / bcd::MultiscaleDenoiser hold) ---------------
+ * A group keeps one handle and one host thread per row tile, every device allocation, stream and peer link across
+ * frames, and page-locks the caller's buffers the first time it sees them (a renderer hands over the same DeepImage
  * storage frame after frame; reference call sites src/cli/main.cpp:457-468, src/gui/GuiWindow.cpp:345-376).
- * group_denoise: host buffers in, host buffer out, like bcd_b200_denoise. With nb_gpus > 1 the frame is cut into row
- * tiles (bcd_b200_tile_plan), every GPU streams its rows from the host buffers and the tiles run in peer mode; the
- * number of tiles is reduced when the frame is too small for nb_gpus bands. device_ids may repeat a device (tests on a
- * one-GPU box). pin_host: 1 = cudaHostRegister the five host ranges (cached per pointer), 0 = leave them pageable. */
+ * The frame is cut into tiles_per_gpu x GPUs row tiles dealt out CYCLICALLY (tile j on GPU j mod G): with several tiles
+ * per GPU the raster-order marking chain pipelines behind the selection instead of starting when whole 1/G-ths of the
+ * frame are selected. tiles_per_gpu = 0 picks it from the frame height; the tile count shrinks when
+ * the frame is too small. device_ids may repeat a device (tests on a one-GPU box).
+ * group_denoise: host buffers in, host buffer out, like bcd_b200_denoise. pin_host: 1 = cudaHostRegister the five host
+ * ranges (cached per pointer), 0 = leave them pageable. */
 typedef struct bcd_b200_group bcd_b200_group;
 int  bcd_b200_group_create(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus);
 void bcd_b200_group_destroy(bcd_b200_group* g);
 int  bcd_b200_group_set_pinning(bcd_b200_group* g, int pin_host);
+int  bcd_b200_group_set_tiles_per_gpu(bcd_b200_group* g, int tiles_per_gpu);
 int  bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb,
                             bcd_b200_progress_fn progress, void* user);
-/* counters summed over the tiles; timings: per-stage sums over the tiles, total_ms = the slowest tile */
+/* counters summed over the (local) tiles; timings: per-stage sums over the tiles, total_ms = the slowest tile */
 int  bcd_b200_group_get_stats(bcd_b200_group* g, bcd_b200_stats* s);
 int  bcd_b200_group_get_timings(bcd_b200_group* g, bcd_b200_timings* t);
-int  bcd_b200_group_tiles(bcd_b200_group* g); /* tiles the last frame was cut into */
+int  bcd_b200_group_tiles(bcd_b200_group* g);       /* tiles the frame is cut into (all processes) */
+int  bcd_b200_group_local_tiles(bcd_b200_group* g); /* tiles held by this process */
 /* one-shot multi-GPU variant of bcd_b200_denoise (creates and destroys a group) */
 int  bcd_b200_denoise_multi(const bcd_b200_images* in, const bcd_b200_params* p, float* out_rgb, const int32_t* device_ids,
                             int nb_gpus, bcd_b200_progress_fn progress, void* user);
+
+/* The same group when the GPUs of the box are spread over several processes (one process per GPU under torchrun /
+ * MPI: rank r of `world`, each with nb_gpus local devices). No process sees the whole frame: it asks for its tiles
+ * (group_setup, group_tile_info), hands over their rows and drives them; the arenas of the neighbouring tiles are
+ * linked through CUDA IPC from the tokens every process contributes (e.g. one all_gather at start-up, which is also the
+ * barrier between setup and the first run).
+ *   group_setup         plans the tiles of a W x H frame, sets up the local ones (warm-up pass included), returns their
+ *                       tokens and frame-wide tile indices (capacity = room in both arrays);
+ *   group_connect       tokens_by_tile[j] = token of tile j for every tile of the frame (NULL in a one-process group);
+ *   group_set_tile_buffers  host rows of a local tile (sub_row0 .. sub_row1) and where its output rows go: used by
+ *                       group_run(from_host = 1) = streamed upload + run + download per tile, all tiles concurrently;
+ *   group_upload_tile   synchronous upload of a local tile's rows; group_run(from_host = 0) then runs on the resident rows;
+ *   group_download_tile owned output rows of a local tile after a run. */
+int  bcd_b200_group_create_ranked(bcd_b200_group** out, const int32_t* device_ids, int nb_gpus, int rank, int world);
+int  bcd_b200_group_setup(bcd_b200_group* g, int width, int height, int hist_depth, const bcd_b200_params* p,
+                          bcd_b200_peer_token* tokens_out, int32_t* tile_indices_out, int capacity);
+int  bcd_b200_group_connect(bcd_b200_group* g, const bcd_b200_peer_token* tokens_by_tile, int nb_tiles);
+int  bcd_b200_group_tile_info(bcd_b200_group* g, int local_tile, bcd_b200_tile* out);
+int  bcd_b200_group_set_tile_buffers(bcd_b200_group* g, int local_tile, const bcd_b200_images* rows_in, float* rows_out);
+int  bcd_b200_group_upload_tile(bcd_b200_group* g, int local_tile, const bcd_b200_images* rows_in);
+int  bcd_b200_group_run(bcd_b200_group* g, const bcd_b200_params* p, int from_host);
+int  bcd_b200_group_download_tile(bcd_b200_group* g, int local_tile, float* rows_out);
 
 /* ---- stage-level read-backs used by the parity tests (level 0 of the last run) ---------------------------------
  * masks: W*H*words uint32, bit index (dy+b)*(2b+1)+(dx+b) — the ordered similar set S(p) of

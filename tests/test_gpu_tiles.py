@@ -118,6 +118,28 @@ def test_group_tiles_on_one_device_equal_full_frame(count, kw):
         g.close()
 
 
+@pytest.mark.parametrize("gpus,per,kw", [
+    (2, 2, dict(m=1.0, scales=2)),
+    (2, 3, dict(m=1.0, scales=1)),
+    (3, 2, dict(m=0.0, scales=2)),
+])
+def test_group_with_several_cyclic_tiles_per_gpu(gpus, per, kw):
+    """tiles_per_gpu > 1: tile j runs on GPU j mod G, so neighbouring tiles sit on different GPUs and a GPU holds several
+    handles whose marking chains depend on each other through the other GPUs."""
+    from bcd_b200 import capi, host
+    inp = host.synth(136, 64 * gpus * per + 24, spp=16)
+    ref, st_ref = _full(capi, inp, **kw)
+    g = capi.Group([0] * gpus, tiles_per_gpu=per)
+    try:
+        for _ in range(2):
+            out = g.denoise(**inp, **kw)
+            assert g.tiles() == gpus * per
+            _counters_equal(g.stats(), st_ref)
+            assert O.rel_linf(out, ref) <= 2e-6
+    finally:
+        g.close()
+
+
 def test_group_reduces_the_tile_count_for_small_frames():
     from bcd_b200 import capi, host
     inp = host.synth(64, 96, spp=16)
@@ -175,3 +197,20 @@ def test_cxx_session_keeps_its_device_session_across_frames():
             assert O.rel_linf(s.fetch(), ref) <= 2e-6
     finally:
         s.close()
+
+
+def test_peer_tiles_across_processes_equal_one_gpu():
+    """One process per GPU (torchrun), arenas shared through CUDA IPC — the path bench.py's N > 1 arm takes.
+    Skipped on a one-GPU box."""
+    import os
+    import subprocess
+    import sys
+    from bcd_b200 import capi
+    n = min(capi.lib().bcd_b200_device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29431", os.path.join(root, "tools", "dist_parity.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_PARITY OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

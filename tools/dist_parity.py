@@ -1,7 +1,12 @@
-"""Multi-process check of the row-tile path over NCCL (run under torchrun on the GPU box):
-every rank denoises its band; rank 0 also denoises the full frame on its own GPU and compares."""
+"""Multi-process check of the row-tile path (run under torchrun on the GPU box): every rank denoises its band; rank 0
+also denoises the full frame on its own GPU and compares. Default: peer mode (CUDA IPC arenas over NVLink,
+bcd_b200_tile_setup / _connect / _run — what bench.py's N > 1 arm uses); BCD_B200_EXCHANGE=nccl: the previous exchange
+(torch.distributed send/recv per strip)."""
 import os
 import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import numpy as np
 import torch
@@ -28,9 +33,17 @@ def main():
         rows = t.sub_row1 - t.sub_row0
         sub = host.synth(W, H, spp=24, row0=t.sub_row0, rows=rows)
         h = capi.Handle(lr)
-        worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr), stream, None)  # one marking stream per level
-        h.upload(**sub)
-        tiles.run_tile(worker, tiles.DistExchange(dist, rank, world))
+        if os.environ.get("BCD_B200_EXCHANGE", "peer") == "nccl":
+            worker = tiles.TileWorker(h, params, t, torch.device("cuda", lr), stream, None)  # one marking stream per level
+            h.upload(**sub)
+            tiles.run_tile(worker, tiles.DistExchange(dist, rank, world))
+        else:
+            worker = tiles.TileWorker.__new__(tiles.TileWorker)
+            worker.h, worker.tile = h, t
+            tiles.peer_connect_dist(h, params, t, dist, rank, world)
+            for _ in range(3):  # several frames: the epochs advance in step on every rank
+                h.upload_async(**sub)
+                tiles.peer_run(h, params)
         mine = torch.from_numpy(worker.download()).cuda()
         sizes = [tiles.plan(W, H, i, world, params) for i in range(world)]
         parts = [torch.empty((s.own_row1 - s.own_row0, W, 3), device="cuda") for s in sizes] if rank == 0 else None
@@ -42,6 +55,10 @@ def main():
             dist.send(mine, dst=0)
         st = torch.tensor([float(h.stats()[k]) for k in ("interior", "strong", "active", "full", "fallback")], device="cuda", dtype=torch.float64)
         dist.all_reduce(st)
+        if os.environ.get("BCD_B200_EXCHANGE", "peer") != "nccl":
+            tiles.peer_connect(h, tiles.UP, None)
+            tiles.peer_connect(h, tiles.DOWN, None)
+            dist.barrier()
         h.close()
         if rank == 0:
             full = host.synth(W, H, spp=24)
