@@ -559,7 +559,7 @@ int collectTimings(bcd_b200_handle* h)
 		{
 			float t0 = 0.f;
 			cudaEventElapsedTime(&t0, h->evTotal[0], h->events[sp.b]);
-			fprintf(stderr, "[bcd_b200 trace] dev %d %-12s start %8.3f  dur %7.3f\n", h->device,
+			fprintf(stderr, "[bcd_b200 trace] dev %d tile %2d %-12s start %8.3f  dur %7.3f\n", h->device, h->tiled ? h->tileIndex : 0,
 					sp.stage >= 0 && sp.stage < BCD_B200_STAGE_COUNT ? names[sp.stage] : "?", t0, ms);
 		}
 	}

@@ -98,7 +98,7 @@ def test_group_tiles_on_one_device_equal_full_frame(count, kw):
     from bcd_b200 import capi, host
     inp = host.synth(120, 208, spp=24)
     ref, st_ref = _full(capi, inp, **kw)
-    g = capi.Group([0] * count)
+    g = capi.Group([0] * count, tiles_per_gpu=1)
     try:
         out = g.denoise(**inp, **kw)
         assert g.tiles() == count
@@ -170,7 +170,7 @@ def test_group_on_several_gpus_equals_one_gpu():
     inp = host.synth(640, 64 * n + 40, spp=16)
     for kw in (dict(m=1.0, scales=3), dict(m=0.0, scales=1), dict(m=1.0, scales=2, b=4)):
         ref, st_ref = _full(capi, inp, **kw)
-        g = capi.Group(list(range(n)))
+        g = capi.Group(list(range(n)), tiles_per_gpu=1)
         try:
             for _ in range(3):
                 out = g.denoise(**inp, **kw)
