@@ -266,7 +266,14 @@ namespace
 
 		SpikeRemovalFilter::s_device = a.m_device;
 		if(a.m_prefilterSpikes)
+		{
 			SpikeRemovalFilter::filter(color, nbOfSamples, histogram, covariance, a.m_prefilterFactor);
+			if(!SpikeRemovalFilter::s_lastCallSucceeded) // mismatched input files or no device: do not denoise unfiltered inputs silently
+			{
+				std::cerr << "ERROR: spike removal prefiltering failed" << std::endl;
+				return 1;
+			}
+		}
 
 		DenoiserInputs inputs;
 		inputs.m_pColors = &color;

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <exception>
 #include <iostream>
 #include <vector>
 
@@ -33,7 +34,38 @@ namespace bcd
 
 	const std::string& ImageIO::lastError() { return t_lastError; }
 
+	static bool loadEXRBody(DeepImage<float>& o_rImage, const char* i_pFilePath);
+	static bool loadMultiChannelsEXRBody(DeepImage<float>& o_rImage, const char* i_pFilePath);
+
+	// The loaders size their images from the file's header; whatever goes wrong on the way — including running out of
+	// memory on a hostile header — comes back as `false` + lastError(), never as an exception through the host renderer.
 	bool ImageIO::loadEXR(DeepImage<float>& o_rImage, const char* i_pFilePath)
+	{
+		try
+		{
+			return loadEXRBody(o_rImage, i_pFilePath);
+		}
+		catch(const std::exception& e)
+		{
+			o_rImage.clearAndFreeMemory();
+			return failWith(std::string("cannot load the image: ") + e.what(), i_pFilePath);
+		}
+	}
+
+	bool ImageIO::loadMultiChannelsEXR(DeepImage<float>& o_rImage, const char* i_pFilePath)
+	{
+		try
+		{
+			return loadMultiChannelsEXRBody(o_rImage, i_pFilePath);
+		}
+		catch(const std::exception& e)
+		{
+			o_rImage.clearAndFreeMemory();
+			return failWith(std::string("cannot load the image: ") + e.what(), i_pFilePath);
+		}
+	}
+
+	static bool loadEXRBody(DeepImage<float>& o_rImage, const char* i_pFilePath)
 	{
 		std::cout << "Loading " << i_pFilePath << std::endl;
 		bcdio::ExrReader rd;
@@ -62,7 +94,7 @@ namespace bcd
 		return true;
 	}
 
-	bool ImageIO::loadMultiChannelsEXR(DeepImage<float>& o_rImage, const char* i_pFilePath)
+	static bool loadMultiChannelsEXRBody(DeepImage<float>& o_rImage, const char* i_pFilePath)
 	{
 		std::cout << "Loading " << i_pFilePath << std::endl;
 		bcdio::ExrReader rd;

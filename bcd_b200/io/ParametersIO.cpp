@@ -174,17 +174,25 @@ namespace bcd
 			}
 			return q + "\"";
 		}
-		std::string number(double v)
+		std::string number(int v)
 		{
-			// shortest text that reads back as the same float (the fields are floats or ints)
+			char b[32];
+			snprintf(b, sizeof b, "%d", v);
+			return b;
+		}
+
+		std::string number(float v)
+		{
+			// shortest text that reads back as the same float; a float field always reads as a JSON real ("1.0", like
+			// nlohmann::json writes it), so that a strict reader sees the same types the reference's files have
 			char b[64];
 			for(int prec = 1; prec <= 17; ++prec)
 			{
-				snprintf(b, sizeof b, "%.*g", prec, v);
-				if((float)strtod(b, nullptr) == (float)v) break;
+				snprintf(b, sizeof b, "%.*g", prec, (double)v);
+				if((float)strtod(b, nullptr) == v) break;
 			}
 			std::string s = b;
-			if(s.find_first_of(".eEn") == std::string::npos && v != (long long)v) s += ".0";
+			if(s.find_first_of(".eEn") == std::string::npos) s += ".0";
 			return s;
 		}
 	}

@@ -822,6 +822,7 @@ static bool exrOpenBody(const char* path, ExrReader& rd, std::string& err)
 	std::vector<ExrReader::Chunk>& refs = rd.chunks;
 	refs.resize(nChunks);
 	const uint8_t* seq = r.p;
+	std::vector<bool> seen(nChunks, false); // every block of lines exactly once: no duplicates, no holes
 	for(int i = 0; i < nChunks; ++i)
 	{
 		if(offsets[i] >= buf.size()) { err = "bad chunk offset"; return false; }
@@ -832,10 +833,21 @@ static bool exrOpenBody(const char* path, ExrReader& rd, std::string& err)
 		seq = c.p + n;
 		const long ly = (long)y - out.minY;
 		if(ly < 0 || ly >= h || ly % lpc) { err = "bad chunk coordinate"; return false; }
+		if(seen[ly / lpc]) { err = "duplicate chunk"; return false; }
+		seen[ly / lpc] = true;
 		refs[i].offset = (size_t)(c.p - buf.data());
 		refs[i].size = (size_t)n;
 		refs[i].line = ly;
 		refs[i].lines = (int)std::min<long>(lpc, h - ly);
+		// what the chunk claims to expand to is bounded by what its bytes can encode (deflate tops out near 1032:1, the
+		// run-length and Huffman coders below that), and an uncompressed chunk has exactly its size: a small file cannot
+		// make the decoder — or the caller sizing its image from the header — allocate gigabytes
+		const uint64_t rawSize = (uint64_t)lineBytes * refs[i].lines;
+		if(out.compression == EXR_NONE ? rawSize != (uint64_t)n : rawSize > (uint64_t)n * 1100u + 4096u)
+		{
+			err = "chunk too small for the data window";
+			return false;
+		}
 	}
 	return true;
 }

@@ -25,6 +25,9 @@ namespace bcd
 		/// under GCC/glibc and to the float overload under MSVC; true (default) reproduces the GCC build.
 		static bool s_useIntegerAbsLikeGccBuild;
 		static int s_device;
+		/// bcd_b200 extension: false when the last filter() call left the images untouched (mismatched sizes, no device);
+		/// filter() keeps the reference's void signature.
+		static bool s_lastCallSucceeded;
 	};
 
 } // namespace bcd

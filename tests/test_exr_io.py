@@ -112,6 +112,59 @@ def test_error_paths_return_false_with_a_message(tmp_path):
         pass
 
 
+def _exr_header(width, height, channels, compression):
+    """Minimal single-part scan-line OpenEXR header (version 2): FLOAT channels, data window at the origin."""
+    import struct
+
+    def attr(name, typ, payload):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(payload)) + payload
+
+    chl = b"".join(c.encode() + b"\0" + struct.pack("<iBBBBii", 2, 0, 0, 0, 0, 1, 1) for c in channels) + b"\0"
+    box = struct.pack("<iiii", 0, 0, width - 1, height - 1)
+    hdr = struct.pack("<II", 20000630, 2)
+    hdr += attr("channels", "chlist", chl) + attr("compression", "compression", bytes([compression]))
+    hdr += attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box)
+    hdr += attr("lineOrder", "lineOrder", b"\0") + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+    hdr += attr("screenWindowCenter", "v2f", struct.pack("<ff", 0, 0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+    return hdr + b"\0"
+
+
+def test_hostile_headers_cannot_make_the_loaders_allocate_the_declared_window(tmp_path):
+    """a half-megabyte file may declare a 2^20-wide window with thousands of channels and point every table
+    entry at one small chunk. The loaders must refuse it (false + message) before sizing anything from the header — no
+    std::bad_alloc through the host process, no gigabytes zero-filled."""
+    import struct
+    import resource
+    channels = ["Bin_%04d" % i for i in range(2000)]
+    for compression, lines in ((3, 16), (0, 1)):  # ZIP (16 lines per chunk), NONE
+        height = 64
+        hdr = _exr_header(1 << 20, height, channels, compression)
+        nchunks = (height + lines - 1) // lines
+        table_at = len(hdr)
+        chunk_at = table_at + 8 * nchunks
+        payload = b"\x78\x9c" + b"\0" * 64
+        body = struct.pack("<ii", 0, len(payload)) + payload
+        data = hdr + b"".join(struct.pack("<Q", chunk_at) for _ in range(nchunks)) + body
+        path = str(tmp_path / ("hostile_%d.exr" % compression))
+        open(path, "wb").write(data)
+        before = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss
+        for multi in (True, False):
+            with pytest.raises(host.ExrError) as e:
+                host.exr_load(path, multi)
+            assert str(e.value)
+        assert resource.getrusage(resource.RUSAGE_SELF).ru_maxrss - before < 200 * 1024  # KiB: nothing near the declared 500+ GB
+    # distinct table entries that all name the same block of lines: duplicates are refused as well
+    hdr = _exr_header(8, 32, ["R", "G", "B"], 0)
+    row = struct.pack("<ii", 0, 8 * 3 * 4) + b"\0" * (8 * 3 * 4)
+    table_at = len(hdr)
+    offs = [table_at + 8 * 32 + i * len(row) for i in range(32)]
+    data = hdr + b"".join(struct.pack("<Q", o) for o in offs) + row * 32  # every chunk says y = 0
+    path = str(tmp_path / "dup.exr")
+    open(path, "wb").write(data)
+    with pytest.raises(host.ExrError):
+        host.exr_load(path, False)
+
+
 def test_own_round_trip_special_values(tmp_path):
     rng = np.random.default_rng(3)
     a = rng.standard_normal((23, 31, 4)).astype(np.float32) * 50

@@ -132,3 +132,16 @@ def test_pair_term_planes_reproduce_the_golden_selection(crop_a):
         assert np.array_equal(sel, got.astype(bool)), "offset %d" % j
         checked += sel.size
     assert checked > 50000
+
+
+def test_port_matches_reference_golden_at_c1_scale():
+    """BASELINE.json configs[0], G(256,256) s=1 m=1: the C restatement against the stored output of the compiled
+    reference (tests/golden/make_golden_scale.py); inputs regenerated by the seeded generator."""
+    import os
+    from bcd_b200 import host
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scale_c1_256.npz"))
+    c1 = host.synth(256, 256, spp=64)
+    chk = np.array([float(np.asarray(c1[k], np.float64).sum()) for k in ("color", "nsamples", "hist", "cov")])
+    assert np.allclose(chk, g["checksum"], rtol=1e-12)
+    out = O.port_denoise(**c1, m=1.0, scales=1)
+    assert O.rel_linf(out, g["ref_s1_m1"]) <= 1e-5
