@@ -9,6 +9,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -212,6 +213,10 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // upload band: the pair terms of band [r0, r1) read histogram rows < min(H, r1 + b) (band heights are multiples of the
 // tile height), and the patch selection of a band follows as soon as the pair terms of the next band (its w halo rows)
 // are there — so only the last band's kernels run after the transfer.
+// whole-frame schedule: false = the levels are filtered one after the other on the main stream behind a host read-back
+// of their work counters (round 1); true = every level is a pipeline of its own (marking -> filter -> finalize on the
+// level's stream, list lengths stay on the device, no host wait inside a frame) — BCD_B200_SCHED=serial|levels
+bool g_schedLevels = true;
 bool g_streamCoarse = true; // BCD_B200_STREAM_COARSE=0: coarser levels start their selection after the upload (A/B hook)
 
 // Under a streamed upload the coarser levels do not have to wait for the frame either: rows < rowEnd >> k of level k
@@ -265,7 +270,7 @@ int coarseBand(bcd_b200_handle* h, const bcd_b200_params& p, int k, int availRow
 	return 0;
 }
 
-int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p, int coarseLevels = 0)
+int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p, int coarseLevels)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
@@ -383,7 +388,7 @@ int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 		h->pyrHistDone = l;
 	}
 	if(!rc) rc = levelClear(h, k, p);
-	if(!rc) rc = levelPairAndPatchSelect(h, k, p);
+	if(!rc) rc = levelPairAndPatchSelect(h, k, p, 0);
 	return rc;
 }
 
@@ -451,10 +456,11 @@ int levelMark(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 }
 
 // stage 3: fallback mean + two-step Bayesian filter, accumulated into acc.
-// Whole-frame runs (st = main stream, private = false): the host has read the level's work counters (levelMarkWait), the
-// chunks of the full list go through the scratch shared by all levels. Row-tile peer mode (private = true): the level
-// runs on its own stream with its own scratch and the list length stays on the device.
-int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStream_t st, bool deviceCounts)
+// deviceCounts = false: the host has read the level's work counters (levelMarkWait) and sizes the chunk loop from them;
+// true (row tiles in peer mode): the list length stays on the device, no host wait between marking and filter.
+// privateScratch: the level has its own chain scratch (levels filtered side by side on their own streams) instead of
+// the one shared by all levels of the handle (levels filtered one after the other on the main stream).
+int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStream_t st, bool deviceCounts, bool privateScratch)
 {
 	LevelBufs& L = h->levels[k];
 	const LevelGeom g = levelGeom(h, k, p);
@@ -467,14 +473,14 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 					&dc->nFallback, L.acc.as<float4>(), st, &h->launches));
 	});
 	FilterBuffers fb;
-	fb.A = (deviceCounts ? L.fA : h->fA).as<float>();
-	fb.Minv = (deviceCounts ? L.fMinv : h->fMinv).as<float>();
-	fb.mean = (deviceCounts ? L.fMean : h->fMean).as<float>();
-	fb.noise = (deviceCounts ? L.fNoise : h->fNoise).as<float>();
+	fb.A = (privateScratch ? L.fA : h->fA).as<float>();
+	fb.Minv = (privateScratch ? L.fMinv : h->fMinv).as<float>();
+	fb.mean = (privateScratch ? L.fMean : h->fMean).as<float>();
+	fb.noise = (privateScratch ? L.fNoise : h->fNoise).as<float>();
 	fb.xScratch = h->fX.as<float>();
 	fb.smCount = h->smCount;
 	fb.gridCap = h->smCount * 2;
-	const int chunk = deviceCounts ? L.filterChunk : h->filterChunk;
+	const int chunk = privateScratch ? L.filterChunk : h->filterChunk;
 	// upper bound of the list length the host knows without a read-back: the owned patch centres
 	const long long bound = deviceCounts ? (long long)std::max(0, g.rowEnd - g.rowBeg) * std::max(0, g.W - 2 * g.w) : c.nFull;
 	for(long long first = 0; first < bound; first += chunk)
@@ -504,7 +510,7 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 
 int levelFilter(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 {
-	return levelFilterOn(h, k, p, h->stream, false);
+	return levelFilterOn(h, k, p, h->stream, false, false);
 }
 
 // row-tile entry: filters of level k; colour / covariance part of the pyramid and the per-pixel covariances on demand
@@ -547,6 +553,7 @@ int levelMerge(bcd_b200_handle* h, int k)
 
 int collectTimings(bcd_b200_handle* h)
 {
+	h->timingsPending = false;
 	static const char* names[] = {"prepass", "pair", "select", "marking", "fallback", "filter_stats", "filter_eig", "filter_apply",
 			"finalize", "pyramid", "exchange"};
 	for(const bcd_b200_handle::Span& sp : h->spans)
@@ -811,6 +818,10 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		e = getenv("BCD_B200_EIG_GROUP");
 		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
 			g_eigGroup = atoi(e);
+		e = getenv("BCD_B200_SCHED");
+		if(e) g_schedLevels = strcmp(e, "serial") != 0;
+		e = getenv("BCD_B200_EIG_GENERIC");
+		g_eigGenericOrder = e && e[0] == '1';
 		e = getenv("BCD_B200_TRACE");
 		h->trace = e && e[0] == '1';
 		int sms = 0;
@@ -1025,6 +1036,8 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	int rc = checkParams(p);
 	if(rc) return rc;
 	CU(cudaSetDevice(h->device));
+	if(g_schedLevels)
+		return runLevelPipelines(h, p, progress, user);
 	rc = ensureBuffers(h, *p);
 	if(rc) return rc;
 	memset(&h->stats, 0, sizeof(h->stats));
@@ -1087,8 +1100,9 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 		progress(1.f, user);
 	CU(cudaEventRecord(h->evTotal[1], st));
 	CU(cudaStreamSynchronize(st));
-	rc = collectTimings(h);
-	if(rc) return rc;
+	h->stats.kernel_launches = h->launches;
+	h->timingsPending = true; // the spans are resolved when somebody asks (bcd_b200_get_timings) or traces
+	if(h->trace && (rc = collectTimings(h))) return rc;
 	h->ran = true;
 	return 0;
 }
@@ -1121,6 +1135,12 @@ int bcd_b200_get_stats(bcd_b200_handle* h, bcd_b200_stats* s)
 int bcd_b200_get_timings(bcd_b200_handle* h, bcd_b200_timings* t)
 {
 	if(!h || !t) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / output");
+	if(h->timingsPending)
+	{
+		CU(cudaSetDevice(h->device));
+		int rc = collectTimings(h);
+		if(rc) return rc;
+	}
 	*t = h->timings;
 	return 0;
 }
@@ -1178,11 +1198,20 @@ int bcd_b200_tile_plan(int image_width, int image_height, int tile_index, int ti
 	const int align = 1 << (p->nb_scales - 1);            // band boundaries fall on the same rows at every level
 	const int halo = (p->search_radius + p->patch_radius) * align;
 	const int units = (image_height + align - 1) / align; // rows in units of `align`
-	auto boundary = [&](int t) { return (int)std::min<long long>((long long)image_height, ((long long)units * t / tile_count) * align); };
-	const int r0 = tile_index == 0 ? 0 : boundary(tile_index);
-	const int r1 = tile_index == tile_count - 1 ? image_height : boundary(tile_index + 1);
+	const int minRows = (p->search_radius + p->patch_radius + 2) << (p->nb_scales - 1);
+	// tile boundaries (rows), tile_count + 1 of them
+	std::vector<int> bound(tile_count + 1, 0);
+	auto equalSplit = [&]() {
+		for(int t = 0; t <= tile_count; ++t)
+			bound[t] = t == tile_count ? image_height : (int)std::min<long long>((long long)image_height, ((long long)units * t / tile_count) * align);
+	};
+	equalSplit();
+	// (Band heights shaped by a cost model of the marking chain — start_r = max(a R_r, done_{r-1}), done_r = start_r + c R_r,
+	// finish_r = done_r + f R_r with the measured a : c : f = 7.2 : 1.07 : 5.6 — were tried and dropped: the optimum of that
+	// model is within 1 % of equal bands, because a tile that gets more rows also selects longer and holds the chain up.)
+	const int r0 = bound[tile_index], r1 = bound[tile_index + 1];
 	// every level must keep at least b+w owned rows (contributions never reach beyond the direct neighbour)
-	if(tile_count > 1 && ((r1 - r0) >> (p->nb_scales - 1)) < p->search_radius + p->patch_radius + 2)
+	if(tile_count > 1 && r1 - r0 < minRows)
 		return fail(BCD_B200_ERR_UNSUPPORTED, "tile %d has too few rows (%d) for %d scales and b+w=%d", tile_index, r1 - r0,
 				p->nb_scales, p->search_radius + p->patch_radius);
 	out->image_width = image_width;

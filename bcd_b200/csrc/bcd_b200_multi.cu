@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 #include <thread>
 #include <unistd.h>
 
@@ -204,6 +205,8 @@ int markPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 			CU(launchAllActive(g, L.active.as<uint32_t>(), Wp, st, &h->launches));
 		CU(launchBuildLists(L.counts.as<int>(), L.active.as<uint32_t>(), Wp, g, L.fullList.as<int>(),
 				L.fallbackList.as<int>(), L.ctr.as<DeviceCounters>(), st, &h->launches));
+		// work counters of the level: statistics, and (whole-frame runs) the list lengths the host sizes the filter with
+		CU(cudaMemcpyAsync(L.hostCtr, L.ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
 	});
 	CU(cudaEventRecord(L.evMark, st));
 	return 0;
@@ -220,10 +223,17 @@ int filterPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	int own0, own1;
 	tileOwnedRows(h, k, own0, own1);
 	CU(cudaStreamWaitEvent(st, h->peer.evColor, 0));
-	int rc = levelFilterOn(h, k, p, st, true);
+	int rc;
+	if(h->tiled)
+		rc = levelFilterOn(h, k, p, st, true, true); // list lengths stay on the device: no host hop in the chain of the tiles
+	else
+	{
+		// whole frame: nothing depends on another GPU, and the host has queued all the work that does not need the
+		// counters — waiting for them here costs no device time and spares the empty chunk launches
+		rc = levelMarkWait(h, k);
+		if(!rc) rc = levelFilterOn(h, k, p, st, false, true);
+	}
 	if(rc) return rc;
-	// work counters of the level for the statistics (read after the final synchronisation)
-	CU(cudaMemcpyAsync(L.hostCtr, L.ctr.p, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, st));
 	const size_t accRow = (size_t)g.W * sizeof(float4), outRow = (size_t)g.W * 3 * sizeof(float);
 	STAGE_ON(h, st, BCD_B200_STAGE_EXCHANGE, {
 		// partial sums accumulated outside my band go to their owner and are ADDED there
@@ -266,7 +276,7 @@ int mergedRowsPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 }
 
 // solo = the warm-up pass of bcd_b200_tile_setup: the same launches without any neighbour (see there)
-int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
+int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd_b200_progress_fn progress = nullptr, void* user = nullptr)
 {
 	if(!h->peer.enabled) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before bcd_b200_tile_setup");
 	if(!h->haveInputs) return fail(BCD_B200_ERR_STATE, "bcd_b200_tile_run called before upload/bind_device");
@@ -301,9 +311,30 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
 	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));
 	// selection of every level on the main stream, finest first (its marking chain is the longest); each level's chain
 	// follows on the level's own stream as soon as its selection is there
+	int streamedCoarse = 0; // whole-frame runs under a streamed upload: levels whose selection ran band by band behind level 0
 	for(int k = 0; k < s; ++k)
 	{
-		if((rc = levelSelect(h, k, p))) return rc;
+		if(h->tiled || k == 0 || k > streamedCoarse)
+		{
+			if(h->tiled)
+				rc = levelSelect(h, k, p);
+			else
+			{
+				rc = k > 0 ? pyramidLevel(h, k, 1) : 0;
+				if(!rc) rc = levelClear(h, k, p);
+				if(!rc) rc = levelPairAndPatchSelect(h, k, p, k == 0 ? s - 1 : 0);
+				if(k == 0) streamedCoarse = h->up.coarseDone;
+			}
+			if(rc) return rc;
+		}
+		else
+		{
+			// selected on the coarse stream already; the accumulator / bit-rows / counters still have to be cleared before
+			// the level's marking stream may start: re-record the selection event behind the clear
+			CU(cudaStreamWaitEvent(st, h->levels[k].evSel, 0));
+			if((rc = levelClear(h, k, p))) return rc;
+			CU(cudaEventRecord(h->levels[k].evSel, st));
+		}
 		if((rc = markPeer(h, k, p))) return rc;
 	}
 	// colour / covariance side of the pyramid, per-pixel covariances
@@ -315,8 +346,11 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
 	CU(cudaEventRecord(h->peer.evColor, st));
 	// the levels' filter pipelines run side by side; coarsest first in issue order (its chain through the ranks is the
 	// shortest, so on the lower tiles it is ready first)
-	for(int k = s - 1; k >= 0; --k)
+	for(int i = 0; i < s; ++i)
+	{
+		const int k = h->tiled ? s - 1 - i : i; // whole frame: finest first — its marking was started first
 		if((rc = filterPeer(h, k, p))) return rc;
+	}
 	// merges coarsest to finest on the main stream (MultiscaleDenoiser.cpp:79-134)
 	CU(cudaStreamWaitEvent(st, h->peer.evOut[s - 1], 0));
 	for(int k = s - 2; k >= 0; --k)
@@ -328,9 +362,29 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
 	CU(cudaMemcpyAsync(h->peer.hostTimeouts, h->peer.tickets.as<unsigned int>() + TIMEOUT_WORD, sizeof(unsigned int),
 			cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(h->evTotal[1], st));
+	if(progress)
+	{
+		// the host has nothing left to do but wait: report the levels as they finish (weights like
+		// MultiscaleDenoiser.cpp:85,103-112: a finer scale counts 4x), on the caller's thread
+		const float total = float(((1 << (2 * s)) - 1) / 3);
+		float doneWeight = 0.f;
+		std::vector<bool> seen(s, false);
+		while(cudaStreamQuery(st) == cudaErrorNotReady)
+		{
+			for(int k = 0; k < s; ++k)
+				if(!seen[k] && cudaEventQuery(h->peer.evOut[k]) == cudaSuccess)
+				{
+					seen[k] = true;
+					doneWeight += float(1 << (2 * (s - 1 - k)));
+					progress(std::min(0.99f, doneWeight / total), user);
+				}
+			std::this_thread::sleep_for(std::chrono::microseconds(50));
+		}
+		cudaGetLastError();
+	}
 	CU(cudaStreamSynchronize(st));
 	unsigned int markTimeouts = 0;
-	for(int k = 0; k < s; ++k)
+	for(int k = 0; k < s && h->tiled; ++k) // (whole-frame runs took the counters in levelMarkWait)
 	{
 		const DeviceCounters c = *h->levels[k].hostCtr;
 		h->levels[k].counters = c;
@@ -345,20 +399,52 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false)
 		return fail(BCD_B200_ERR_CUDA, "tile %d of %d: %u strip waits and %u marking hand-offs timed out (neighbouring tile lost or out of step)",
 				h->tileIndex, h->tileCount, t, markTimeouts);
 	}
-	if((rc = collectTimings(h))) return rc;
+	h->stats.kernel_launches = h->launches;
+	h->timingsPending = true;
+	if(h->trace && (rc = collectTimings(h))) return rc;
 	h->ran = true;
 	return 0;
 }
 
 } // namespace
 
-extern "C"
+int peerPrepare(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth);
+
+namespace bcdeng
 {
 
-int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth,
-		bcd_b200_peer_token* token_out)
+// bcd_b200_run in its "levels" schedule: the whole frame as one tile without neighbours
+int runLevelPipelines(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress_fn progress, void* user)
 {
-	if(!h || !t || !token_out) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / tile / token");
+	bcd_b200_handle::Peer& P = h->peer;
+	const bool same = P.enabled && !h->tiled && h->tileCount == 1 && P.geomW == h->W && P.geomH == h->H && P.geomHist == h->B &&
+			P.geomB == p->search_radius && P.geomWr == p->patch_radius && P.geomScales == p->nb_scales;
+	if(!same)
+	{
+		// inputs are resident (or streaming in): only the bookkeeping of the level pipelines is (re)built
+		bcd_b200_tile t;
+		t.image_width = h->W; t.image_height = h->H;
+		t.own_row0 = 0; t.own_row1 = h->H; t.sub_row0 = 0; t.sub_row1 = h->H;
+		t.tile_index = 0; t.tile_count = 1;
+		const bool had = h->haveInputs, pending = h->up.pending;
+		int rc = peerPrepare(h, p, &t, h->B);
+		h->haveInputs = had;
+		h->up.pending = pending;
+		if(rc) return rc;
+	}
+	if(progress) progress(0.f, user);
+	int rc = tileRun(h, *p, true, progress, user);
+	h->peer.solo = false;
+	if(rc) return rc;
+	if(progress) progress(1.f, user);
+	return 0;
+}
+
+} // namespace bcdeng
+
+// buffers, per-level filter scratch, arena, events of the level pipelines for tile t (tile_count == 1: the whole frame)
+int peerPrepare(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth)
+{
 	int rc = checkParams(p);
 	if(rc) return rc;
 	if(hist_depth <= 0 || hist_depth > 255 || t->image_width <= 0 || t->sub_row1 <= t->sub_row0 || t->tile_count < 1 ||
@@ -379,7 +465,7 @@ int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	if(rc) return rc;
 	// everything a run may need is created now: allocations and stream creation synchronise with running kernels, and
 	// during a run a neighbouring tile's kernel may already be waiting for this tile
-	if((rc = prepareUpload(h, h->W, h->H, h->B))) return rc;
+	if(t->tile_count > 1 && (rc = prepareUpload(h, h->W, h->H, h->B))) return rc;
 	if((rc = reserveEvents(h, 1024))) return rc;
 	// per-level filter scratch: the levels are filtered side by side
 	const LevelGeom g0 = makeGeom(h->W, h->H, h->B, p->patch_radius, p->search_radius);
@@ -416,8 +502,22 @@ int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 		CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		P.evOut.push_back(e);
 	}
-	P.geomW = h->W; P.geomB = p->search_radius; P.geomWr = p->patch_radius; P.geomScales = p->nb_scales;
+	P.geomW = h->W; P.geomH = h->H; P.geomHist = h->B; P.geomB = p->search_radius; P.geomWr = p->patch_radius; P.geomScales = p->nb_scales;
 	P.enabled = true;
+	return 0;
+}
+
+extern "C"
+{
+
+int bcd_b200_tile_setup(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_tile* t, int hist_depth,
+		bcd_b200_peer_token* token_out)
+{
+	if(!h || !t || !token_out) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / tile / token");
+	int rc = peerPrepare(h, p, t, hist_depth);
+	if(rc) return rc;
+	bcd_b200_handle::Peer& P = h->peer;
+	const size_t bytes = P.arenaBytes;
 	// Warm-up: one pass over zeroed inputs without neighbours, plus empty launches of the exchange kernels. CUDA loads a
 	// kernel the first time it is used and that load waits for the device to go idle — in a real frame it would wait for
 	// this tile's kernels that are waiting for a neighbour whose host thread is stuck in the same way. After this pass
@@ -673,6 +773,13 @@ void workerLoop(Slot* s, uint64_t seen)
 int dispatch(bcd_b200_group* g, int job)
 {
 	for(int i = 0; i < g->nLocal; ++i) { g->slots[i]->rc = 0; g->slots[i]->err.clear(); }
+	if(g->nLocal == 1) // one tile in this process (one process per GPU): no thread hop, the caller drives it
+	{
+		g->job = job;
+		cudaSetDevice(g->slots[0]->device);
+		slotJob(*g->slots[0]);
+	}
+	else
 	{
 		std::unique_lock<std::mutex> lk(g->mu);
 		g->job = job;
@@ -764,10 +871,22 @@ void collectGroupStats(bcd_b200_group* g)
 		const bcd_b200_stats& s = g->slots[i]->h->stats;
 		g->stats.interior += s.interior; g->stats.strong += s.strong; g->stats.active += s.active; g->stats.full += s.full;
 		g->stats.fallback += s.fallback; g->stats.sum_n_full += s.sum_n_full; g->stats.kernel_launches += s.kernel_launches;
-		const bcd_b200_timings& t = g->slots[i]->h->timings;
+	}
+}
+
+// per-stage sums over the local tiles, resolved on demand (the event queries cost ~0.1 ms per tile)
+int collectGroupTimings(bcd_b200_group* g)
+{
+	memset(&g->timings, 0, sizeof(g->timings));
+	for(int i = 0; i < g->nLocal; ++i)
+	{
+		bcd_b200_timings t;
+		int rc = bcd_b200_get_timings(g->slots[i]->h, &t);
+		if(rc) return rc;
 		for(int k = 0; k < BCD_B200_STAGE_COUNT; ++k) g->timings.stage_ms[k] += t.stage_ms[k];
 		g->timings.total_ms = std::max(g->timings.total_ms, t.total_ms);
 	}
+	return 0;
 }
 
 } // namespace
@@ -1073,6 +1192,8 @@ int bcd_b200_group_get_stats(bcd_b200_group* g, bcd_b200_stats* s)
 int bcd_b200_group_get_timings(bcd_b200_group* g, bcd_b200_timings* t)
 {
 	if(!g || !t) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null group / output");
+	int rc = collectGroupTimings(g);
+	if(rc) return rc;
 	*t = g->timings;
 	return 0;
 }

@@ -118,6 +118,7 @@ struct bcd_b200_handle
 	std::vector<Span> spans;         // timed stage instances of the current run
 	int smCount = 148;               // multiprocessors of the device
 	bool trace = false;              // BCD_B200_TRACE=1 (read once at bcd_b200_create)
+	bool timingsPending = false;     // the last run's spans have not been resolved into `timings` yet
 	cudaEvent_t evTotal[2] = {nullptr, nullptr};
 	size_t eventsUsed = 0;
 	int launches = 0;
@@ -156,7 +157,7 @@ struct bcd_b200_handle
 		unsigned int* hostTimeouts = nullptr; // pinned read-back
 		cudaEvent_t evColor = nullptr;     // colour / covariance pyramid + per-pixel covariances of all levels ready
 		std::vector<cudaEvent_t> evOut;    // level k finalized and its halo rows received
-		int geomW = 0, geomB = 0, geomWr = 0, geomScales = 0; // geometry the arena was laid out for
+		int geomW = 0, geomH = 0, geomHist = 0, geomB = 0, geomWr = 0, geomScales = 0; // geometry the arena was laid out for
 	} peer;
 	bcd_b200_params runParams;
 };
@@ -170,6 +171,7 @@ bcdk::LevelGeom levelGeom(const bcd_b200_handle* h, int k, const bcd_b200_params
 void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1);
 cudaStream_t auxOf(bcd_b200_handle* h, int k);
 
+extern bool g_schedLevels;
 int checkParams(const bcd_b200_params* p);
 int checkImages(const bcd_b200_images* in);
 int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p);
@@ -180,12 +182,14 @@ int pyramidLevel(bcd_b200_handle* h, int k, int parts);
 int levelClear(bcd_b200_handle* h, int k, const bcd_b200_params& p);
 int levelPixelCov(bcd_b200_handle* h, int k, const bcd_b200_params& p);
 int levelSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p);
+int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p, int coarseLevels);
+int runLevelPipelines(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress_fn progress, void* user);
 int levelMerge(bcd_b200_handle* h, int k);
 int collectTimings(bcd_b200_handle* h);
 int stageBegin(bcd_b200_handle* h, int stage, cudaStream_t st);
 int stageEnd(bcd_b200_handle* h, cudaStream_t st);
 int takeEvent(bcd_b200_handle* h, int* idx);
-int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStream_t st, bool deviceCounts);
+int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStream_t st, bool deviceCounts, bool privateScratch);
 int levelMarkWait(bcd_b200_handle* h, int k);
 void addCounters(bcd_b200_handle* h, const bcdk::DeviceCounters& c);
 

@@ -108,10 +108,13 @@ struct SubSmem
 
 // outG (global, n x n) <- V f(L) V^T of the matrix whose lower triangle is in M (mode 0: f = max(0, l); mode 1:
 // f = 1/max(eps, l)). `commit` (per matrix): when false the matrix only keeps the warp in step and nothing is written.
-template <int G>
-__device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, bool commit, float* __restrict__ outG)
+// NC > 0: the matrix order is the compile-time constant NC (27 for patch radius 1: index arithmetic folds, the inner
+// loops unroll); NC = 0: run-time order nRt.
+template <int G, int NC>
+__device__ void eigFunctionSub(const SubSmem& S, int nRt, int mode, float eps, bool commit, float* __restrict__ outG)
 {
-	constexpr int RMAX = (32 + G - 1) / G;
+	constexpr int RMAX = ((NC > 0 ? NC : 32) + G - 1) / G;
+	const int n = NC > 0 ? NC : nRt;
 	float* M = S.M;
 	const int lid = threadIdx.x & (G - 1), sgrp = (threadIdx.x & 31) / G;
 	// ---- scale the lower triangle into [-1,1], clear the strict upper triangle
@@ -386,9 +389,10 @@ __device__ void eigFunctionSub(const SubSmem& S, int n, int mode, float eps, boo
 // A^-1 = X^T X is written to outG. Returns true per matrix when the factorisation exists and 1/||A^-1||_inf > 2 eps;
 // never breaks out early, so all matrices of the warp stay in step (a failed factorisation just computes garbage that
 // the caller replaces).
-template <int G>
-__device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps, float* __restrict__ outG, bool valid)
+template <int G, int NC>
+__device__ bool choleskyInverseSub(const SubSmem& S, int nRt, float eps, float* __restrict__ outG, bool valid)
 {
+	const int n = NC > 0 ? NC : nRt;
 	float* M = S.M;
 	const int lid = threadIdx.x & (G - 1);
 	bool ok = true;
@@ -459,12 +463,13 @@ __device__ bool choleskyInverseSub(const SubSmem& S, int n, float eps, float* __
 
 // A (in): the matrices; in a clamp launch A[slot] is overwritten with V max(0,L) V^T (its consumer, the apply kernel,
 // rewrites A anyway). MinvG (out): the clamped inverses.
-template <int G>
+template <int G, int NC>
 __global__ void __launch_bounds__(32, G == 16 ? 24 : 14)
 k_eig_chain_sub(float* __restrict__ A, float* __restrict__ MinvG, const float* __restrict__ noiseG, int count,
-		const int* __restrict__ countDev, int first, int n, int np, float eps, int doClamp)
+		const int* __restrict__ countDev, int first, int nRt, int np, float eps, int doClamp)
 {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
+	const int n = NC > 0 ? NC : nRt;
 	count = chunkCount(count, countDev, first);
 	constexpr int NM = 32 / G; // matrices per warp
 	const int sub = threadIdx.x / G, lid = threadIdx.x & (G - 1);
@@ -507,20 +512,21 @@ k_eig_chain_sub(float* __restrict__ A, float* __restrict__ MinvG, const float* _
 		};
 		if(doClamp)
 		{
-			eigFunctionSub<G>(S, n, 0, 0.f, valid, Aslot); // A[slot] <- V max(0,L) V^T
+			eigFunctionSub<G, NC>(S, n, 0, 0.f, valid, Aslot); // A[slot] <- V max(0,L) V^T
 			reloadWithNoise(true);
 		}
-		const bool okChol = choleskyInverseSub<G>(S, n, eps, outSlot, valid);
+		const bool okChol = choleskyInverseSub<G, NC>(S, n, eps, outSlot, valid);
 		if(!__all_sync(FULL, okChol)) // rare: the failed matrices of the warp take the reference's eigen path
 		{
 			reloadWithNoise(doClamp != 0);
-			eigFunctionSub<G>(S, n, 1, eps, valid && !okChol, outSlot);
+			eigFunctionSub<G, NC>(S, n, 1, eps, valid && !okChol, outSlot);
 		}
 	}
 }
 
 } // namespace
 
+bool g_eigGenericOrder = false; // BCD_B200_EIG_GENERIC=1: the run-time-order kernel also for d = 27 (A/B hook)
 int g_eigGroup = 16; // lanes per matrix for d <= 32 (BCD_B200_EIG_GROUP = 32 selects the one-warp-per-matrix kernel)
 
 cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, const int* countDev, int first,
@@ -532,16 +538,22 @@ cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int cou
 	const int resident = (group == 16 ? 24 : 14) * (smCount > 0 ? smCount : 148);
 	const int grid = std::min((count + nm - 1) / nm, 2 * resident);
 	cudaError_t err;
+#define LAUNCH_SUB(GV, NV) \
+	do { \
+		if((err = allowDynamicSmem((const void*)k_eig_chain_sub<GV, NV>, smem)) != cudaSuccess) return err; \
+		k_eig_chain_sub<GV, NV><<<grid, 32, smem, st>>>(A, Minv, noise, count, countDev, first, n, np, eps, doClamp); \
+	} while(0)
 	if(group == 16)
 	{
-		if((err = cudaFuncSetAttribute(k_eig_chain_sub<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-		k_eig_chain_sub<16><<<grid, 32, smem, st>>>(A, Minv, noise, count, countDev, first, n, np, eps, doClamp);
+		if(n == 27 && !g_eigGenericOrder) LAUNCH_SUB(16, 27);
+		else LAUNCH_SUB(16, 0);
 	}
 	else
 	{
-		if((err = cudaFuncSetAttribute(k_eig_chain_sub<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
-		k_eig_chain_sub<8><<<grid, 32, smem, st>>>(A, Minv, noise, count, countDev, first, n, np, eps, doClamp);
+		if(n == 27 && !g_eigGenericOrder) LAUNCH_SUB(8, 27);
+		else LAUNCH_SUB(8, 0);
 	}
+#undef LAUNCH_SUB
 	return cudaGetLastError();
 }
 

@@ -1022,9 +1022,9 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 	auto kStats = k_filter_stats<NT, DT>;
 	auto kA1 = k_filter_apply<NT, GS, 1, DT>;
 	auto kA2 = k_filter_apply<NT, GS, 2, DT>;
-	if((err = cudaFuncSetAttribute(kStats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smStats)) != cudaSuccess) return err;
-	if((err = cudaFuncSetAttribute(kA1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
-	if((err = cudaFuncSetAttribute(kA2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smApply)) != cudaSuccess) return err;
+	if((err = allowDynamicSmem((const void*)kStats, smStats)) != cudaSuccess) return err;
+	if((err = allowDynamicSmem((const void*)kA1, smApply)) != cudaSuccess) return err;
+	if((err = allowDynamicSmem((const void*)kA2, smApply)) != cudaSuccess) return err;
 
 	auto launchEig = [&](int doClamp) -> cudaError_t {
 		if(eigNT == 32 && g.d <= 32 && (g_eigGroup == 16 || g_eigGroup == 8))
@@ -1032,17 +1032,17 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 		const int eg = std::min(count, sms * 8);
 		if(eigNT == 32)
 		{
-			cudaFuncSetAttribute(k_eig_chain<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			allowDynamicSmem((const void*)k_eig_chain<32>, smEig);
 			k_eig_chain<32><<<eg, 32, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		else if(eigNT == 96)
 		{
-			cudaFuncSetAttribute(k_eig_chain<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			allowDynamicSmem((const void*)k_eig_chain<96>, smEig);
 			k_eig_chain<96><<<eg, 96, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		else
 		{
-			cudaFuncSetAttribute(k_eig_chain<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smEig);
+			allowDynamicSmem((const void*)k_eig_chain<160>, smEig);
 			k_eig_chain<160><<<eg, 160, smEig, st>>>(fb.A, fb.Minv, fb.noise, count, countDev, first, g.d, g.np, minEig, doClamp);
 		}
 		return cudaGetLastError();

@@ -945,7 +945,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 			const size_t smem = (size_t)((NWV) + 1) * sysPktStride(a.tEnd) * 16 + 16; \
 			if(smem <= 112 * 1024 && divUp(bands, NWV) <= 2 * 148) { \
 				auto kern = always ? k_marking_sys6<NWV, true> : k_marking_sys6<NWV, false>; \
-				if((err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+				if((err = allowDynamicSmem((const void*)kern, smem)) != cudaSuccess) return err; \
 				kern<<<divUp(bands, NWV), 32 * ((NWV) + 1), smem, st>>>(a); \
 				if((err = cudaGetLastError()) != cudaSuccess) return err; \
 				if(ringIn) { \
@@ -972,10 +972,10 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 	do { \
 		const size_t smem = (asWords + (size_t)2 * 32 * (8 * 4 * fastMarkWords(BT) + 4)) * 4; \
 		if(skipProb >= 1.f) { \
-			if((err = cudaFuncSetAttribute(k_marking_fast<BT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+			if((err = allowDynamicSmem((const void*)k_marking_fast<BT, true>, smem)) != cudaSuccess) return err; \
 			k_marking_fast<BT, true><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
 		} else { \
-			if((err = cudaFuncSetAttribute(k_marking_fast<BT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err; \
+			if((err = allowDynamicSmem((const void*)k_marking_fast<BT, false>, smem)) != cudaSuccess) return err; \
 			k_marking_fast<BT, false><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
 		} \
 	} while(0)
@@ -985,7 +985,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 	else
 	{
 		const size_t smem = ((size_t)(32 + g.b) * Wp + (size_t)2 * 32 * (32 * g.Pw + 1)) * 4;
-		if((err = cudaFuncSetAttribute(k_marking_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+		if((err = allowDynamicSmem((const void*)k_marking_generic<0>, smem)) != cudaSuccess) return err;
 		k_marking_generic<0><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress);
 	}
 #undef LAUNCH_FAST

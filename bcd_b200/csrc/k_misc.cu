@@ -9,9 +9,30 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace bcdk
 {
+
+cudaError_t allowDynamicSmem(const void* kernel, size_t bytes)
+{
+	static std::mutex mu;
+	static std::map<std::pair<int, const void*>, size_t> granted; // (device, kernel) -> current limit
+	if(bytes <= 48 * 1024)
+		return cudaSuccess; // always allowed
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if(e != cudaSuccess) return e;
+	std::lock_guard<std::mutex> lk(mu);
+	size_t& cur = granted[std::make_pair(dev, kernel)];
+	if(bytes <= cur)
+		return cudaSuccess;
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+	if(e == cudaSuccess) cur = bytes;
+	return e;
+}
 
 __global__ void k_pixel_cov(const float* __restrict__ cov, const float* __restrict__ ns, size_t npix,
 		float* __restrict__ pixcov)

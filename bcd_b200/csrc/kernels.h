@@ -13,6 +13,11 @@ struct DeviceCounters
 	unsigned int markTimeouts, pad_; // bounded waits of the marking kernel that expired (must stay 0)
 };
 
+// Raises cudaFuncAttributeMaxDynamicSharedMemorySize of `kernel` on the current device to at least `bytes` — never lowers
+// it, and serialises the callers: several host threads (one per row tile) launch the same kernels with different
+// shared-memory sizes, and a plain cudaFuncSetAttribute before every launch lets one thread shrink the limit between
+// another thread's attribute call and its launch ("too many resources requested for launch").
+cudaError_t allowDynamicSmem(const void* kernel, size_t bytes);
 // K0  Denoiser::computePixelCovFromSampleCov
 cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches);
 // K1a/b/c
@@ -33,6 +38,7 @@ extern int g_markingKernel; // b = 6: 1 = systolic kernel (default), 0 = shared-
 // K3e for d <= 32: lanes per matrix (16 or 8: several matrices per warp, k_eig_sub.cu; 32: one warp per matrix). Test hook
 // BCD_B200_EIG_GROUP.
 extern int g_eigGroup;
+extern bool g_eigGenericOrder;
 cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int count, const int* countDev, int first,
 		int n, int np, float eps, int doClamp, int group, int smCount, cudaStream_t st);
 int markingPreLayout(int b); // what k_symmetrize must write: 0 generic, 1 `pre2` row-major, 2 `pre2` band-major (systolic kernel)

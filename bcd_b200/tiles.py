@@ -405,11 +405,7 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(a.steps):
-            fn()
-            st, tm = stats_timings()
-            for k, v in tm.items():
-                stage_acc[k] = stage_acc.get(k, 0.0) + v
-            launches += st["kernel_launches"]
+            fn()  # nothing but the step itself inside the timed region
         torch.cuda.synchronize()
         e1.record(stream)
         torch.cuda.synchronize()
@@ -418,6 +414,14 @@ def bench_tiled(a, rank, world, local_rank, W, H, config, workload, dist, saved_
         clocks = sampler.stop()
         ms = torch.tensor([ms_local], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # per-stage device times and launch counts from extra, untimed steps (every rank runs them: the tiles are coupled)
+        probes = 3
+        for _ in range(probes):
+            fn()
+            st, tm = stats_timings()
+            for k, v in tm.items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v * a.steps / probes
+            launches = st["kernel_launches"] * a.steps
         ln = torch.tensor([float(launches)], device=dev)
         dist.all_reduce(ln, op=dist.ReduceOp.SUM)
         return float(ms.item()), stage_acc, int(ln.item()), clocks

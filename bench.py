@@ -363,18 +363,23 @@ def main():
         sampler = ClockSampler(local_rank, gpu_uuid(local_rank))
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage_acc, launches = {}, 0
         torch.cuda.synchronize()
         e0.record(stream)
         for _ in range(a.steps):
-            fn()
-            for k, v in h.timings().items():
-                stage_acc[k] = stage_acc.get(k, 0.0) + v
-            launches += h.stats()["kernel_launches"]
+            fn()  # nothing but the step itself inside the timed region
         e1.record(stream)
         torch.cuda.synchronize()
         clocks = sampler.stop()
-        return e0.elapsed_time(e1), stage_acc, launches, clocks
+        ms = e0.elapsed_time(e1)
+        # per-stage device times and the launch count: sampled on extra, untimed steps (resolving the stage events costs
+        # host time that does not belong to a step)
+        stage_acc, launches, probes = {}, 0, 3
+        for _ in range(probes):
+            fn()
+            for k, v in h.timings().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v * a.steps / probes
+            launches = h.stats()["kernel_launches"] * a.steps
+        return ms, stage_acc, launches, clocks
 
     ms_res, stages, launches, clocks = timed(step_resident, True)
     stats = h.stats()
