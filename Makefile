@@ -56,8 +56,19 @@ oracle/_ref/ref_raw2bcd: $(REF)/src/raw_converter/main.cpp bcd_b200/libbcdcore_b
 	@mkdir -p oracle/_ref
 	$(CXX) -std=c++11 -O2 -w -include cmath $(HOSTINC) -o $@ $< -Lbcd_b200 -lbcdcore_b200 -lbcd_b200 -Wl,-rpath,'$$ORIGIN/../../bcd_b200'
 
+# Guard of the bit-exact pair-term kernel (k_distance.cu): the reference rounds ny*b1 and nx*b2 separately and divides with
+# IEEE division. ptxas must therefore (a) keep the packed products as FMUL2 / FFMA2-with-zero-addend instead of contracting
+# them into the following subtraction, (b) keep div.rn's refinement (5 packed FMA-pipe steps behind the two MUFU.RCP of the
+# negated denominators) and (c) use the FSET masks of the contribution test. Counts below are those of the walk loops.
+check-sass: $(CSRC)/k_distance.o
+	@cuobjdump -sass -fun '_ZN4bcdk19k_pair_terms_sparseILi32ELi4ELi4ELi2EEEvPKfS2_NS_9LevelGeomEPfPh' $< > /tmp/bcd_b200_k1a.sass
+	@n_rcpneg=$$(grep -c "MUFU.RCP R[0-9]*, -R" /tmp/bcd_b200_k1a.sass); n_fset=$$(grep -c "FSET.BF.GTU" /tmp/bcd_b200_k1a.sass); \
+	 n_fmul2=$$(grep -c "FMUL2" /tmp/bcd_b200_k1a.sass); n_ffma2=$$(grep -c "FFMA2" /tmp/bcd_b200_k1a.sass); \
+	 echo "k_pair_terms_sparse<32,4,4,2>: MUFU.RCP(-x) $$n_rcpneg, FSET.BF.GTU $$n_fset, FMUL2 $$n_fmul2, FFMA2 $$n_ffma2"; \
+	 test $$n_rcpneg -ge 8 && test $$n_fset -ge 8 && test $$n_fmul2 -ge 8 && test $$n_ffma2 -ge 20 || (echo "check-sass: unexpected code shape in the pair-term walk" && exit 1)
+
 clean:
 	rm -f $(CSRC)/*.o $(CSRC)/*.log bcd_b200/*.so bin/bcd_cli bin/raw2bcd
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle ref_frontends clean
+.PHONY: all oracle ref_frontends clean check-sass
