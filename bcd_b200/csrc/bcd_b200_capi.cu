@@ -881,7 +881,7 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX, &h->peer.tickets};
 	for(DevBuf* b : bufs) b->release();
 	for(int side = 0; side < 2; ++side)
-		if(h->peer.nb[side] && h->peer.nbIpc[side]) cudaIpcCloseMemHandle(h->peer.nb[side]);
+		releaseNeighbourArena(h, side);
 	h->peer.arena.release();
 	if(h->peer.hostTimeouts) cudaFreeHost(h->peer.hostTimeouts);
 	if(h->peer.evColor) cudaEventDestroy(h->peer.evColor);

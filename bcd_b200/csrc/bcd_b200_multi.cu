@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <chrono>
 #include <thread>
 #include <unistd.h>
@@ -82,10 +84,51 @@ void applyTile(bcd_b200_handle* h, const bcd_b200_params& p, const bcd_b200_tile
 	h->runParams = p;
 }
 
+// Arenas of other processes mapped into this one. An IPC handle can be opened once per process and device, but with
+// several tiles per GPU two local tiles are neighbours of the same remote tile (tile j + 1 lies between the local tiles j
+// and j + 2 when the box is split over two processes): the mapping is shared and reference-counted.
+struct IpcMapping { void* ptr; int refs; };
+std::mutex g_ipcMutex;
+std::map<std::tuple<int, int64_t, uint64_t>, IpcMapping> g_ipcMappings; // (local device, exporting pid, address there)
+
+cudaError_t openArena(int device, const Token& tok, void** out)
+{
+	std::lock_guard<std::mutex> lk(g_ipcMutex);
+	const auto key = std::make_tuple(device, tok.pid, tok.ptr);
+	auto it = g_ipcMappings.find(key);
+	if(it != g_ipcMappings.end())
+	{
+		++it->second.refs;
+		*out = it->second.ptr;
+		return cudaSuccess;
+	}
+	void* ptr = nullptr;
+	cudaError_t e = cudaIpcOpenMemHandle(&ptr, tok.ipc, cudaIpcMemLazyEnablePeerAccess);
+	if(e != cudaSuccess) { cudaGetLastError(); return e; }
+	g_ipcMappings[key] = IpcMapping{ptr, 1};
+	*out = ptr;
+	return cudaSuccess;
+}
+
+void closeArena(void* ptr)
+{
+	std::lock_guard<std::mutex> lk(g_ipcMutex);
+	for(auto it = g_ipcMappings.begin(); it != g_ipcMappings.end(); ++it)
+		if(it->second.ptr == ptr)
+		{
+			if(--it->second.refs == 0)
+			{
+				cudaIpcCloseMemHandle(ptr);
+				g_ipcMappings.erase(it);
+			}
+			return;
+		}
+}
+
 void closeNeighbour(bcd_b200_handle* h, int side)
 {
 	if(h->peer.nb[side] && h->peer.nbIpc[side])
-		cudaIpcCloseMemHandle(h->peer.nb[side]);
+		closeArena(h->peer.nb[side]);
 	h->peer.nb[side] = nullptr;
 	h->peer.nbIpc[side] = false;
 }
@@ -413,6 +456,8 @@ int peerPrepare(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_til
 namespace bcdeng
 {
 
+void releaseNeighbourArena(bcd_b200_handle* h, int side) { closeNeighbour(h, side); }
+
 // bcd_b200_run in its "levels" schedule: the whole frame as one tile without neighbours
 int runLevelPipelines(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress_fn progress, void* user)
 {
@@ -599,10 +644,9 @@ int bcd_b200_tile_connect(bcd_b200_handle* h, int side, const bcd_b200_peer_toke
 	else
 	{
 		void* ptr = nullptr;
-		cudaError_t e = cudaIpcOpenMemHandle(&ptr, tok.ipc, cudaIpcMemLazyEnablePeerAccess);
+		cudaError_t e = openArena(h->device, tok, &ptr);
 		if(e != cudaSuccess)
 		{
-			cudaGetLastError();
 			return fail(BCD_B200_ERR_CUDA, "cudaIpcOpenMemHandle (arena of device %d, pid %lld) failed: %s", tok.device, (long long)tok.pid,
 					cudaGetErrorString(e));
 		}
@@ -844,10 +888,11 @@ int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::
 	int T = g->tilesPerGpu;
 	if(T <= 0)
 	{
-		// default: bands of at least ~48 level-0 rows per scale step, at most 4 per GPU (measured: profiles/r02_scaling.md)
-		const int minRows = 48 << (p.nb_scales > 1 ? 1 : 0);
-		T = std::max(1, std::min(4, H / std::max(1, G * minRows)));
-		if(G == 1) T = 1;
+		// Several tiles per GPU pay when the marking chain (one dependency through all rows, ~1 us per 1080p-wide row)
+		// weighs as much as a GPU's share of the selection — many GPUs, tall frames — and the tiles stay large enough
+		// for their kernels to fill a GPU: bands of at least 256 rows, at most 4 per GPU, only from 4 GPUs on
+		// (measured on 8 B200: profiles/r02_scaling.md; 1080p always gets one band per GPU).
+		T = G >= 4 ? std::max(1, std::min(4, H / std::max(1, G * 256))) : 1;
 	}
 	for(int tiles = G * T; tiles > 1; tiles = tiles > G ? tiles - G : tiles - 1)
 	{

@@ -172,6 +172,7 @@ void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1);
 cudaStream_t auxOf(bcd_b200_handle* h, int k);
 
 extern bool g_schedLevels;
+void releaseNeighbourArena(bcd_b200_handle* h, int side); // bcd_b200_multi.cu: unmaps (reference-counted) the neighbour's arena
 int checkParams(const bcd_b200_params* p);
 int checkImages(const bcd_b200_images* in);
 int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p);
