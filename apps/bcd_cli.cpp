@@ -23,6 +23,7 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <vector>
 
 using namespace std;
 using namespace bcd;
@@ -46,6 +47,8 @@ namespace
 		int m_nbOfCores = 0;
 		bool m_useCuda = true;
 		int m_device = 0;
+		int m_nbOfGpus = 1;          // --gpus: devices m_device .. m_device + n - 1 (0 = every visible GPU)
+		bool m_spikeFloatAbs = false; // --spike-float-abs: the float reading of the reference's abs() in the spike prefilter
 	};
 
 	void printUsage()
@@ -73,6 +76,8 @@ namespace
 		cout << "    --use-cuda <0/1>     Accepted for compatibility (the B200 path is CUDA-only)" << endl;
 		cout << "    -e <float>           Minimum eigen value for matrix inversion (default: " << d.m_minEigenValue << ")" << endl;
 		cout << "    --device <int>       CUDA device index (default: " << d.m_device << ")" << endl;
+		cout << "    --gpus <int>         Number of GPUs the frame is spread over, starting at --device; 0 = all visible (default: " << d.m_nbOfGpus << ")" << endl;
+		cout << "    --spike-float-abs <0/1>  1: spike prefilter compares |colour - mean| as a float (MSVC builds of bcd-cli); 0: truncated to an integer like the GCC build (default: 0)" << endl;
 	}
 
 	template <typename T> bool parseValue(const char* text, T& out)
@@ -104,7 +109,8 @@ namespace
 			{"-b", "radius of search window"}, {"-w", "radius of patch"}, {"-e", "minimum eigen value"},
 			{"-r", "0 or 1"}, {"-p", "0 or 1"}, {"--p-factor", "standard deviation factor for spike prefiltering threshold"},
 			{"-m", "float in [0,1]"}, {"-s", "number of scales"}, {"--ncores", "number of cores for OpenMP"},
-			{"--use-cuda", "0 or 1"}, {"--device", "CUDA device index"}};
+			{"--use-cuda", "0 or 1"}, {"--device", "CUDA device index"}, {"--gpus", "number of GPUs"},
+			{"--spike-float-abs", "0 or 1"}};
 		for(int i = 1; i < argc; ++i)
 		{
 			const string opt = argv[i];
@@ -191,6 +197,8 @@ namespace
 			else if(opt == "--ncores") parseValue(v, a.m_nbOfCores);
 			else if(opt == "--use-cuda") { if(!parse01("--use-cuda", v, a.m_useCuda)) return false; }
 			else if(opt == "--device") parseValue(v, a.m_device);
+			else if(opt == "--gpus") parseValue(v, a.m_nbOfGpus);
+			else if(opt == "--spike-float-abs") { if(!parse01("--spike-float-abs", v, a.m_spikeFloatAbs)) return false; }
 		}
 		// the histogram and covariance files default to <colour>_hist.exr / <colour>_cov.exr (main.cpp:345-371)
 		if(!a.m_color.empty() && a.m_color.size() > 4)
@@ -265,6 +273,7 @@ namespace
 		}
 
 		SpikeRemovalFilter::s_device = a.m_device;
+		SpikeRemovalFilter::s_useIntegerAbsLikeGccBuild = !a.m_spikeFloatAbs;
 		if(a.m_prefilterSpikes)
 		{
 			SpikeRemovalFilter::filter(color, nbOfSamples, histogram, covariance, a.m_prefilterFactor);
@@ -294,7 +303,16 @@ namespace
 		parameters.m_useCuda = a.m_useCuda;
 
 		unique_ptr<Denoiser> denoiser(a.m_nbOfScales > 1 ? new MultiscaleDenoiser(a.m_nbOfScales) : new Denoiser());
-		denoiser->setDevice(a.m_device);
+		if(a.m_nbOfGpus == 1)
+			denoiser->setDevice(a.m_device);
+		else if(a.m_nbOfGpus <= 0)
+			denoiser->setDevices(nullptr, 0); // every visible GPU
+		else
+		{
+			std::vector<int> ids;
+			for(int i = 0; i < a.m_nbOfGpus; ++i) ids.push_back(a.m_device + i);
+			denoiser->setDevices(ids.data(), int(ids.size()));
+		}
 		denoiser->setInputs(inputs);
 		denoiser->setOutputs(outputs);
 		denoiser->setParameters(parameters);
