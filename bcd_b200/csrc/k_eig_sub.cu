@@ -535,7 +535,7 @@ cudaError_t launchEigChainSub(float* A, float* Minv, const float* noise, int cou
 	const int nm = 32 / group;
 	const size_t smem = (size_t)nm * (n * n + 7 * n + np * 6) * 4;
 	// persistent warps (slot loop): two waves of the resident CTAs at most
-	const int resident = (group == 16 ? 24 : 14) * (smCount > 0 ? smCount : 148);
+	const int resident = (group == 16 ? 24 : 14) * (smCount > 0 ? smCount : currentSmCount());
 	const int grid = std::min((count + nm - 1) / nm, 2 * resident);
 	cudaError_t err;
 #define LAUNCH_SUB(GV, NV) \

@@ -203,7 +203,7 @@ k_fallback(const float* __restrict__ color, const uint32_t* __restrict__ smask, 
 cudaError_t launchFallback(const float* color, const uint32_t* smask, const int* counts, const LevelGeom& g,
 		const int* fallbackList, const int* nFallback, float4* acc, cudaStream_t st, int* launches)
 {
-	const int blocks = 148 * 16;
+	const int blocks = currentSmCount() * 16;
 	*launches += 1;
 	if(g.d <= 32)
 		k_fallback<1><<<blocks, 128, 0, st>>>(color, smask, counts, g, fallbackList, nFallback, acc);
@@ -1013,7 +1013,7 @@ static cudaError_t runFilterChunk(const float* color, const float* pixcov, const
 	if(!xInSmem && !fb.xScratch)
 		return cudaErrorInvalidConfiguration;
 	float* xs = xInSmem ? nullptr : fb.xScratch;
-	const int sms = fb.smCount > 0 ? fb.smCount : 148;
+	const int sms = fb.smCount > 0 ? fb.smCount : currentSmCount();
 	const int grid = std::min(count, xInSmem ? sms * 16 : fb.gridCap);
 	const size_t smStats = filterSmemBytes(g, xInSmem, false, 0);
 	const size_t smApply = filterSmemBytes(g, xInSmem, true, NT / GS);

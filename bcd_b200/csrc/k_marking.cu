@@ -47,9 +47,29 @@ __device__ __forceinline__ uint32_t extractBits(const uint32_t* w, int off, int 
 }
 
 // Generic kernel (any radius b <= 15): one pixel per lane-step.
+// A band waits for the progress word of the band above. CUDA does not promise that CTAs start in blockIdx order, so the
+// wait is bounded in time like the systolic kernel's: on expiry the band counts a time-out (the run then fails with an
+// error instead of hanging the GPU) and goes on with whatever it has.
+__device__ __forceinline__ void boundedProgressWait(const volatile unsigned int* prevProgress, unsigned int needCols, unsigned int ns,
+		unsigned int* timeouts)
+{
+	if(*prevProgress >= needCols)
+		return;
+	const long long t0 = clock64();
+	while(*prevProgress < needCols)
+	{
+		if(clock64() - t0 > (1ll << 33)) // ~4 s
+		{
+			if(timeouts) atomicAdd(timeouts, 1u);
+			return;
+		}
+		__nanosleep(ns);
+	}
+}
+
 template <int BT>
 __global__ void __launch_bounds__(32)
-k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
+k_marking_generic(unsigned int* timeouts, const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
 		uint32_t* __restrict__ actBits, uint32_t* asBits, int Wp, unsigned int* progress)
 {
 	extern __shared__ uint32_t smem[];
@@ -115,7 +135,7 @@ k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, f
 			const int needWords = min(Wp, ((t + 31 + b + MARK_PAD) >> 5) + 1);
 			const unsigned int needCols = (unsigned int)min(W, (needWords << 5) - MARK_PAD);
 			if(band > 0 && lane == 0) // band 0 reads rows the host prepared (zeros, or the upper row tile's hand-off)
-				while(*prevProgress < needCols) { __nanosleep(100); }
+				boundedProgressWait(prevProgress, needCols, 100, timeouts);
 			__syncwarp();
 			if(needWords > copiedWords)
 			{
@@ -213,7 +233,7 @@ k_marking_generic(const uint32_t* __restrict__ pre, int prePitch, LevelGeom g, f
 // ---------------------------------------------------------------------------------------------------------------
 template <int BT, bool ALWAYS>
 __global__ void __launch_bounds__(32)
-k_marking_fast(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
+k_marking_fast(unsigned int* timeouts, const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, float skipProb, uint32_t seed,
 		uint32_t* __restrict__ actBits, uint32_t* asBits, int Wp, unsigned int* progress)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -302,7 +322,7 @@ k_marking_fast(const uint32_t* __restrict__ pre2, int prePitch, LevelGeom g, flo
 			{
 				const unsigned int needCols = (unsigned int)min(W, (needWords << 5) - MARK_PAD);
 				if(band > 0 && lane == 0)
-					while(*prevProgress < needCols) { __nanosleep(32); }
+					boundedProgressWait(prevProgress, needCols, 32, timeouts);
 				__syncwarp();
 				__threadfence();
 				const int nw = needWords - copiedWords;
@@ -891,7 +911,7 @@ static int sysBandsPerCta(const LevelGeom& g)
 		if(nw > 1 && g_markingBandsPerCta < nw)
 			continue;
 		const size_t smem = (size_t)(nw + 1) * sysPktStride(tEnd) * 16 + 16;
-		if(smem <= 112 * 1024 && divUp(bands, nw) <= 2 * 148)
+		if(smem <= 112 * 1024 && divUp(bands, nw) <= 2 * currentSmCount())
 			return nw;
 	}
 	return 0;
@@ -943,7 +963,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 #define LAUNCH_SYS(NWV) \
 		do { \
 			const size_t smem = (size_t)((NWV) + 1) * sysPktStride(a.tEnd) * 16 + 16; \
-			if(smem <= 112 * 1024 && divUp(bands, NWV) <= 2 * 148) { \
+			if(smem <= 112 * 1024 && divUp(bands, NWV) <= 2 * currentSmCount()) { \
 				auto kern = always ? k_marking_sys6<NWV, true> : k_marking_sys6<NWV, false>; \
 				if((err = allowDynamicSmem((const void*)kern, smem)) != cudaSuccess) return err; \
 				kern<<<divUp(bands, NWV), 32 * ((NWV) + 1), smem, st>>>(a); \
@@ -973,10 +993,10 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 		const size_t smem = (asWords + (size_t)2 * 32 * (8 * 4 * fastMarkWords(BT) + 4)) * 4; \
 		if(skipProb >= 1.f) { \
 			if((err = allowDynamicSmem((const void*)k_marking_fast<BT, true>, smem)) != cudaSuccess) return err; \
-			k_marking_fast<BT, true><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
+			k_marking_fast<BT, true><<<bands, 32, smem, st>>>(timeouts, pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
 		} else { \
 			if((err = allowDynamicSmem((const void*)k_marking_fast<BT, false>, smem)) != cudaSuccess) return err; \
-			k_marking_fast<BT, false><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
+			k_marking_fast<BT, false><<<bands, 32, smem, st>>>(timeouts, pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress); \
 		} \
 	} while(0)
 	if(g.b == 6 && !g_forceGenericMarking) LAUNCH_FAST(6);
@@ -986,7 +1006,7 @@ cudaError_t launchMarking(const uint32_t* pre, int prePitch, const LevelGeom& g,
 	{
 		const size_t smem = ((size_t)(32 + g.b) * Wp + (size_t)2 * 32 * (32 * g.Pw + 1)) * 4;
 		if((err = allowDynamicSmem((const void*)k_marking_generic<0>, smem)) != cudaSuccess) return err;
-		k_marking_generic<0><<<bands, 32, smem, st>>>(pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress);
+		k_marking_generic<0><<<bands, 32, smem, st>>>(timeouts, pre, prePitch, g, skipProb, seed, actBits, asBits, Wp, progress);
 	}
 #undef LAUNCH_FAST
 	return cudaGetLastError();

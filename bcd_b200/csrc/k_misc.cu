@@ -16,6 +16,22 @@
 namespace bcdk
 {
 
+int currentSmCount()
+{
+	static int cached[64] = {0};
+	int dev = 0;
+	if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+		return 148;
+	if(cached[dev] == 0)
+	{
+		int sms = 0;
+		if(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+			sms = 148;
+		cached[dev] = sms;
+	}
+	return cached[dev];
+}
+
 cudaError_t allowDynamicSmem(const void* kernel, size_t bytes)
 {
 	static std::mutex mu;

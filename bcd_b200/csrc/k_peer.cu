@@ -73,7 +73,7 @@ k_recv(T* __restrict__ dst, const T* slot, size_t n, const uint32_t* flag, uint3
 	}
 }
 
-int gridFor(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148); }
+int gridFor(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)currentSmCount()); }
 
 } // namespace
 

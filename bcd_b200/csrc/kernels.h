@@ -18,6 +18,8 @@ struct DeviceCounters
 // shared-memory sizes, and a plain cudaFuncSetAttribute before every launch lets one thread shrink the limit between
 // another thread's attribute call and its launch ("too many resources requested for launch").
 cudaError_t allowDynamicSmem(const void* kernel, size_t bytes);
+// multiprocessors of the current device (cached; 148 on a B200): persistent grids and residency tests are sized from it
+int currentSmCount();
 // K0  Denoiser::computePixelCovFromSampleCov
 cudaError_t launchPixelCov(const float* cov, const float* ns, size_t npix, float* pixcov, cudaStream_t st, int* launches);
 // K1a/b/c

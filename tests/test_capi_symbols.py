@@ -65,3 +65,31 @@ def test_fails_loudly_without_device_or_bad_args():
     out = np.zeros(48, np.float32)
     rc = L.bcd_b200_denoise(ctypes.byref(img), ctypes.byref(p), out.ctypes.data, 0, None, None)
     assert rc == -1 and b"nullptr for input color image" in L.bcd_b200_last_error()
+
+
+def test_group_api_fails_loudly_without_device_and_plans_on_the_host():
+    """The multi-GPU entry points: no device -> BCD_B200_ERR_NO_DEVICE (there is no CPU path), bad arguments are refused
+    before any device work, and the tile plan (pure host arithmetic) is consistent with what a group would cut."""
+    import pytest
+    from bcd_b200 import capi, tiles
+    L = capi.lib()
+    if L.bcd_b200_device_count() == 0:
+        with pytest.raises(capi.BcdError) as e:
+            capi.Group([0, 1])
+        assert e.value.code == -3 and "no CPU path" in str(e.value)
+        import numpy as np
+        z = np.zeros((8, 8, 3), np.float32)
+        with pytest.raises(capi.BcdError) as e:
+            capi.denoise_multi(z, np.zeros((8, 8, 1), np.float32), np.zeros((8, 8, 60), np.float32), np.zeros((8, 8, 6), np.float32),
+                               devices=[0, 0])
+        assert e.value.code == -3
+    p = capi.make_params(scales=3)
+    # a null group / a ranked group with a bad rank never touch a device
+    assert L.bcd_b200_group_denoise(None, None, ctypes.byref(p), None, None, None) == -1
+    g = ctypes.c_void_p()
+    ids = (ctypes.c_int32 * 1)(0)
+    assert L.bcd_b200_group_create_ranked(ctypes.byref(g), ids, 1, 3, 2) in (-1, -3)
+    # 8 tiles of a 1080p frame at 3 scales: bands on multiples of 4 rows, 28 halo rows, cyclic owners are the caller's business
+    ts = [tiles.plan(1920, 1080, i, 8, p) for i in range(8)]
+    assert [t.own_row1 - t.own_row0 for t in ts] == [132, 136, 136, 136, 132, 136, 136, 136]
+    assert all(t.sub_row0 == max(0, t.own_row0 - 28) and t.sub_row1 == min(1080, t.own_row1 + 28) for t in ts)
