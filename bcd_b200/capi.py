@@ -28,6 +28,7 @@ SYMBOLS = [
     "bcd_b200_tile_plan", "bcd_b200_tile_begin", "bcd_b200_tile_select", "bcd_b200_tile_mark", "bcd_b200_tile_filter",
     "bcd_b200_tile_finalize", "bcd_b200_tile_merge", "bcd_b200_tile_xfer_bytes", "bcd_b200_tile_export",
     "bcd_b200_tile_import", "bcd_b200_tile_end", "bcd_b200_tile_download",
+    "bcd_b200_accumulate_samples",
     # peer mode of the row tiles + the group API (bcd_b200_multi.cu)
     "bcd_b200_tile_setup", "bcd_b200_tile_connect", "bcd_b200_tile_run",
     "bcd_b200_group_create", "bcd_b200_group_destroy", "bcd_b200_group_set_pinning", "bcd_b200_group_denoise",
@@ -103,6 +104,8 @@ def lib():
         L.bcd_b200_download_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.bcd_b200_spike_removal_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                   C.c_float, C.c_int, C.c_int]
+        L.bcd_b200_accumulate_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                  C.c_float, C.c_float]
         L.bcd_b200_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int]
         L.bcd_b200_group_destroy.argtypes = [C.c_void_p]
         L.bcd_b200_group_destroy.restype = None
@@ -332,6 +335,20 @@ class Handle:
         p = C.c_void_p()
         _check(lib().bcd_b200_result_device_ptr(self._h, C.byref(p)))
         return p.value
+
+    def accumulate_samples(self, samples, weights=None, nb_bins=20, gamma=2.2, max_value=2.5, device_ptrs=None):
+        """bcd_b200_accumulate_samples: (H, W, spp, 3) host samples (or device_ptrs=(samples_ptr, weights_ptr|0, H, W, spp))
+        -> the handle's resident inputs (SamplesAccumulator on the GPU)."""
+        if device_ptrs is not None:
+            sp, wp, H, W, spp = device_ptrs
+            _check(lib().bcd_b200_accumulate_samples(self._h, C.c_void_p(sp), C.c_void_p(wp) if wp else None, 1, W, H, spp, nb_bins, gamma, max_value))
+        else:
+            samples = np.ascontiguousarray(samples, np.float32)
+            H, W, spp, _ = samples.shape
+            wts = np.ascontiguousarray(weights, np.float32) if weights is not None else None
+            _check(lib().bcd_b200_accumulate_samples(self._h, samples.ctypes.data, wts.ctypes.data if wts is not None else None, 0,
+                                                     W, H, spp, nb_bins, gamma, max_value))
+        self.shape = (H, W, 3 * nb_bins)
 
     def spike_removal(self, factor=2.0, int_abs=True):
         """SpikeRemovalFilter on the resident (uploaded) inputs; they stay resident for the next run."""

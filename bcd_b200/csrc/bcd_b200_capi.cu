@@ -1415,6 +1415,48 @@ int bcd_b200_spike_removal(bcd_b200_handle* h, float threshold_std_factor, int i
 	return 0;
 }
 
+int bcd_b200_accumulate_samples(bcd_b200_handle* h, const float* samples, const float* weights, int samples_on_device,
+		int32_t width, int32_t height, int32_t spp, int32_t nb_bins, float gamma, float max_value)
+{
+	if(!h || !samples) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle / samples");
+	if(width <= 0 || height <= 0 || spp <= 0 || nb_bins < 2 || 3 * nb_bins > 255)
+		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "bad sample block (%dx%d, %d spp, %d bins)", width, height, spp, nb_bins);
+	CU(cudaSetDevice(h->device));
+	{ int rcu = finishUpload(h); if(rcu) return rcu; }
+	CU(cudaStreamSynchronize(h->stream));
+	const int B = 3 * nb_bins;
+	int rc = prepareUpload(h, width, height, B); // storage of the level-0 inputs
+	if(rc) return rc;
+	LevelBufs& L = h->levels[0];
+	const size_t np = (size_t)width * height;
+	DevBuf stage, stageW; // host samples are copied into a temporary device block
+	const float *dS = samples, *dW = weights;
+	if(!samples_on_device)
+	{
+		CU(stage.reserve(np * spp * 3 * sizeof(float)));
+		CU(cudaMemcpyAsync(stage.p, samples, np * spp * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+		dS = stage.as<float>();
+		if(weights)
+		{
+			CU(stageW.reserve(np * spp * sizeof(float)));
+			CU(cudaMemcpyAsync(stageW.p, weights, np * spp * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+			dW = stageW.as<float>();
+		}
+	}
+	cudaError_t e = launchAccumulateSamples(dS, dW, np, spp, nb_bins, gamma, max_value, L.ownColor.as<float>(), L.ownNs.as<float>(),
+			L.ownHist.as<float>(), L.ownCov.as<float>(), h->stream, &h->launches);
+	cudaError_t e2 = cudaStreamSynchronize(h->stream);
+	stage.release();
+	stageW.release();
+	if(e != cudaSuccess || e2 != cudaSuccess)
+		return fail(BCD_B200_ERR_CUDA, "sample accumulation failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+	L.color = L.ownColor.as<float>(); L.ns = L.ownNs.as<float>(); L.hist = L.ownHist.as<float>(); L.cov = L.ownCov.as<float>();
+	h->W = width; h->H = height; h->B = B;
+	h->haveInputs = true;
+	h->ran = false;
+	return 0;
+}
+
 int bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples, float* hist, float* cov)
 {
 	if(!h) return fail(BCD_B200_ERR_INVALID_ARGUMENT, "null handle");

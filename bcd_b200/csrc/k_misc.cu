@@ -163,6 +163,103 @@ cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStrea
 	return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// (device side) SamplesAccumulator::addSample + computeSampleStatistics —
+// src/core/SamplesAccumulator.cpp:44-107,110-141 — for a renderer whose samples already live on the GPU: one thread per
+// pixel walks its samples in order (the reference's accumulation order, separate multiply and add: this file is built
+// with --fmad=false), so mean, sample count and covariance are the reference's numbers bit for bit; the histogram goes
+// through powf (gamma), which differs from glibc's in the last place for some inputs — a 1e-7 shift of weight between
+// two neighbouring bins. The per-thread histogram lives in shared memory ([bin][thread]: conflict-free).
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_accumulate_samples(const float* __restrict__ samples, const float* __restrict__ weights, size_t npix, int spp, int nbBins,
+		float gamma, float maxValue, float* __restrict__ color, float* __restrict__ ns, float* __restrict__ hist, float* __restrict__ cov)
+{
+	extern __shared__ float shHist[]; // [3 * nbBins][NT]
+	const int tid = threadIdx.x;
+	const size_t p = (size_t)blockIdx.x * NT + tid;
+	const int B = 3 * nbBins;
+	for(int k = 0; k < B; ++k)
+		shHist[k * NT + tid] = 0.f;
+	if(p >= npix)
+		return;
+	const float saturation = 2.f;
+	const float invGamma = __fdiv_rn(1.f, gamma);
+	float wSum = 0.f, w2Sum = 0.f, sum[3] = {0.f, 0.f, 0.f}, c2[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+	const float* sp = samples + p * (size_t)spp * 3;
+	for(int k = 0; k < spp; ++k, sp += 3)
+	{
+		const float w = weights ? weights[p * (size_t)spp + k] : 1.f;
+		const float rgb[3] = {sp[0], sp[1], sp[2]};
+		wSum = __fadd_rn(wSum, w);
+		w2Sum = __fadd_rn(w2Sum, __fmul_rn(w, w));
+		for(int c = 0; c < 3; ++c)
+			sum[c] = __fadd_rn(sum[c], __fmul_rn(w, rgb[c]));
+		// xx, yy, zz, yz, xz, xy: (w * a) * b like the reference's left-to-right products
+		c2[0] = __fadd_rn(c2[0], __fmul_rn(__fmul_rn(w, rgb[0]), rgb[0]));
+		c2[1] = __fadd_rn(c2[1], __fmul_rn(__fmul_rn(w, rgb[1]), rgb[1]));
+		c2[2] = __fadd_rn(c2[2], __fmul_rn(__fmul_rn(w, rgb[2]), rgb[2]));
+		c2[3] = __fadd_rn(c2[3], __fmul_rn(__fmul_rn(w, rgb[1]), rgb[2]));
+		c2[4] = __fadd_rn(c2[4], __fmul_rn(__fmul_rn(w, rgb[0]), rgb[2]));
+		c2[5] = __fadd_rn(c2[5], __fmul_rn(__fmul_rn(w, rgb[0]), rgb[1]));
+		for(int c = 0; c < 3; ++c)
+		{
+			float v = rgb[c] > 0.f ? rgb[c] : 0.f;
+			if(gamma > 1.f) v = powf(v, invGamma);
+			if(maxValue > 0.f) v = __fdiv_rn(v, maxValue);
+			v = v > saturation ? saturation : v;
+			const float position = __fmul_rn(v, (float)(nbBins - 2));
+			int lowBin = (int)position;
+			float highWeight;
+			if(lowBin < nbBins - 2)
+				highWeight = __fsub_rn(position, (float)lowBin);
+			else
+			{
+				lowBin = nbBins - 2;
+				highWeight = __fdiv_rn(__fsub_rn(v, 1.f), __fsub_rn(saturation, 1.f));
+			}
+			const float lowWeight = __fsub_rn(1.f, highWeight);
+			float* hb = shHist + (c * nbBins + lowBin) * NT + tid;
+			hb[0] = __fadd_rn(hb[0], __fmul_rn(w, lowWeight));
+			hb[NT] = __fadd_rn(hb[NT], __fmul_rn(w, highWeight));
+		}
+	}
+	// computeSampleStatistics (:110-141)
+	const float invW = __fdiv_rn(1.f, wSum);
+	float mean[3];
+	for(int c = 0; c < 3; ++c)
+	{
+		mean[c] = __fmul_rn(invW, sum[c]);
+		color[p * 3 + c] = mean[c];
+	}
+	ns[p] = wSum;
+	const float unbias = __fdiv_rn(1.f, __fsub_rn(1.f, __fdiv_rn(w2Sum, __fmul_rn(wSum, wSum))));
+	const int ia[6] = {0, 1, 2, 1, 0, 0}, ib[6] = {0, 1, 2, 2, 2, 1};
+	for(int e = 0; e < 6; ++e)
+	{
+		float cv = __fmul_rn(c2[e], invW);
+		cv = __fsub_rn(cv, __fmul_rn(mean[ia[e]], mean[ib[e]]));
+		cov[p * 6 + e] = __fmul_rn(cv, unbias);
+	}
+	for(int k = 0; k < B; ++k)
+		hist[p * B + k] = shHist[k * NT + tid];
+}
+
+cudaError_t launchAccumulateSamples(const float* samples, const float* weights, size_t npix, int spp, int nbBins, float gamma,
+		float maxValue, float* color, float* ns, float* hist, float* cov, cudaStream_t st, int* launches)
+{
+	constexpr int NT = 64;
+	const size_t smem = (size_t)3 * nbBins * NT * sizeof(float);
+	cudaError_t err = allowDynamicSmem((const void*)k_accumulate_samples<NT>, smem);
+	if(err != cudaSuccess) return err;
+	k_accumulate_samples<NT><<<(unsigned)((npix + NT - 1) / NT), NT, smem, st>>>(samples, weights, npix, spp, nbBins, gamma, maxValue,
+			color, ns, hist, cov);
+	*launches += 1;
+	return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 //  SpikeRemovalFilter::filter — src/core/SpikeRemovalFilter.cpp:18-75 with :77-92 (average and
 // standard deviation of the 3x3 neighbourhood, sequential sums) and :94-116 (L1 median of the 9 colours).

@@ -89,6 +89,9 @@ cudaError_t launchFinalize(const float4* acc, size_t npix, float* out, cudaStrea
 // (row f1) SpikeRemovalFilter: out-of-place; src = W*H ints of scratch
 cudaError_t launchSpikeFilter(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
 		float factor, int intAbs, int* src, float* colorOut, float* nsOut, float* histOut, float* covOut, cudaStream_t st, int* launches);
+// (row f3, device side) SamplesAccumulator on the GPU: samples [pixel][spp][rgb] (+ optional weights [pixel][spp]) -> statistics
+cudaError_t launchAccumulateSamples(const float* samples, const float* weights, size_t npix, int spp, int nbBins, float gamma,
+		float maxValue, float* color, float* ns, float* hist, float* cov, cudaStream_t st, int* launches);
 // K5 pyramid down, K6 merge
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
 		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts = 3,

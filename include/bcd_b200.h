@@ -150,6 +150,18 @@ int  bcd_b200_spike_removal_host(float* color, float* nsamples, float* hist, flo
 /* device -> host copy of the resident level-0 inputs (e.g. after bcd_b200_spike_removal) */
 int  bcd_b200_download_inputs(bcd_b200_handle* h, float* color, float* nsamples, float* hist, float* cov);
 
+/* ---- (device side) sample accumulation on the GPU ------------------------------------------------------
+ * Replaces SamplesAccumulator::addSample + computeSampleStatistics (reference src/core/SamplesAccumulator.cpp:44-107,
+ * 110-141) for a renderer whose samples already live in device memory (or in one host block): samples are
+ * [height][width][spp][3] floats, weights (may be NULL: all 1) [height][width][spp]. The statistics — mean colour, sample
+ * count, 3*nb_bins histogram (gamma / max_value as in HistogramParameters, SamplesAccumulator.h:20-30), bias-corrected
+ * covariance — become the handle's resident inputs, ready for bcd_b200_spike_removal / bcd_b200_run; nothing
+ * round-trips through the host. samples_on_device: 1 = device pointers, 0 = host pointers (copied first).
+ * Mean, count and covariance are the reference's numbers bit for bit; histogram bins may differ in the last place
+ * (device powf vs glibc powf in the gamma curve). */
+int  bcd_b200_accumulate_samples(bcd_b200_handle* h, const float* samples, const float* weights, int samples_on_device,
+                                 int32_t width, int32_t height, int32_t spp, int32_t nb_bins, float gamma, float max_value);
+
 /* ---- row-tile API (multi-GPU: one handle per GPU, one process per GPU) ---------------------------------------------
  * The frame is cut into horizontal bands. Tile t of n produces the output rows [own_row0, own_row1) and keeps the
  * input rows [sub_row0, sub_row1) resident (its band plus (b+w)*2^(s-1) halo rows, so that every pyramid level has
