@@ -180,7 +180,7 @@ int finishUpload(bcd_b200_handle* h)
 constexpr int UPLOAD_HALO = 16;
 
 // K1b + K1c on the rows [r0, r1) of the level (the whole selection region when r0 < 0)
-int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st, bool privateScratch = false)
+int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st, bool privateScratch)
 {
 	LevelBufs& L = h->levels[k];
 	LevelGeom g = levelGeom(h, k, p);
@@ -217,6 +217,8 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // of their work counters (round 1); true = every level is a pipeline of its own (marking -> filter -> finalize on the
 // level's stream, list lengths stay on the device, no host wait inside a frame) — BCD_B200_SCHED=serial|levels
 bool g_schedLevels = true;
+// level pipelines: K1b/K1c at the head of the level's stream instead of behind K1a on the main stream (BCD_B200_DEFER_SELECT=0|1)
+bool g_deferSelect = true;
 bool g_streamCoarse = true; // BCD_B200_STREAM_COARSE=0: coarser levels start their selection after the upload (A/B hook)
 
 // Under a streamed upload the coarser levels do not have to wait for the frame either: rows < rowEnd >> k of level k
@@ -323,7 +325,7 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p,
 				});
 				CU(cudaEventRecord(up.evPair[i], st));
 				CU(cudaStreamWaitEvent(sel, up.evPair[i], 0));
-				if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+				if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel, false))) return rc;
 				prev0 = r0;
 				prev1 = r1;
 				r0 = r1;
@@ -337,18 +339,32 @@ int levelPairAndPatchSelect(bcd_b200_handle* h, int k, const bcd_b200_params& p,
 				if((rc = coarseBand(h, p, l, avail, i == nb - 1, coarse[l]))) return rc;
 			}
 		}
-		if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel))) return rc;
+		if(prev1 > prev0 && (rc = patchSelectRows(h, k, p, prev0, prev1, sel, false))) return rc;
 		CU(cudaEventRecord(up.evSelDone, sel));
 		CU(cudaStreamWaitEvent(st, up.evSelDone, 0));
 		up.histOrdered = true;
 	}
 	else
 	{
+		// Level pipelines (h->deferSelect): only the pair terms run here; the patch selection (K1b/K1c: streams the pair
+		// planes, memory-bound) moves to the head of the level's own stream, where it overlaps the issue-bound pair kernel
+		// of the next level. Every level then needs its own planes: level 0 keeps the shared ones, the coarser levels use
+		// their private ones.
+		const bool priv = h->deferSelect && k > 0;
 		STAGE(h, BCD_B200_STAGE_PAIR, {
-			CU(launchPairTerms(L.hist, L.ns, g, h->sP.as<float>(), h->cP.as<unsigned char>(), st, &h->launches));
+			CU(launchPairTerms(L.hist, L.ns, g, priv ? L.sPl.as<float>() : h->sP.as<float>(),
+					priv ? L.cPl.as<unsigned char>() : h->cP.as<unsigned char>(), st, &h->launches));
 		});
-		if((rc = patchSelectRows(h, k, p, -1, -1, st))) return rc;
+		if(h->deferSelect)
+		{
+			CU(cudaEventRecord(L.evPair, st));
+			L.selectPending = true;
+			L.selectPrivate = priv;
+			return 0;
+		}
+		if((rc = patchSelectRows(h, k, p, -1, -1, st, false))) return rc;
 	}
+	L.selectPending = false;
 	CU(cudaEventRecord(L.evSel, st));
 	return 0;
 }
@@ -638,6 +654,8 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 			CU(cudaEventCreateWithFlags(&L.evSel, cudaEventDisableTiming));
 		if(!L.evMark)
 			CU(cudaEventCreateWithFlags(&L.evMark, cudaEventDisableTiming));
+		if(!L.evPair)
+			CU(cudaEventCreateWithFlags(&L.evPair, cudaEventDisableTiming));
 	}
 	// filter chunk: bounded scratch (two d x d matrices per slot)
 	const size_t perSlot = (size_t)2 * g.d * g.d * 4;
@@ -820,6 +838,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 			g_eigGroup = atoi(e);
 		e = getenv("BCD_B200_SCHED");
 		if(e) g_schedLevels = strcmp(e, "serial") != 0;
+		e = getenv("BCD_B200_DEFER_SELECT");
+		if(e) g_deferSelect = e[0] != '0';
 		e = getenv("BCD_B200_EIG_GENERIC");
 		g_eigGenericOrder = e && e[0] == '1';
 		e = getenv("BCD_B200_TRACE");
@@ -877,6 +897,7 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 		if(L.hostCtr) cudaFreeHost(L.hostCtr);
 		if(L.evSel) cudaEventDestroy(L.evSel);
 		if(L.evMark) cudaEventDestroy(L.evMark);
+		if(L.evPair) cudaEventDestroy(L.evPair);
 	}
 	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX, &h->peer.tickets};
 	for(DevBuf* b : bufs) b->release();
@@ -1038,6 +1059,7 @@ int bcd_b200_run(bcd_b200_handle* h, const bcd_b200_params* p, bcd_b200_progress
 	CU(cudaSetDevice(h->device));
 	if(g_schedLevels)
 		return runLevelPipelines(h, p, progress, user);
+	h->deferSelect = false;
 	rc = ensureBuffers(h, *p);
 	if(rc) return rc;
 	memset(&h->stats, 0, sizeof(h->stats));
@@ -1249,6 +1271,7 @@ int bcd_b200_tile_begin(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_
 	h->tileIndex = t->tile_index; h->tileCount = t->tile_count;
 	h->runParams = *p;
 	h->ran = false;
+	h->deferSelect = false;
 	CU(cudaEventRecord(h->evTotal[0], h->stream));
 	h->pyrHistDone = h->pyrColorDone = 0; // the pyramid is built on demand by tile_select / tile_filter
 	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));

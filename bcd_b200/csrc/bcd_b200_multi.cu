@@ -221,7 +221,17 @@ int markPeer(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 	const int Wp = markingRowWords(g.W), b = p.search_radius;
 	int own0, own1;
 	tileOwnedRows(h, k, own0, own1);
-	CU(cudaStreamWaitEvent(st, L.evSel, 0));
+	if(L.selectPending)
+	{
+		// patch selection of the level at the head of its own stream (see levelPairAndPatchSelect)
+		CU(cudaStreamWaitEvent(st, L.evPair, 0));
+		int rc = patchSelectRows(h, k, p, -1, -1, st, L.selectPrivate);
+		if(rc) return rc;
+		L.selectPending = false;
+		CU(cudaEventRecord(L.evSel, st));
+	}
+	else
+		CU(cudaStreamWaitEvent(st, L.evSel, 0));
 	STAGE_ON(h, st, BCD_B200_STAGE_MARKING, {
 		if(p.skip_prob > 0.f)
 		{
@@ -345,6 +355,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	h->spans.clear();
 	h->launches = 0;
 	h->ran = false;
+	h->deferSelect = g_deferSelect;
 	if(!solo) h->peer.epoch += 1;
 	cudaStream_t st = h->stream;
 	const int s = p.nb_scales;
@@ -404,6 +415,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	}
 	CU(cudaMemcpyAsync(h->peer.hostTimeouts, h->peer.tickets.as<unsigned int>() + TIMEOUT_WORD, sizeof(unsigned int),
 			cudaMemcpyDeviceToHost, st));
+	h->deferSelect = false;
 	CU(cudaEventRecord(h->evTotal[1], st));
 	if(progress)
 	{
@@ -527,6 +539,13 @@ int peerPrepare(bcd_b200_handle* h, const bcd_b200_params* p, const bcd_b200_til
 		CU(L.fMinv.reserve(chunk * g.d * g.d * 4));
 		CU(L.fMean.reserve(chunk * g.d * 4));
 		CU(L.fNoise.reserve(chunk * g.np * 6 * 4));
+		if(k > 0) // pair-term planes of its own: the level's patch selection runs on its stream next to the pair kernel of level k + 1
+		{
+			const size_t npl = std::max<size_t>((size_t)g.W * g.H, 1);
+			CU(L.sPl.reserve(npl * g.J * sizeof(float)));
+			CU(L.cPl.reserve(npl * g.J));
+			CU(L.mplusl.reserve(npl * g.Jw * 4));
+		}
 	}
 	bcd_b200_handle::Peer& P = h->peer;
 	const size_t bytes = layoutArena(h, *p);

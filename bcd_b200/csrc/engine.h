@@ -65,7 +65,8 @@ struct LevelBufs
 	int filterChunk = 0;
 	DeviceCounters* hostCtr = nullptr; // pinned read-back of ctr
 	DeviceCounters counters;           // host copy used to size the filter launches
-	cudaEvent_t evSel = nullptr, evMark = nullptr;
+	cudaEvent_t evSel = nullptr, evMark = nullptr, evPair = nullptr;
+	bool selectPending = false, selectPrivate = false; // level pipelines: K1b/K1c of this level still to be issued on its stream
 };
 
 } // namespace bcdeng
@@ -118,6 +119,7 @@ struct bcd_b200_handle
 	std::vector<Span> spans;         // timed stage instances of the current run
 	int smCount = 148;               // multiprocessors of the device
 	bool trace = false;              // BCD_B200_TRACE=1 (read once at bcd_b200_create)
+	bool deferSelect = false;        // set by the level-pipeline schedule for the duration of a run (see levelPairAndPatchSelect)
 	bool timingsPending = false;     // the last run's spans have not been resolved into `timings` yet
 	cudaEvent_t evTotal[2] = {nullptr, nullptr};
 	size_t eventsUsed = 0;
@@ -171,7 +173,8 @@ bcdk::LevelGeom levelGeom(const bcd_b200_handle* h, int k, const bcd_b200_params
 void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1);
 cudaStream_t auxOf(bcd_b200_handle* h, int k);
 
-extern bool g_schedLevels;
+extern bool g_schedLevels, g_deferSelect;
+int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st, bool privateScratch);
 void releaseNeighbourArena(bcd_b200_handle* h, int side); // bcd_b200_multi.cu: unmaps (reference-counted) the neighbour's arena
 int checkParams(const bcd_b200_params* p);
 int checkImages(const bcd_b200_images* in);
