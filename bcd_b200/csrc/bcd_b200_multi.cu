@@ -703,6 +703,8 @@ struct bcd_b200_group
 	int rank = 0, world = 1;       // this process' position when the GPUs of the box are spread over several processes
 	std::vector<int> dev;          // CUDA devices of this process
 	int tilesPerGpu = 0;           // 0: chosen from the frame height
+	int hostTiles = 3;             // one GPU, frames from host memory: tiles whose chained uploads pipeline with the kernels
+	bool hostPath = false;         // the current setup is for bcd_b200_group_denoise (host buffers)
 	bool pin = true;
 	std::vector<std::pair<const void*, size_t>> pinned;
 
@@ -747,7 +749,7 @@ struct bcd_b200_group
 namespace
 {
 
-enum { JOB_SETUP = 1, JOB_CONNECT = 2, JOB_RUN = 3, JOB_E2E = 4 };
+enum { JOB_SETUP = 1, JOB_CONNECT = 2, JOB_RUN = 3, JOB_E2E = 4, JOB_RUN_DOWNLOAD = 5 };
 
 typedef bcd_b200_group::Slot Slot;
 
@@ -796,6 +798,13 @@ void slotJob(Slot& s)
 	case JOB_RUN:
 		note(s, bcd_b200_tile_run(s.h, &g->p));
 		break;
+	case JOB_RUN_DOWNLOAD: // the uploads were enqueued (chained) by the dispatching thread
+	{
+		int rc = bcd_b200_tile_run(s.h, &g->p);
+		if(!rc) rc = bcd_b200_tile_download(s.h, s.hostOut);
+		note(s, rc);
+		break;
+	}
 	case JOB_E2E:
 	{
 		// every tile must reach the run (its neighbours wait for its strips), so a local failure is only noted
@@ -901,7 +910,7 @@ void pinRange(bcd_b200_group* g, const void* ptr, size_t bytes)
 }
 
 // number of tiles for a frame: tilesPerGpu x GPUs, fewer when the bands would get too thin for the pyramid
-int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::vector<bcd_b200_tile>& plan)
+int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::vector<bcd_b200_tile>& plan, bool hostPath)
 {
 	const int G = gpusTotal(g);
 	int T = g->tilesPerGpu;
@@ -912,6 +921,12 @@ int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::
 		// for their kernels to fill a GPU: bands of at least 256 rows, at most 4 per GPU, only from 4 GPUs on
 		// (measured on 8 B200: profiles/r02_scaling.md; 1080p always gets one band per GPU).
 		T = G >= 4 ? std::max(1, std::min(4, H / std::max(1, G * 256))) : 1;
+		// Frames that come from host memory (bcd_b200_group_denoise: what bcd::Denoiser calls) are upload-bound on one
+		// GPU: 581 MB at 1080p take 10.5 ms of PCIe 5 against 13 ms of kernels that can only finish once the last row has
+		// landed. Cut into a few tiles whose uploads are chained, the first tile selects, marks and filters while the
+		// rows of the next ones are still in flight — only the last tile's work is left after the transfer.
+		if(G == 1 && hostPath)
+			T = std::max(1, std::min(g->hostTiles, H / 256));
 	}
 	for(int tiles = G * T; tiles > 1; tiles = tiles > G ? tiles - G : tiles - 1)
 	{
@@ -978,6 +993,8 @@ int bcd_b200_group_create_ranked(bcd_b200_group** out, const int32_t* device_ids
 		g->pin = !(e && e[0] == '0');
 		e = getenv("BCD_B200_TILES_PER_GPU");
 		if(e && atoi(e) > 0) g->tilesPerGpu = std::min(atoi(e), 16);
+		e = getenv("BCD_B200_HOST_TILES");
+		if(e && atoi(e) > 0) g->hostTiles = std::min(atoi(e), 8);
 	}
 	for(int i = 0; i < nb_gpus; ++i)
 	{
@@ -1057,7 +1074,7 @@ int bcd_b200_group_setup(bcd_b200_group* g, int width, int height, int hist_dept
 	g->p = *p;
 	g->W = width; g->H = height; g->B = hist_depth;
 	std::vector<bcd_b200_tile> plan;
-	g->tiles = chooseTiles(g, width, height, *p, plan);
+	g->tiles = chooseTiles(g, width, height, *p, plan, g->hostPath);
 	// local tiles, in frame order
 	int n = 0;
 	for(int j = 0; j < g->tiles; ++j)
@@ -1212,7 +1229,9 @@ int bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const b
 			g->conWr == p->patch_radius && g->conBr == p->search_radius && g->conS == p->nb_scales;
 	if(!same)
 	{
+		g->hostPath = true;
 		rc = bcd_b200_group_setup(g, in->width, in->height, in->hist_depth, p, nullptr, nullptr, 0);
+		g->hostPath = false;
 		if(!rc) rc = bcd_b200_group_connect(g, nullptr, 0);
 		if(rc) return rc;
 	}
@@ -1240,8 +1259,23 @@ int bcd_b200_group_denoise(bcd_b200_group* g, const bcd_b200_images* in, const b
 		s.hostOut = out_rgb + (size_t)t.own_row0 * W * 3;
 	}
 	if(progress) progress(0.f, user);
-	rc = bcd_b200_group_run(g, p, 1);
+	// uploads: enqueued here, in tile order; tiles that share a device (and so a PCIe link) are chained, so that the rows
+	// of the first tile arrive first and its kernels start while the next tiles are still in flight
+	{
+		std::map<int, cudaEvent_t> lastOnDevice;
+		for(int i = 0; i < g->nLocal; ++i)
+		{
+			Slot& s = *g->slots[i];
+			auto it = lastOnDevice.find(s.device);
+			rc = uploadAsyncAfter(s.h, &s.hostIn, it == lastOnDevice.end() ? nullptr : it->second);
+			if(rc) return rc;
+			lastOnDevice[s.device] = s.h->up.evAll;
+		}
+	}
+	g->p = *p;
+	rc = dispatch(g, JOB_RUN_DOWNLOAD);
 	if(rc) return rc;
+	collectGroupStats(g);
 	if(progress) progress(1.f, user);
 	return 0;
 }

@@ -180,6 +180,7 @@ int checkParams(const bcd_b200_params* p);
 int checkImages(const bcd_b200_images* in);
 int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p);
 int finishUpload(bcd_b200_handle* h);
+int uploadAsyncAfter(bcd_b200_handle* h, const bcd_b200_images* in, cudaEvent_t after);
 int prepareUpload(bcd_b200_handle* h, int width, int height, int histDepth);
 int reserveEvents(bcd_b200_handle* h, size_t count);
 int pyramidLevel(bcd_b200_handle* h, int k, int parts);

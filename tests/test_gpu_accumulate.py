@@ -43,20 +43,37 @@ def test_device_accumulation_matches_the_host_accumulator():
         h.close()
 
 
+def _cudart():
+    import ctypes
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            return ctypes.CDLL(name)
+        except OSError:
+            continue
+    pytest.skip("no CUDA runtime library to allocate a device block with")
+
+
 def test_device_accumulation_from_device_memory_with_weights():
-    import torch
+    """The samples (and per-sample weights) already live in device memory, like a GPU renderer's would."""
+    import ctypes
     from bcd_b200 import capi
+    rt = _cudart()
     H, W, spp = 24, 32, 8
     samples = _samples(H, W, spp, 9)
     weights = np.random.default_rng(3).uniform(0.25, 2.0, (H, W, spp)).astype(np.float32)
-    ds, dw = torch.from_numpy(samples).cuda(), torch.from_numpy(weights).cuda()
-    torch.cuda.synchronize()
-    h = capi.Handle(0)
+    h = capi.Handle(0)  # creates the context
+    ds, dw = ctypes.c_void_p(), ctypes.c_void_p()
+    assert rt.cudaMalloc(ctypes.byref(ds), ctypes.c_size_t(samples.nbytes)) == 0
+    assert rt.cudaMalloc(ctypes.byref(dw), ctypes.c_size_t(weights.nbytes)) == 0
     try:
-        h.accumulate_samples(None, device_ptrs=(ds.data_ptr(), dw.data_ptr(), H, W, spp))
+        assert rt.cudaMemcpy(ds, ctypes.c_void_p(samples.ctypes.data), ctypes.c_size_t(samples.nbytes), 1) == 0
+        assert rt.cudaMemcpy(dw, ctypes.c_void_p(weights.ctypes.data), ctypes.c_size_t(weights.nbytes), 1) == 0
+        h.accumulate_samples(None, device_ptrs=(ds.value, dw.value, H, W, spp))
         got = h.download_inputs()
     finally:
         h.close()
+        rt.cudaFree(ds)
+        rt.cudaFree(dw)
     # weighted mean / count against a float64 evaluation (the reference's accumulator with weights, in float32 order)
     wsum = weights.astype(np.float64).sum(-1)
     mean = (weights[..., None].astype(np.float64) * samples).sum(2) / wsum[..., None]
