@@ -703,7 +703,8 @@ struct bcd_b200_group
 	int rank = 0, world = 1;       // this process' position when the GPUs of the box are spread over several processes
 	std::vector<int> dev;          // CUDA devices of this process
 	int tilesPerGpu = 0;           // 0: chosen from the frame height
-	int hostTiles = 3;             // one GPU, frames from host memory: tiles whose chained uploads pipeline with the kernels
+	int hostTiles = 1;             // one GPU, frames from host memory: tiles whose chained uploads pipeline with the kernels
+	                               // (BCD_B200_HOST_TILES; measured slower than the whole frame so far, see chooseTiles)
 	bool hostPath = false;         // the current setup is for bcd_b200_group_denoise (host buffers)
 	bool pin = true;
 	std::vector<std::pair<const void*, size_t>> pinned;
@@ -924,7 +925,9 @@ int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::
 		// Frames that come from host memory (bcd_b200_group_denoise: what bcd::Denoiser calls) are upload-bound on one
 		// GPU: 581 MB at 1080p take 10.5 ms of PCIe 5 against 13 ms of kernels that can only finish once the last row has
 		// landed. Cut into a few tiles whose uploads are chained, the first tile selects, marks and filters while the
-		// rows of the next ones are still in flight — only the last tile's work is left after the transfer.
+		// rows of the next ones are still in flight. Measured at 1080p (profiles/r02_host_tiles.md): 21.0 / 19.6 / 20.7 ms
+		// with 2 / 3 / 4 tiles against 17.4 ms for the whole frame — the tiles' band kernels get too small (12 bands of
+		// 30 rows per tile) and compete with the filters of the tile before — so the default stays 1; BCD_B200_HOST_TILES.
 		if(G == 1 && hostPath)
 			T = std::max(1, std::min(g->hostTiles, H / 256));
 	}
