@@ -74,6 +74,9 @@ k_recv(T* __restrict__ dst, const T* slot, size_t n, const uint32_t* flag, uint3
 }
 
 int gridFor(size_t n) { return (int)std::min<size_t>((n + 255) / 256, (size_t)currentSmCount()); }
+// a receiving kernel may sit on the device for milliseconds waiting for its neighbour: few blocks (grid-stride copy of a
+// strip of some ten thousand elements), so that the waiting threads do not take the slots of the kernels that do work
+int recvGridFor(size_t n) { return (int)std::max<size_t>(1, std::min<size_t>((n + 1023) / 1024, 16)); }
 
 } // namespace
 
@@ -100,17 +103,17 @@ cudaError_t launchPeerRecv(void* dst, const void* slot, size_t bytes, bool addFl
 	if(addFloat4)
 	{
 		const size_t n = bytes / 16;
-		k_recv<float4, true><<<gridFor(n), 256, 0, st>>>(static_cast<float4*>(dst), static_cast<const float4*>(slot), n, flag, epoch, timeouts);
+		k_recv<float4, true><<<recvGridFor(n), 256, 0, st>>>(static_cast<float4*>(dst), static_cast<const float4*>(slot), n, flag, epoch, timeouts);
 	}
 	else if(bytes % 16 == 0 && ((uintptr_t)dst % 16) == 0 && ((uintptr_t)slot % 16) == 0)
 	{
 		const size_t n = bytes / 16;
-		k_recv<float4, false><<<gridFor(n), 256, 0, st>>>(static_cast<float4*>(dst), static_cast<const float4*>(slot), n, flag, epoch, timeouts);
+		k_recv<float4, false><<<recvGridFor(n), 256, 0, st>>>(static_cast<float4*>(dst), static_cast<const float4*>(slot), n, flag, epoch, timeouts);
 	}
 	else
 	{
 		const size_t n = bytes / 4;
-		k_recv<uint32_t, false><<<gridFor(n), 256, 0, st>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(slot), n, flag, epoch, timeouts);
+		k_recv<uint32_t, false><<<recvGridFor(n), 256, 0, st>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(slot), n, flag, epoch, timeouts);
 	}
 	*launches += 1;
 	return cudaGetLastError();
