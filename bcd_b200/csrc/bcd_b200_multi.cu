@@ -917,11 +917,14 @@ int chooseTiles(bcd_b200_group* g, int W, int H, const bcd_b200_params& p, std::
 	int T = g->tilesPerGpu;
 	if(T <= 0)
 	{
-		// Several tiles per GPU pay when the marking chain (one dependency through all rows, ~1 us per 1080p-wide row)
-		// weighs as much as a GPU's share of the selection — many GPUs, tall frames — and the tiles stay large enough
-		// for their kernels to fill a GPU: bands of at least 256 rows, at most 4 per GPU, only from 4 GPUs on
-		// (measured on 8 B200: profiles/r02_scaling.md; 1080p always gets one band per GPU).
-		T = G >= 4 ? std::max(1, std::min(4, H / std::max(1, G * 256))) : 1;
+		// One tile per GPU. Several cyclic tiles per GPU (tile j on GPU j mod G) are meant to let the marking chain — one
+		// dependency through all rows — run through the first G tiles while the GPUs still select their second ones. As
+		// measured (profiles/r02_scaling.md) that does not pay yet: the tiles of one GPU are driven by independent host
+		// threads on streams of equal priority, so their selections share the GPU and finish TOGETHER instead of tile
+		// after tile (4096^2 on 4 GPUs: 28.1 ms with 4 tiles per GPU against 28.4 ms with one), and at 1080p the small
+		// tiles make a rank launch-bound (8 GPUs: 4.2 / 3.6 ms with 2 / 3 tiles against 3.24 ms). Next step: stream
+		// priorities by tile order. bcd_b200_group_set_tiles_per_gpu / BCD_B200_TILES_PER_GPU select it explicitly.
+		T = 1;
 		// Frames that come from host memory (bcd_b200_group_denoise: what bcd::Denoiser calls) are upload-bound on one
 		// GPU: 581 MB at 1080p take 10.5 ms of PCIe 5 against 13 ms of kernels that can only finish once the last row has
 		// landed. Cut into a few tiles whose uploads are chained, the first tile selects, marks and filters while the
