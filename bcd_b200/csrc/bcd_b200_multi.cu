@@ -355,6 +355,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	h->spans.clear();
 	h->launches = 0;
 	h->ran = false;
+	h->nsEarly = false;
 	h->deferSelect = g_deferSelect;
 	if(!solo) h->peer.epoch += 1;
 	cudaStream_t st = h->stream;
@@ -365,6 +366,22 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));
 	// selection of every level on the main stream, finest first (its marking chain is the longest); each level's chain
 	// follows on the level's own stream as soon as its selection is there
+	// Under a streamed upload that sends covariance + colour first, everything that needs only those — the colour side of
+	// the pyramid, the per-pixel covariances — goes to the front of the main stream: it runs while the histogram is still
+	// crossing PCIe, and the filters of the coarser levels (selected band by band behind the transfer) can follow there too
+	const bool colourEarly = h->up.pending && g_colorFirst && !false;
+	if(colourEarly)
+	{
+		CU(cudaStreamWaitEvent(st, h->up.evColorCov, 0));
+		for(int k = 1; k < s; ++k) // sample counts first: the covariance of level k + 1 is weighted with those of level k
+			if((rc = pyramidLevel(h, k, 4))) return rc;
+		h->nsEarly = true;
+		for(int k = 1; k < s; ++k)
+			if((rc = pyramidLevel(h, k, 2))) return rc;
+		for(int k = 0; k < s; ++k)
+			if((rc = levelPixelCov(h, k, p))) return rc;
+		CU(cudaEventRecord(h->peer.evColor, st));
+	}
 	int streamedCoarse = 0; // whole-frame runs under a streamed upload: levels whose selection ran band by band behind level 0
 	for(int k = 0; k < s; ++k)
 	{
@@ -391,18 +408,25 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 		}
 		if((rc = markPeer(h, k, p))) return rc;
 	}
-	// colour / covariance side of the pyramid, per-pixel covariances
+	// colour / covariance side of the pyramid, per-pixel covariances (unless they went first, above)
 	if((rc = finishUpload(h))) return rc;
-	for(int k = 1; k < s; ++k)
-		if((rc = pyramidLevel(h, k, 2))) return rc;
-	for(int k = 0; k < s; ++k)
-		if((rc = levelPixelCov(h, k, p))) return rc;
-	CU(cudaEventRecord(h->peer.evColor, st));
+	if(!colourEarly)
+	{
+		for(int k = 1; k < s; ++k)
+			if((rc = pyramidLevel(h, k, 2))) return rc;
+		for(int k = 0; k < s; ++k)
+			if((rc = levelPixelCov(h, k, p))) return rc;
+		CU(cudaEventRecord(h->peer.evColor, st));
+	}
 	// the levels' filter pipelines run side by side; coarsest first in issue order (its chain through the ranks is the
 	// shortest, so on the lower tiles it is ready first)
 	for(int i = 0; i < s; ++i)
 	{
-		const int k = h->tiled ? s - 1 - i : i; // whole frame: finest first — its marking was started first
+		// order of issue (whole frames: also the order in which the host waits for the levels' counters): the level whose
+		// marking finishes first. Resident inputs: the finest (its chain was started first). Row tiles: the coarsest (its
+		// chain through the ranks is the shortest). Streamed upload with the coarser levels selected behind the bands:
+		// the coarser levels are through long before level 0, whose last band only arrives with the end of the transfer.
+		const int k = (h->tiled || (colourEarly && streamedCoarse > 0)) ? s - 1 - i : i;
 		if((rc = filterPeer(h, k, p))) return rc;
 	}
 	// merges coarsest to finest on the main stream (MultiscaleDenoiser.cpp:79-134)
@@ -416,6 +440,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	CU(cudaMemcpyAsync(h->peer.hostTimeouts, h->peer.tickets.as<unsigned int>() + TIMEOUT_WORD, sizeof(unsigned int),
 			cudaMemcpyDeviceToHost, st));
 	h->deferSelect = false;
+	h->nsEarly = false;
 	CU(cudaEventRecord(h->evTotal[1], st));
 	if(progress)
 	{

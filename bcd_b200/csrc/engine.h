@@ -102,6 +102,7 @@ struct bcd_b200_handle
 		int rowEnd[16];
 		cudaEvent_t ev[16] = {};
 		cudaEvent_t evAll = nullptr, evOrder = nullptr;
+		cudaEvent_t evColorCov = nullptr; // covariance + colour of the pending upload have landed
 		// banded level-0 selection: K1b/K1c of band i-1 run on `sel` next to K1a of band i+1 on the main stream
 		cudaStream_t sel = nullptr;
 		cudaEvent_t evPair[16] = {};
@@ -119,6 +120,7 @@ struct bcd_b200_handle
 	std::vector<Span> spans;         // timed stage instances of the current run
 	int smCount = 148;               // multiprocessors of the device
 	bool trace = false;              // BCD_B200_TRACE=1 (read once at bcd_b200_create)
+	bool nsEarly = false;            // this run built the sample counts of the pyramid ahead of the histograms (colour-first upload)
 	bool deferSelect = false;        // set by the level-pipeline schedule for the duration of a run (see levelPairAndPatchSelect)
 	bool timingsPending = false;     // the last run's spans have not been resolved into `timings` yet
 	cudaEvent_t evTotal[2] = {nullptr, nullptr};
@@ -173,7 +175,7 @@ bcdk::LevelGeom levelGeom(const bcd_b200_handle* h, int k, const bcd_b200_params
 void tileOwnedRows(const bcd_b200_handle* h, int k, int& own0, int& own1);
 cudaStream_t auxOf(bcd_b200_handle* h, int k);
 
-extern bool g_schedLevels, g_deferSelect;
+extern bool g_schedLevels, g_deferSelect, g_colorFirst;
 int patchSelectRows(bcd_b200_handle* h, int k, const bcd_b200_params& p, int r0, int r1, cudaStream_t st, bool privateScratch);
 void releaseNeighbourArena(bcd_b200_handle* h, int side); // bcd_b200_multi.cu: unmaps (reference-counted) the neighbour's arena
 int checkParams(const bcd_b200_params* p);

@@ -413,11 +413,15 @@ cudaError_t launchDownscale(const float* color, const float* ns, const float* hi
 	if(npd == 0 || npr == 0)
 		return cudaSuccess;
 	auto blocks = [](size_t n) { return (unsigned)((n + 255) / 256); };
-	if(parts & 1) // what the selection stage of the coarser level reads
+	if(parts & (1 | 4)) // sample counts: read by the selection stage of the coarser level and by the covariance part below
 	{
 		k_downscale<<<blocks(npr), 256, 0, st>>>(ns, W, H, 1, 0, nsD, rowBeg, rows);
+		*launches += 1;
+	}
+	if(parts & (1 | 8)) // histograms: what the selection stage of the coarser level reads
+	{
 		k_downscale<<<blocks(npr * B), 256, 0, st>>>(hist, W, H, B, 0, histD, rowBeg, rows);
-		*launches += 2;
+		*launches += 1;
 	}
 	if(parts & 2) // what its filters read
 	{

@@ -95,7 +95,9 @@ cudaError_t launchAccumulateSamples(const float* samples, const float* weights, 
 // K5 pyramid down, K6 merge
 cudaError_t launchDownscale(const float* color, const float* ns, const float* hist, const float* cov, int W, int H, int B,
 		float* colorD, float* nsD, float* histD, float* covD, cudaStream_t st, int* launches, int parts = 3,
-		int rowBeg = 0, int rows = -1); // rows >= 0: only these rows of the coarser level (part 1)
+		int rowBeg = 0, int rows = -1); // rows >= 0: only these rows of the coarser level (parts 1 / 4 / 8)
+// parts: 1 = sample counts + histograms, 2 = colour + covariance (reads the FINER level's sample counts), 4 = sample counts
+// only, 8 = histograms only
 cudaError_t launchMerge(float* hi, int W, int H, const float* lowOut, float* tmpLow, cudaStream_t st, int* launches);
 
 } // namespace bcdk
