@@ -216,8 +216,10 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // whole-frame schedule: false = the levels are filtered one after the other on the main stream behind a host read-back
 // of their work counters (round 1); true = every level is a pipeline of its own (marking -> filter -> finalize on the
 // level's stream, list lengths stay on the device, no host wait inside a frame) — BCD_B200_SCHED=serial|levels
-// streamed upload: covariance + colour before the histogram (BCD_B200_COLOR_FIRST=0: after it, the round-1 order)
-bool g_colorFirst = true;
+// streamed upload: covariance + colour before the histogram instead of after it (BCD_B200_COLOR_FIRST=1). Measured at
+// 1080p: 18.83 ms against 17.41 ms — sent last, the 75 MB of covariance + colour cross PCIe under the last selection band
+// and the level-0 marking for free; sent first, they delay the histogram, whose end is what the tail of the frame waits for.
+bool g_colorFirst = false;
 bool g_schedLevels = true;
 // level pipelines: K1b/K1c at the head of the level's stream instead of behind K1a on the main stream (BCD_B200_DEFER_SELECT=0|1)
 bool g_deferSelect = false; // measured: 13.29 ms deferred vs 13.19 ms — kept as an A/B hook only
@@ -1018,10 +1020,8 @@ int bcdeng::uploadAsyncAfter(bcd_b200_handle* h, const bcd_b200_images* in, cuda
 	CU(cudaMemcpyAsync(L.ownNs.p, in->nsamples, np * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 	if(g_colorFirst)
 	{
-		// covariance + colour (13 % of the bytes) before the histogram: the colour side of the pyramid, the per-pixel
-		// covariances and the filters of the coarser levels (whose selection streams behind the histogram bands) then run
-		// UNDER the transfer instead of after it; the band kernels are transfer-bound anyway, so starting the histogram
-		// 1.4 ms later at 1080p costs nothing at the end
+		// A/B variant: covariance + colour (13 % of the bytes) before the histogram, so that the colour side of the pyramid
+		// and the per-pixel covariances run under the transfer (see g_colorFirst for why it is not the default)
 		CU(cudaMemcpyAsync(L.ownCov.p, in->cov, np * 6 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 		CU(cudaMemcpyAsync(L.ownColor.p, in->color, np * 3 * sizeof(float), cudaMemcpyHostToDevice, up.copy));
 		CU(cudaEventRecord(up.evColorCov, up.copy));
