@@ -339,6 +339,12 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	if(h->H != h->subRow1 - h->subRow0 || h->W != h->peer.geomW)
 		return fail(BCD_B200_ERR_INVALID_ARGUMENT, "resident inputs are %dx%d but the tile was set up for %dx%d", h->W, h->H,
 				h->peer.geomW, h->subRow1 - h->subRow0);
+	// per-run switches of the handle, cleared again on every way out of this function
+	struct RunFlags
+	{
+		bcd_b200_handle* h;
+		~RunFlags() { h->deferSelect = false; h->nsEarly = false; h->peer.solo = false; }
+	} runFlags{h};
 	h->peer.solo = solo;
 	for(int side = 0; side < 2 && !solo; ++side)
 	{
@@ -364,12 +370,9 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 	CU(cudaEventRecord(h->evTotal[0], st));
 	h->pyrHistDone = h->pyrColorDone = 0;
 	memset(h->pixcovDone, 0, sizeof(h->pixcovDone));
-	// selection of every level on the main stream, finest first (its marking chain is the longest); each level's chain
-	// follows on the level's own stream as soon as its selection is there
-	// Under a streamed upload that sends covariance + colour first, everything that needs only those — the colour side of
-	// the pyramid, the per-pixel covariances — goes to the front of the main stream: it runs while the histogram is still
-	// crossing PCIe, and the filters of the coarser levels (selected band by band behind the transfer) can follow there too
-	const bool colourEarly = h->up.pending && g_colorFirst && !false;
+	// (A/B variant BCD_B200_COLOR_FIRST=1) under a streamed upload that sends covariance + colour first, everything that
+	// needs only those — the colour side of the pyramid, the per-pixel covariances — goes to the front of the main stream
+	const bool colourEarly = h->up.pending && g_colorFirst;
 	if(colourEarly)
 	{
 		CU(cudaStreamWaitEvent(st, h->up.evColorCov, 0));
@@ -382,6 +385,8 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 			if((rc = levelPixelCov(h, k, p))) return rc;
 		CU(cudaEventRecord(h->peer.evColor, st));
 	}
+	// selection of every level on the main stream, finest first (its marking chain is the longest); each level's chain
+	// follows on the level's own stream as soon as its selection is there
 	int streamedCoarse = 0; // whole-frame runs under a streamed upload: levels whose selection ran band by band behind level 0
 	for(int k = 0; k < s; ++k)
 	{
@@ -418,8 +423,7 @@ int tileRun(bcd_b200_handle* h, const bcd_b200_params& p, bool solo = false, bcd
 			if((rc = levelPixelCov(h, k, p))) return rc;
 		CU(cudaEventRecord(h->peer.evColor, st));
 	}
-	// the levels' filter pipelines run side by side; coarsest first in issue order (its chain through the ranks is the
-	// shortest, so on the lower tiles it is ready first)
+	// the levels' filter pipelines run side by side
 	for(int i = 0; i < s; ++i)
 	{
 		// order of issue (whole frames: also the order in which the host waits for the levels' counters): the level whose
