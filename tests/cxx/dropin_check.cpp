@@ -124,6 +124,42 @@ int main(int argc, char** argv)
 	}
 	else
 		CHECK(!ok); // no device: denoise() must fail (never silently fall back to a CPU path)
+	// --- bcd_b200 extension: several GPUs behind the same call (here two row tiles on device 0, so that a one-GPU box can
+	//     run it), and the object reused frame after frame like the reference's GUI does (src/gui/GuiWindow.cpp:345-376)
+	if(gpu)
+	{
+		Deepimf outSingle(stats.m_meanImage), outMulti(stats.m_meanImage);
+		DenoiserOutputs oSingle, oMulti;
+		oSingle.m_pDenoisedColors = &outSingle;
+		oMulti.m_pDenoisedColors = &outMulti;
+		Denoiser single;
+		single.setInputs(inputs);
+		single.setOutputs(oSingle);
+		single.setParameters(params);
+		CHECK(single.denoise());
+		CHECK(single.getNbOfDevices() == 1 && single.getParameters().m_nbOfCores == 1);
+		Denoiser multi;
+		const int ids[2] = { 0, 0 };
+		multi.setDevices(ids, 2);
+		multi.setInputs(inputs);
+		multi.setOutputs(oMulti);
+		multi.setParameters(params);
+		for(int frame = 0; frame < 2; ++frame) // the second call reuses the device session (handles, peer links, pinned ranges)
+		{
+			outMulti.fill(-1.f);
+			CHECK(multi.denoise());
+			CHECK(multi.getNbOfDevices() == 2 && multi.getParameters().m_nbOfCores == 2); // two tiles worked on the frame
+			double worst = 0., scale = 0.;
+			for(int i = 0; i < outSingle.getSize(); ++i)
+			{
+				worst = std::fmax(worst, std::fabs(double(outMulti.get(i)) - double(outSingle.get(i))));
+				scale = std::fmax(scale, std::fabs(double(outSingle.get(i))));
+			}
+			CHECK(worst <= 1e-5 * scale); // only the order of the float atomics differs between the tilings
+		}
+		multi.releaseDeviceResources();
+		CHECK(multi.denoise()); // and comes back after an explicit release
+	}
 	std::printf("dropin_check: %d failure(s)\n", g_failures);
 	return g_failures ? 1 : 0;
 }
