@@ -220,6 +220,7 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // 1080p: 18.83 ms against 17.41 ms — sent last, the 75 MB of covariance + colour cross PCIe under the last selection band
 // and the level-0 marking for free; sent first, they delay the histogram, whose end is what the tail of the frame waits for.
 bool g_colorFirst = false;
+bool g_fallbackStream = true; // fallback kernel on a side stream next to the filter chain (BCD_B200_FALLBACK_STREAM=0|1)
 bool g_schedLevels = true;
 // level pipelines: K1b/K1c at the head of the level's stream instead of behind K1a on the main stream (BCD_B200_DEFER_SELECT=0|1)
 bool g_deferSelect = false; // measured: 13.29 ms deferred vs 13.19 ms — kept as an A/B hook only
@@ -488,11 +489,22 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 	const DeviceCounters c = L.counters;
 	DeviceCounters* dc = L.ctr.as<DeviceCounters>();
 	CU(cudaStreamWaitEvent(st, L.evMark, 0));
-	STAGE_ON(h, st, BCD_B200_STAGE_FALLBACK, {
+	// The fallback pixels (mean of the similar patches, DenoisingUnit.cpp:455-481) and the full pixels (two-step filter) are
+	// independent work lists that only meet in the accumulator (atomics): the fallback kernel runs on a side stream next
+	// to the filter chain instead of in front of it (BCD_B200_FALLBACK_STREAM=0: in front, on the same stream).
+	cudaStream_t fbSt = g_fallbackStream ? L.fbStream : st;
+	if(fbSt != st)
+	{
+		CU(cudaEventRecord(L.evFbBegin, st)); // everything the level's stream has waited for so far (marking, colour)
+		CU(cudaStreamWaitEvent(fbSt, L.evFbBegin, 0));
+	}
+	STAGE_ON(h, fbSt, BCD_B200_STAGE_FALLBACK, {
 		if(deviceCounts || c.nFallback > 0)
 			CU(launchFallback(L.color, L.smask.as<uint32_t>(), L.counts.as<int>(), g, L.fallbackList.as<int>(),
-					&dc->nFallback, L.acc.as<float4>(), st, &h->launches));
+					&dc->nFallback, L.acc.as<float4>(), fbSt, &h->launches));
 	});
+	if(fbSt != st)
+		CU(cudaEventRecord(L.evFbDone, fbSt));
 	FilterBuffers fb;
 	fb.A = (privateScratch ? L.fA : h->fA).as<float>();
 	fb.Minv = (privateScratch ? L.fMinv : h->fMinv).as<float>();
@@ -526,6 +538,8 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 		for(int i = 0; i < 5; ++i)
 			h->spans.push_back({ei[i], ei[i + 1], stageOf[i]});
 	}
+	if(fbSt != st)
+		CU(cudaStreamWaitEvent(st, L.evFbDone, 0)); // the accumulator is complete behind this point of the level's stream
 	return 0;
 }
 
@@ -661,6 +675,12 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 			CU(cudaEventCreateWithFlags(&L.evMark, cudaEventDisableTiming));
 		if(!L.evPair)
 			CU(cudaEventCreateWithFlags(&L.evPair, cudaEventDisableTiming));
+		if(!L.evFbBegin)
+			CU(cudaEventCreateWithFlags(&L.evFbBegin, cudaEventDisableTiming));
+		if(!L.evFbDone)
+			CU(cudaEventCreateWithFlags(&L.evFbDone, cudaEventDisableTiming));
+		if(!L.fbStream)
+			CU(cudaStreamCreateWithFlags(&L.fbStream, cudaStreamNonBlocking));
 	}
 	// filter chunk: bounded scratch (two d x d matrices per slot)
 	const size_t perSlot = (size_t)2 * g.d * g.d * 4;
@@ -842,6 +862,8 @@ int bcd_b200_create(bcd_b200_handle** out, int device)
 		e = getenv("BCD_B200_EIG_GROUP");
 		if(e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32))
 			g_eigGroup = atoi(e);
+		e = getenv("BCD_B200_FALLBACK_STREAM");
+		if(e) g_fallbackStream = e[0] != '0';
 		e = getenv("BCD_B200_COLOR_FIRST");
 		if(e) g_colorFirst = e[0] != '0';
 		e = getenv("BCD_B200_SCHED");
@@ -907,6 +929,9 @@ void bcd_b200_destroy(bcd_b200_handle* h)
 		if(L.evSel) cudaEventDestroy(L.evSel);
 		if(L.evMark) cudaEventDestroy(L.evMark);
 		if(L.evPair) cudaEventDestroy(L.evPair);
+		if(L.evFbBegin) cudaEventDestroy(L.evFbBegin);
+		if(L.evFbDone) cudaEventDestroy(L.evFbDone);
+		if(L.fbStream) { cudaStreamSynchronize(L.fbStream); cudaStreamDestroy(L.fbStream); }
 	}
 	DevBuf* bufs[] = {&h->sP, &h->cP, &h->mplus, &h->tmpLow, &h->fA, &h->fMinv, &h->fMean, &h->fNoise, &h->fX, &h->peer.tickets};
 	for(DevBuf* b : bufs) b->release();

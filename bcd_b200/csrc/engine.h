@@ -66,6 +66,8 @@ struct LevelBufs
 	DeviceCounters* hostCtr = nullptr; // pinned read-back of ctr
 	DeviceCounters counters;           // host copy used to size the filter launches
 	cudaEvent_t evSel = nullptr, evMark = nullptr, evPair = nullptr;
+	cudaStream_t fbStream = nullptr;                 // side stream of the fallback kernel (runs next to the filter chain)
+	cudaEvent_t evFbBegin = nullptr, evFbDone = nullptr;
 	bool selectPending = false, selectPrivate = false; // level pipelines: K1b/K1c of this level still to be issued on its stream
 };
 
