@@ -220,7 +220,7 @@ int clearPre(bcd_b200_handle* h, int k, const bcd_b200_params& p)
 // 1080p: 18.83 ms against 17.41 ms — sent last, the 75 MB of covariance + colour cross PCIe under the last selection band
 // and the level-0 marking for free; sent first, they delay the histogram, whose end is what the tail of the frame waits for.
 bool g_colorFirst = false;
-bool g_fallbackStream = true; // fallback kernel on a side stream next to the filter chain (BCD_B200_FALLBACK_STREAM=0|1)
+bool g_fallbackStream = false; // fallback kernel on a side stream next to the filter chain (BCD_B200_FALLBACK_STREAM=1): measured 13.20 vs 13.12 ms, not the default
 bool g_schedLevels = true;
 // level pipelines: K1b/K1c at the head of the level's stream instead of behind K1a on the main stream (BCD_B200_DEFER_SELECT=0|1)
 bool g_deferSelect = false; // measured: 13.29 ms deferred vs 13.19 ms — kept as an A/B hook only
@@ -490,8 +490,8 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 	DeviceCounters* dc = L.ctr.as<DeviceCounters>();
 	CU(cudaStreamWaitEvent(st, L.evMark, 0));
 	// The fallback pixels (mean of the similar patches, DenoisingUnit.cpp:455-481) and the full pixels (two-step filter) are
-	// independent work lists that only meet in the accumulator (atomics): the fallback kernel runs on a side stream next
-	// to the filter chain instead of in front of it (BCD_B200_FALLBACK_STREAM=0: in front, on the same stream).
+	// independent work lists that only meet in the accumulator (atomics): with BCD_B200_FALLBACK_STREAM=1 the fallback
+	// kernel runs on a side stream next to the filter chain instead of in front of it (A/B hook; no gain measured).
 	cudaStream_t fbSt = g_fallbackStream ? L.fbStream : st;
 	if(fbSt != st)
 	{
