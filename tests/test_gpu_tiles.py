@@ -140,6 +140,25 @@ def test_group_with_several_cyclic_tiles_per_gpu(gpus, per, kw):
         g.close()
 
 
+@pytest.mark.parametrize("count,kw", [
+    (3, dict(m=1.0, scales=3)),           # odd width and height: integer halving of the pyramid, clamped merge at the borders
+    (2, dict(m=1.0, scales=2, b=10)),     # wide search window: warp-skewed marking kernel, AS rows travel as a strip
+    (2, dict(m=1.0, scales=1, b=3)),      # small window: generic marking kernel
+])
+def test_group_tiles_odd_sizes_and_other_radii(count, kw):
+    from bcd_b200 import capi, host
+    inp = host.synth(131, 173, spp=16, seed=23)
+    ref, st_ref = _full(capi, inp, **kw)
+    g = capi.Group([0] * count, tiles_per_gpu=1)
+    try:
+        out = g.denoise(**inp, **kw)
+        assert g.tiles() == count
+        _counters_equal(g.stats(), st_ref)
+        assert O.rel_linf(out, ref) <= 2e-6
+    finally:
+        g.close()
+
+
 def test_group_reduces_the_tile_count_for_small_frames():
     from bcd_b200 import capi, host
     inp = host.synth(64, 96, spp=16)
