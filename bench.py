@@ -7,17 +7,25 @@ N = 1 workload (BASELINE.json `metric` / configs[2]): synthetic G(1920,1080,spp=
 covariance buffers, MultiscaleDenoiser s=3, defaults b=6, w=1, tau=1, m=1 (marking strategy, raster order).
 A "step" is one complete denoise of that frame.
 
-  value : Mpixels/s with the inputs already resident in HBM (bind_device; timed with CUDA events on the launching
-          stream, barrier + synchronize on both sides, max over ranks).
-  e2e   : the same metric through the C ABI handle calls a host renderer makes per frame — upload (pinned host ->
-          device) + run + download — all inside the timed region.
+  value        : Mpixels/s with the inputs already resident in HBM (bind_device + bcd_b200_run; CUDA events on the
+                 launching stream around exactly K steps, nothing else inside the timed region).
+  e2e          : the same metric through ONE C-ABI call per frame with host buffers in and out — bcd_b200_group_denoise,
+                 the call bcd::Denoiser::denoise() forwards to: upload (pinned host -> device, streamed under the level-0
+                 selection) + run + download, all inside the timed region. `ms_per_step_handle_api` is the same frame
+                 through bcd_b200_upload_async + bcd_b200_run + bcd_b200_download.
+  e2e_plugin   : the same through the C++ drop-in itself — one bcd::MultiscaleDenoiser object, DeepImages in pageable
+                 std::vector storage, denoise() per frame; first call and steady state separately.
   roofline     : dominant kernel (k_pair_terms_sparse, stage "pair") — algorithmic bytes / CUDA-event time vs the
-                 measured HBM peak (MEASURED_PEAKS.json); the binding roof of this kernel is FP32 issue, not HBM
-                 (SURVEY §8d), so `roofline_fp32` reports the bin-term rate against the FP32 pipe as well.
-  cpu_baseline : the UNMODIFIED reference CPU path (oracle/_ref, all host cores) on a bounded crop of the same frame.
+                 measured HBM peak (MEASURED_PEAKS.json); the binding roof of this kernel is FP32 issue / XU, not HBM
+                 (SURVEY 8d), so `roofline_fp32` reports the bin-term rate against the FP32 pipe as well.
+  nonuniform_n : the same workload with 48 samples per pixel (general-n path of the pair-term kernel).
+  cpu_baseline : the UNMODIFIED reference CPU path (oracle/_ref, all host threads) on a bounded crop of the same frame.
+  parity       : the CUDA path on a window of this very frame against the reference on the same window.
 
-`--impl reference` times only that reference arm (rank 0), one bounded crop per step.
-N > 1: the frame is cut into row tiles, one rank per GPU (bcd_b200/tiles.py); see DESIGN.md §multi-GPU.
+`--impl reference` times only that reference arm (rank 0), one bounded crop per step; nothing of the product is mapped
+into that process.
+N > 1 (launched by torchrun, one process per GPU): the frame is cut into row tiles held by a ranked bcd_b200_group; the
+tiles exchange their strips through peer memory (CUDA IPC over NVLink) — bcd_b200/tiles.py: bench_tiled, DESIGN.md 7.
 """
 import argparse
 import json
