@@ -1,23 +1,18 @@
-"""Row-tiled multi-GPU driver of the hot path: one process per GPU, the frame cut into
-horizontal bands, no collective — only neighbour send/recv of small strips between the stages of each pyramid level.
+"""Python side of the row-tiled multi-GPU path.
 
-The stage functions and the strips are the row-tile API of the C ABI (include/bcd_b200.h, `bcd_b200_tile_*`); this
-module only sequences them and moves the strips:
+The driver itself is C++ (bcd_b200/csrc/bcd_b200_multi.cu): one handle and one host thread per tile, strips exchanged
+through peer memory over NVLink, nothing between the stages of a frame on the host. What lives here:
 
-    per level, finest first (its marking chain is the longest, so it starts first):
-        select                                       (independent on every rank: the dominant cost)
-        [m > 0]  on the level's own stream — AS rows: recv from rank-1 -> mark (enqueue) -> send to rank+1
-                 (the raster-order marking is a chain through the ranks; the chains of the levels run side by side
-                 and under the selection of the other levels)
-    per level, level 0 first, then coarsest .. 1:
-        wait for the level's work counters; filter   (independent)
-        accumulator halo: isend/irecv with both neighbours, add           ((b+w) rows x W x 16 B each way)
-        finalize; output rows: isend/irecv (2 rows)
-    per level s-2 .. 0: merge; output rows again
+  * `plan`, `peer_setup / peer_connect / peer_run`, `peer_connect_dist`  — thin ctypes wrappers of bcd_b200_tile_plan /
+    _tile_setup / _tile_connect / _tile_run, and the one-time all_gather of the tiles' 96-byte arena tokens;
+  * `bench_tiled`  — bench.py's N > 1 arm: one process per GPU (torchrun), a ranked bcd_b200_group per process;
+  * the round-1 exchange, kept as the portable fallback and A/B twin (`BCD_B200_EXCHANGE=nccl`): `TileWorker`,
+    `DistExchange`, `run_tile`, `run_tiles_loopback` sequence the per-stage entry points (tile_select, tile_mark, ...)
+    and move the three kinds of strips with torch.distributed send/recv (NCCL on GPUs, gloo in the CPU tests):
 
-`LoopbackExchange` runs all tiles inside one process (tiles processed stage by stage, strips handed over directly);
-it is what the single-GPU parity test uses to check that tiles reproduce the full-frame result.
-`DistExchange` uses torch.distributed point-to-point ops (NCCL on GPUs, gloo in the CPU tests).
+        per level, finest first:      select;  [m > 0] AS rows: recv from rank-1 -> mark -> send to rank+1
+        per level, 0 then s-1 .. 1:   wait for the work counters; filter; accumulator halo swap + add; finalize; output rows
+        per level s-2 .. 0:           merge; output rows again
 """
 import ctypes as C
 
