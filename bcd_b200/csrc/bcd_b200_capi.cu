@@ -492,7 +492,7 @@ int levelFilterOn(bcd_b200_handle* h, int k, const bcd_b200_params& p, cudaStrea
 	// The fallback pixels (mean of the similar patches, DenoisingUnit.cpp:455-481) and the full pixels (two-step filter) are
 	// independent work lists that only meet in the accumulator (atomics): with BCD_B200_FALLBACK_STREAM=1 the fallback
 	// kernel runs on a side stream next to the filter chain instead of in front of it (A/B hook; no gain measured).
-	cudaStream_t fbSt = g_fallbackStream ? L.fbStream : st;
+	cudaStream_t fbSt = (g_fallbackStream && L.fbStream) ? L.fbStream : st;
 	if(fbSt != st)
 	{
 		CU(cudaEventRecord(L.evFbBegin, st)); // everything the level's stream has waited for so far (marking, colour)
@@ -679,7 +679,7 @@ int ensureBuffers(bcd_b200_handle* h, const bcd_b200_params& p)
 			CU(cudaEventCreateWithFlags(&L.evFbBegin, cudaEventDisableTiming));
 		if(!L.evFbDone)
 			CU(cudaEventCreateWithFlags(&L.evFbDone, cudaEventDisableTiming));
-		if(!L.fbStream)
+		if(g_fallbackStream && !L.fbStream) // only with the A/B hook: the default path keeps its set of streams
 			CU(cudaStreamCreateWithFlags(&L.fbStream, cudaStreamNonBlocking));
 	}
 	// filter chunk: bounded scratch (two d x d matrices per slot)
